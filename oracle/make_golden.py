@@ -1,0 +1,118 @@
+"""Generate tests/golden/*.npz by running the REAL reference module.
+
+Runs only in the build container, where /root/reference exists (it does not
+exist on the GPU box, and nothing at test/bench time imports this script).
+The reference is imported unmodified; the only shim is that `Tensor.cuda` is
+neutralised in this CPU-only process because IWT hard-codes `.cuda()`
+(ref models/M2Trans_network.py:223).
+
+    python oracle/make_golden.py            # rewrites tests/golden/
+
+Each fixture stores the inputs, the reference outputs and a checksum of the
+seeded synthetic weights (so a drift of the weight generator is detected
+instead of showing up as a parity failure).
+"""
+from __future__ import annotations
+
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+import yaml
+
+REF = os.environ.get("M2T_REFERENCE", "/root/reference")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, REF)
+
+torch.Tensor.cuda = lambda self, *a, **k: self  # CPU-only process, see docstring
+torch.set_grad_enabled(False)
+
+from models import M2Trans_network as refnet  # noqa: E402  (the reference)
+from m2trans_b200.synthetic import reference_checkpoint, synthetic_input, synthetic_state_dict  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def ref_args(scale: int):
+    cfg = yaml.load(open(f"{REF}/configs/M2Trans_x{scale}_test.yml"), Loader=yaml.FullLoader)
+    return types.SimpleNamespace(**cfg)
+
+
+def weight_checksum(sd) -> np.ndarray:
+    s = sum(float(v.double().sum()) for v in sd.values())
+    a = sum(float(v.double().abs().sum()) for v in sd.values())
+    return np.array([s, a], dtype=np.float64)
+
+
+def full_forward_case(name, scale, seed, shape, qkv_gain=1.0, kind="uniform"):
+    ckpt = reference_checkpoint(scale, seed, qkv_gain=qkv_gain)
+    model = torch.nn.DataParallel(refnet.M2Trans(ref_args(scale)))
+    model.load_state_dict(ckpt["model_state_dict"], strict=True)   # as ref test.py:70
+    model.eval()
+    x = synthetic_input(*shape, seed=33 + seed, kind=kind)
+    y = model.module(x)
+    sd = synthetic_state_dict(scale, seed, qkv_gain=qkv_gain)
+    np.savez(os.path.join(OUT, name + ".npz"), x=x.numpy(), y=y.contiguous().numpy(),
+             scale=np.int64(scale), seed=np.int64(seed), qkv_gain=np.float64(qkv_gain),
+             wsum=weight_checksum(sd))
+    print(name, tuple(x.shape), "->", tuple(y.shape), "min/max", float(y.min()), float(y.max()),
+          "clamped0", float((y == 0).float().mean()))
+
+
+def unit_cases():
+    g = torch.Generator().manual_seed(7)
+    out = {}
+    # DWT / IWT (ref :198-237)
+    u = torch.randn(2, 3, 8, 12, generator=g)
+    out["dwt_in"], out["dwt_out"] = u.numpy(), refnet.DWT()(u).numpy()
+    v = torch.randn(2, 8, 4, 6, generator=g)
+    out["iwt_in"], out["iwt_out"] = v.numpy(), refnet.IWT()(v).numpy()
+    # TBlock (ref :267-340) for the three channel counts used by CFTM
+    for ch, hw in ((16, (16, 24)), (64, (8, 16)), (256, (8, 8))):
+        torch.manual_seed(100 + ch)
+        blk = refnet.TBlock(ch, block_size=8, halo_size=1, num_heads=1, bias=False).eval()
+        z = torch.randn(1, ch, *hw, generator=g)
+        out[f"tb{ch}_in"] = z.numpy()
+        out[f"tb{ch}_wqkv"] = blk.qkv_conv.weight.detach().numpy()
+        out[f"tb{ch}_relh"] = blk.rel_h.detach().numpy()
+        out[f"tb{ch}_relw"] = blk.rel_w.detach().numpy()
+        out[f"tb{ch}_out"] = blk(z).numpy()
+    # one CFTM (ref :114-164) with seeded synthetic weights (body.0 of x2 seed 5)
+    sd = synthetic_state_dict(2, 5, n_blocks=1)
+    blk = refnet.CFTM(nf=64, block_size=8, halo_size=1, norm=True).eval()
+    blk.load_state_dict({k[len("body.0."):]: v for k, v in sd.items() if k.startswith("body.0.")}, strict=True)
+    xin = torch.randn(1, 64, 32, 32, generator=g) * 0.7 + 0.2
+    out["cftm_in"], out["cftm_out"] = xin.numpy(), blk(xin).numpy()
+    out["cftm_wsum"] = weight_checksum(sd)
+    np.savez(os.path.join(OUT, "units.npz"), **out)
+    print("units", {k: v.shape for k, v in out.items()})
+
+
+def state_dict_manifest():
+    """Key/shape manifest of the reference state dict for x2/x3/x4 (drop-in contract)."""
+    lines = []
+    for s in (2, 3, 4):
+        m = refnet.M2Trans(ref_args(s))
+        for k, v in m.state_dict().items():
+            lines.append(f"x{s} {k} {'x'.join(map(str, v.shape))} {str(v.dtype).replace('torch.', '')}")
+    with open(os.path.join(OUT, "state_dict_manifest.txt"), "w") as f:
+        f.write("\n".join(lines) + "\n")
+    print("manifest", len(lines), "entries")
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    torch.manual_seed(0)
+    state_dict_manifest()
+    unit_cases()
+    full_forward_case("fwd_x2_64x64", 2, 0, (1, 64, 64))                    # BASELINE configs[0]
+    full_forward_case("fwd_x3_40x50", 3, 1, (1, 40, 50))                    # ragged: pads to 64x64
+    full_forward_case("fwd_x4_24x40", 4, 2, (1, 24, 40))                    # ragged: pads to 32x64
+    # sharp-softmax stress.  qkv_gain 1.5 is the largest well-posed setting: at random init the
+    # network turns chaotic for gain >= 2 (fp32 vs fp64 of the SAME code differ by 3e-4 at 2.0 and
+    # by 1.0 at 3.0 on the [0,1] output), so a parity bar there measures nothing.
+    full_forward_case("fwd_x4_32x32_sharp", 4, 3, (1, 32, 32), qkv_gain=1.5)
+    full_forward_case("fwd_x4_b2_32x32_speckle", 4, 0, (2, 32, 32), kind="speckle")
