@@ -1,0 +1,294 @@
+#!/usr/bin/env python
+"""bench.py -- x4 SR output megapixels/s of the M2Trans forward on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2]
+
+One "step" = one forward of the hot path over one batch of synthetic LR frames.  The default
+workload is BASELINE.json configs[1]: M2Trans x4, model_x4 (seeded synthetic checkpoint in the
+reference's format; the released file is not available offline), batch 16 of 3x128x128.
+
+Printed JSON line (rank 0):
+  value      whole-job output MP/s with inputs resident in HBM (CUDA events, max over ranks)
+  e2e        same metric through the public nn.Module call with HOST buffers: pinned H2D of the LR
+             batch + forward + D2H of the SR batch inside the timed region
+  roofline   the dominant kernel (CFTM 3x3 feed-forward conv) timed alone with CUDA events, against
+             MEASURED_PEAKS.json; roofline_forward = whole forward vs. the sustained tensor peak
+  cpu_baseline  the CPU oracle (a torch fp32 port of the reference forward) on the host cores
+Multi-GPU: images are independent, so every rank runs the same per-GPU batch (weak scaling) with no
+collective on the data path; torch.distributed (NCCL) is used only for the barrier and the max-reduce
+of the timings.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+import types
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (scale, batch, H, W)   -- BASELINE.json configs[0..3]
+    "cfg1": (2, 1, 64, 64),
+    "cfg2": (4, 16, 128, 128),
+    "cfg3": (3, 32, 200, 266),
+    "cfg4": (4, 64, 270, 480),
+}
+FLOP_PER_PX = {2: 1299328, 3: 1357568, 4: 1471872}     # algorithmic FLOPs per padded LR px
+FFCONV_FLOP_PER_PX = 2 * 64 * 64 * 9                    # 73 728
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"hbm_gbs": p["hbm_gbs"], "tflops_burst": p["bf16_tflops"], "tflops_sustained": p["bf16_tflops_sustained"],
+                "source": "measured"}
+    return {"hbm_gbs": 6650.0, "tflops_burst": 1590.0, "tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def model_args(scale):
+    return types.SimpleNamespace(scale=scale, rgb_range=1.0, colors=3, n_feats=64, num_heads=4, n_blocks=8)
+
+
+def cpu_reference_pass(scale, x, threads):
+    """The CPU leg: oracle.forward (torch fp32 port of ref M2Trans_network.py:58-76) on the host cores."""
+    import torch
+    from oracle import m2trans_oracle as O
+    from m2trans_b200.synthetic import synthetic_state_dict
+    torch.set_num_threads(threads)
+    sd = synthetic_state_dict(scale, 0)
+    with torch.no_grad():
+        O.forward(sd, x[:1])                                   # warm-up (allocator, threads)
+        t0 = time.perf_counter()
+        y = O.forward(sd, x)
+        dt = time.perf_counter() - t0
+    return dt, y
+
+
+def run_reference(args):
+    """--impl reference: the reference's own algorithm on the box's host cores (oracle port; the
+    reference is Python and /root/reference does not exist on the GPU box).  Rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from m2trans_b200.synthetic import synthetic_input
+    scale, B, H, W = WORKLOADS[args.workload]
+    threads = os.cpu_count() or 1
+    # bounded sample: a slice of the batch such that steps+warmup passes finish in a few minutes
+    per_img = 0.4 * (H * W) / (128 * 128)
+    budget = 150.0 / max(1, args.steps + args.warmup)
+    nimg = max(1, min(B, int(budget / per_img)))
+    x = synthetic_input(B, H, W, seed=33)[:nimg]
+    times = []
+    for i in range(args.warmup + args.steps):
+        dt, _ = cpu_reference_pass(scale, x, threads)
+        if i >= args.warmup:
+            times.append(dt)
+    ms = 1e3 * sum(times) / len(times)
+    mp = nimg * 3 * 0 + nimg * (H * scale) * (W * scale) / 1e6
+    val = mp / (ms / 1e3)
+    sample = f"{nimg} of {B} frames of {args.workload} per step, torch fp32, {threads} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": "x4 SR output megapixels/sec" if scale == 4 else f"x{scale} SR output megapixels/sec",
+        "value": val, "unit": "MP/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": {"workload": f"{args.workload}: M2Trans x{scale}, {B}x3x{H}x{W} LR, synthetic model_x{scale} checkpoint seed 0"},
+        "cpu_baseline": {"value": val, "unit": "MP/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from m2trans_b200 import _lib
+    from m2trans_b200.M2Trans_network import M2Trans
+    from m2trans_b200.synthetic import reference_checkpoint, synthetic_input
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the engine has no CPU path (use --impl reference for the CPU leg)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    scale, B, H, W = WORKLOADS[args.workload]
+    lib = _lib.load()
+
+    model = torch.nn.DataParallel(M2Trans(model_args(scale)), device_ids=[local]).to(dev)
+    model.load_state_dict(reference_checkpoint(scale, 0)["model_state_dict"], strict=True)
+    model.eval()
+    net = model.module
+
+    # Weak scaling: every rank owns its own batch of B frames (different seeds), no exchange.
+    n_rot = 3
+    xs_host = [synthetic_input(B, H, W, seed=33 + 17 * rank + i).pin_memory() for i in range(n_rot)]
+    xs_dev = [x.to(dev) for x in xs_host]
+    flush = torch.empty(192 * 1024 * 1024, dtype=torch.float32, device=dev)     # 768 MB > 126 MB L2
+    out_mp = B * (H * scale) * (W * scale) / 1e6
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing --------------------------------------------------------------------
+    for i in range(args.warmup):
+        net(xs_dev[i % n_rot])
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    t_wall0 = time.perf_counter()
+    for i in range(args.steps):
+        flush.zero_()                                   # evict L2 between timed iterations (not timed)
+        ev[i][0].record()
+        y = net(xs_dev[i % n_rot])
+        ev[i][1].record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    ms = sum(step_ms) / len(step_ms)
+    launches = net.last_launches * args.steps
+
+    # ---- end to end through the public call with host buffers -----------------------------------------
+    y_host = torch.empty((B, 3, H * scale, W * scale), dtype=torch.float32).pin_memory()
+    def e2e_step(i):
+        xd = xs_host[i % n_rot].to(dev, non_blocking=True)
+        yd = model(xd)                                  # the call a user of the reference makes (ref test.py:90)
+        y_host.copy_(yd, non_blocking=True)
+    for i in range(2):
+        e2e_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        e2e_step(i)
+    torch.cuda.synchronize()
+    e2e_ms = 1e3 * (time.perf_counter() - t0) / args.steps
+    clocks = sampler.stop()
+
+    # ---- dominant kernel alone: CFTM feed-forward 3x3 conv --------------------------
+    hp, wp = (H + 31) // 32 * 32, (W + 31) // 32 * 32
+    P = B * hp * wp
+    pk = peaks()
+    Y = torch.randn(B, hp, wp, 64, device=dev).half()
+    Xin = torch.randn(B, hp, wp, 64, device=dev)
+    Xout = torch.empty_like(Xin)
+    ffw = torch.randn(9, 64, 64, device=dev).half() * 0.05
+    ffb = torch.randn(64, device=dev)
+    stats = torch.zeros(B, 64, 2, dtype=torch.float64, device=dev)
+    st = torch.cuda.current_stream(dev).cuda_stream
+    kms = []
+    for i in range(3 + 10):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        _lib.check(lib.m2t_stage_ffconv(0, Y.data_ptr(), ffw.data_ptr(), ffb.data_ptr(), Xin.data_ptr(), Xout.data_ptr(),
+                                        stats.data_ptr(), B, hp, wp, st), "m2t_stage_ffconv")
+        b.record()
+        torch.cuda.synchronize()
+        if i >= 3:
+            kms.append(a.elapsed_time(b))
+    k_ms = sum(kms) / len(kms)
+    k_tflops = FFCONV_FLOP_PER_PX * P / (k_ms * 1e-3) / 1e12
+    fwd_tflops = FLOP_PER_PX[scale] * P / (ms * 1e-3) / 1e12
+
+    # ---- max over ranks ------------------------------------------------------------------------------------
+    if world > 1:
+        t = torch.tensor([ms, e2e_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_ms = t.tolist()
+
+    if rank == 0:
+        line = {
+            "metric": "x4 SR output megapixels/sec" if scale == 4 else f"x{scale} SR output megapixels/sec",
+            "value": world * out_mp / (ms * 1e-3), "unit": "MP/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f16 operands, f32 accumulate/stream", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: M2Trans x{scale}, {B}x3x{H}x{W} LR per GPU, synthetic model_x{scale} checkpoint seed 0",
+                       "l2": "768 MB buffer rewritten between timed iterations; 3 rotating input batches",
+                       "sharding": "images; no collective on the data path"},
+            "clocks": clocks,
+            "e2e": {"value": world * out_mp / (e2e_ms * 1e-3), "unit": "MP/s", "h2d_bytes_per_step": B * 3 * H * W * 4,
+                    "d2h_bytes_per_step": B * 3 * H * scale * W * scale * 4, "ms_per_step": e2e_ms},
+            "gpu_launches": launches,
+            "roofline": {"kernel": "ffconv (CFTM 3x3 feed-forward conv + residual + norm stats)", "bound": "tensor",
+                         "achieved": k_tflops, "peak": pk["tflops_burst"], "unit": "TFLOP/s", "frac": k_tflops / pk["tflops_burst"],
+                         "traffic": None, "peak_source": pk["source"], "ms_per_launch": k_ms},
+            "roofline_forward": {"bound": "tensor", "achieved": fwd_tflops, "peak": pk["tflops_sustained"], "unit": "TFLOP/s",
+                                 "frac": fwd_tflops / pk["tflops_sustained"], "peak_source": pk["source"]},
+            "wall_s_timed_region": t_wall,
+        }
+        if world == 1 and not args.no_cpu:
+            threads = os.cpu_count() or 1
+            nimg = min(B, 16)
+            dt, yref = cpu_reference_pass(scale, xs_host[0][:nimg], threads)
+            from oracle import m2trans_oracle as O
+            yo = net(xs_dev[0])[:nimg].cpu()
+            line["cpu_baseline"] = {"value": nimg * (H * scale) * (W * scale) / 1e6 / dt, "unit": "MP/s", "cores": threads,
+                                    "kind": "port", "sample": f"{nimg} frames of {args.workload}, one pass after a 1-frame warm-up, torch fp32"}
+            line["parity"] = {"psnr_db": O.psnr(yo, yref), "max_abs": O.max_abs(yo, yref), "frames": nimg}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

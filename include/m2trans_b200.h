@@ -1,0 +1,169 @@
+/*
+ * m2trans_b200 -- C ABI of the B200 (sm_100a) engine for the M2Trans forward path.
+ *
+ * The reference (eezkni/M2Trans) is pure Python: its "operator interface" for this
+ * path is the nn.Module `M2Trans` of models/M2Trans_network.py, reached through the
+ * plugin hook `utils.import_module('models.{}_network').create_model(args)`
+ * (ref train.py:69-70, utils.py:175-176) or directly (ref test.py:66,90).  There is
+ * no FFI in the reference; this header is the boundary a binding would sit on
+ * (INTEGRATION.md shows the ctypes stub).  Every entry point cites the reference
+ * code it replaces.
+ *
+ * Conventions
+ *   - plain C types only; pointers named d_* are DEVICE pointers on the current
+ *     CUDA device; `stream` is a cudaStream_t passed as void* (NULL = legacy stream)
+ *   - every int function returns 0 (M2T_OK) or a negative M2T_E* code; the message
+ *     of the last failure on the calling thread is m2t_last_error()
+ *   - nothing here synchronises the device, allocates device memory, or falls back
+ *     to the CPU; a device that is not sm_100 is M2T_E_DEVICE
+ *   - re-entrant: a plan is immutable after creation; concurrent m2t_forward calls
+ *     are allowed when they use different workspaces
+ *
+ * Internal tensor layout: NHWC; residual stream fp32; branch tensors
+ * and GEMM operands fp16 with fp32 accumulation; weights pre-packed by
+ * m2t_pack_weights.
+ */
+#ifndef M2TRANS_B200_H
+#define M2TRANS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define M2T_OK             0
+#define M2T_E_ARG         -1  /* bad argument (null pointer, bad shape)                  */
+#define M2T_E_DEVICE      -2  /* no CUDA device, or the device is not sm_100             */
+#define M2T_E_CUDA        -3  /* a CUDA runtime/driver call or a kernel launch failed    */
+#define M2T_E_UNSUPPORTED -4  /* configuration outside what the reference constructs     */
+
+/* kernel-variant bits for m2t_cfg.variant (0 = the default product path).  The SIMT
+ * variants are CUDA-core kernels with the same operand precision; they exist as an
+ * on-device cross-check for the tcgen05 kernels, not as a fallback: nothing selects
+ * them automatically. */
+#define M2T_VAR_DEFAULT   0u
+#define M2T_VAR_SIMT_CONV (1u << 0)  /* ff 3x3 conv on CUDA cores instead of tcgen05   */
+#define M2T_VAR_SIMT_QKV  (1u << 1)  /* qkv 1x1 conv on CUDA cores instead of tcgen05  */
+#define M2T_VAR_SIMT_TAIL (1u << 2)  /* tail on CUDA cores instead of tcgen05          */
+#define M2T_VAR_SIMT_ATTN (1u << 3)  /* attention on CUDA cores instead of tcgen05     */
+#define M2T_VAR_SIMT_ALL  0xFu
+
+typedef struct m2t_plan m2t_plan;
+
+/* The hyper-parameters M2Trans.__init__ reads (ref M2Trans_network.py:21-25,34) plus
+ * the input geometry of one forward call (ref :60). */
+typedef struct m2t_cfg {
+    int32_t  scale;      /* args.scale: 2, 3 or 4                                    */
+    int32_t  n_feats;    /* args.n_feats: must be 64 (ref configs/M2Trans_x*.yml)    */
+    int32_t  n_blocks;   /* args.n_blocks: number of CFTM blocks, 1..64 (ref: 8)     */
+    int32_t  colors;     /* args.colors: must be 3                                   */
+    int32_t  batch;      /* B >= 1                                                   */
+    int32_t  height;     /* LR H; reflect padding to a multiple of 32 must be defined */
+    int32_t  width;      /* LR W                                                     */
+    uint32_t variant;    /* M2T_VAR_* bits                                           */
+    float    rgb_range;  /* args.rgb_range: upper clamp (ref :74)                    */
+} m2t_cfg;
+
+/* ---- device / library ------------------------------------------------------------ */
+int         m2t_query_device(int* sm_major, int* sm_minor, int* sm_count);
+const char* m2t_last_error(void);
+const char* m2t_version(void);
+
+/* ---- weights ----------------------------------------------------------------------
+ * Replaces nn.Module parameter storage + load_state_dict (ref :88-112, test.py:70).
+ * `d_params` is a HOST array of n_params DEVICE pointers to the fp32 tensors of
+ * M2Trans.state_dict() in registration order (123 tensors for
+ * x4, 121 for x2/x3).  sub_mean/add_mean (entries 0..3) are accepted and ignored
+ * because the reference never calls them in forward (ref :58-76).  `d_packed`
+ * (m2t_packed_weight_bytes, 256-byte aligned) receives the engine's packed copy. */
+int    m2t_num_params(int scale, int n_blocks);
+size_t m2t_packed_weight_bytes(int scale, int n_blocks);
+int    m2t_pack_weights(int scale, int n_blocks, const float* const* d_params, int n_params,
+                        void* d_packed, void* stream);
+/* byte offset of a packed tensor, for tests: name is e.g. "head_w", "head_b",
+ * "body.3.attn2.wqkv", "body.3.attn2.relf", "body.3.attn2.relx", "body.3.ffw", "body.3.ffb",
+ * "t0w", "t0b", "t3w", "t3b", "tcw".  Returns (size_t)-1 for an unknown name. */
+size_t m2t_packed_offset(int scale, int n_blocks, const char* name);
+
+/* ---- plan ------------------------------------------------------------------------- */
+int    m2t_plan_create(const m2t_cfg* cfg, m2t_plan** out);
+void   m2t_plan_destroy(m2t_plan* plan);
+size_t m2t_workspace_bytes(const m2t_plan* plan);
+/* padded frame size (multiples of 32, ref :78-86) */
+int    m2t_plan_padded(const m2t_plan* plan, int* Hp, int* Wp);
+/* kernel launches one m2t_forward issues (bench.py's gpu_launches) */
+int    m2t_plan_num_launches(const m2t_plan* plan);
+/* byte offset of an internal NHWC tensor inside the workspace, for tests:
+ * "res" (head output, fp32 [B,Hp,Wp,64]), "x" (residual stream after the last CFTM,
+ * fp32), "y" (cat[y1..y4] of the last CFTM, fp16).  (size_t)-1 for an unknown name. */
+size_t m2t_workspace_offset(const m2t_plan* plan, const char* name);
+
+/* ---- the hot path -------------------------------------------------------------------
+ * Replaces M2Trans.forward (ref :58-76): check_image_size reflect pad (:78-86), head
+ * conv (:34,:63), n_blocks x CFTM (:132-164: InstanceNorm :135, four chained TBlocks
+ * :290-340 over Haar DWT/IWT pyramids :198-237, 3x3 feed_forward + residual :164),
+ * global residual (:70), tail (:40-56), clamp (:74) and crop (:76).
+ *   d_x  [B,3,H,W]      fp32 NCHW contiguous, values in [0, rgb_range]
+ *   d_y  [B,3,H*s,W*s]  fp32 NCHW contiguous
+ *   d_workspace         m2t_workspace_bytes(plan) bytes, 256-byte aligned          */
+int m2t_forward(const m2t_plan* plan, const void* d_packed, const float* d_x, float* d_y,
+                void* d_workspace, void* stream);
+
+/* ---- per-stage entry points (unit tests, ncu) ------------------------------------------
+ * The same kernels m2t_forward launches, on the engine's native NHWC tensors.
+ * Geometry: B images of Hp x Wp padded LR pixels (multiples of 32). */
+
+/* head: reflect pad + 3->64 conv + bias (ref :34,:63,:78-86); also accumulates the
+ * InstanceNorm sums of the first CFTM.  d_stats: double [B][64][2], zeroed by caller. */
+int m2t_stage_head(const float* d_x, const float* d_head_w, const float* d_head_b, float* d_res,
+                   double* d_stats, int B, int H, int W, void* stream);
+/* (sum, sumsq) -> (mean, rstd): nn.InstanceNorm2d statistics (ref :127,:135) */
+int m2t_stage_stats_finalize(const double* d_stats, float* d_munorm /* float2 [B][64] */, int B,
+                             int npix, void* stream);
+/* branch glue (ref :135-161): prep writes Z = DWT^L((n_k + y_{k-1})/2) as fp16
+ * [B,Hp>>L,Wp>>L,16*4^L]; post writes y_k = IWT^L(O) + t_k into channels 16k.. of Y. */
+int m2t_stage_branch_prep(int branch, const float* d_X, const float* d_munorm, const void* d_Y,
+                          void* d_Z, int B, int Hp, int Wp, void* stream);
+int m2t_stage_branch_post(int branch, const void* d_O, const float* d_X, const float* d_munorm,
+                          void* d_Y, int B, int Hp, int Wp, void* stream);
+/* TBlock qkv 1x1 conv (ref :307): QKV[m][3C] = Z[m][C] . Wqkv^T, fp16 */
+int m2t_stage_qkv(uint32_t variant, const void* d_Z, const void* d_wqkv, void* d_QKV, int M, int C,
+                  void* stream);
+/* TBlock attention core (ref :310-332) on QKV [B,h,w,3C] -> O [B,h,w,C], fp16 */
+int m2t_stage_attn(uint32_t variant, int C, const void* d_QKV, const float* d_relf,
+                   const void* d_relx, void* d_O, int B, int h, int w, void* stream);
+/* CFTM.feed_forward + residual (ref :124-126,:164) + next block's InstanceNorm sums */
+int m2t_stage_ffconv(uint32_t variant, const void* d_Y, const void* d_ffw, const float* d_ffb,
+                     const float* d_Xin, float* d_Xout, double* d_stats, int B, int Hp, int Wp,
+                     void* stream);
+/* tail (ref :40-56,:70-76) on B images whose NHWC streams start at d_X / d_res, written to
+ * output images b0.. of d_y [*,3,H*s,W*s]; d_scratch holds m2t_tail_scratch_bytes(scale, B, Hp, Wp)
+ * bytes; d_packed is the blob of m2t_pack_weights(scale, n_blocks, ...). */
+size_t m2t_tail_scratch_bytes(int scale, int B, int Hp, int Wp);
+int m2t_stage_tail(uint32_t variant, int scale, int n_blocks, const void* d_packed, const float* d_X,
+                   const float* d_res, float* d_y, int B, int b0, int H, int W, float rgb_range,
+                   void* d_scratch, void* stream);
+
+/* ---- hardware probes (development aids; tests/test_probes.py) ---------------------------
+ * m2t_probe_umma: copies two raw shared-memory images (A, B operands), issues k_steps
+ * tcgen05.mma (kind::f16, cta_group::1, M=128) with the given 64-bit shared-memory
+ * descriptors (the 14-bit start-address field is added to the image base; each k step
+ * adds a_step/b_step to the descriptor's low word) and instruction descriptor, and
+ * dumps the fp32 accumulator [128 lanes][n_cols]. */
+int m2t_probe_umma(const void* d_a_image, uint32_t a_bytes, const void* d_b_image, uint32_t b_bytes,
+                   uint64_t a_desc, uint64_t b_desc, uint32_t a_step, uint32_t b_step, int k_steps,
+                   uint32_t idesc, int n_cols, float* d_out, void* stream);
+/* m2t_probe_tma: builds a tiled tensor map over d_tensor (dims / strides_bytes / box given
+ * innermost first, HOST arrays of `rank` entries; swizzle 0 none, 1 32B, 2 64B, 3 128B), loads
+ * one box at `coords` (may be negative / out of bounds: zero fill) into 1024-byte-aligned
+ * shared memory and copies the raw shared-memory image (out_bytes = box bytes) to d_out. */
+int m2t_probe_tma(const void* d_tensor, int elem_bytes, int rank, const uint64_t* dims,
+                  const uint64_t* strides_bytes, const uint32_t* box, int swizzle,
+                  const int32_t* coords, void* d_out, uint32_t out_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* M2TRANS_B200_H */

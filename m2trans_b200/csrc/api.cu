@@ -1,0 +1,365 @@
+// C ABI (include/m2trans_b200.h): plan, weight packing, the forward orchestration and the per-stage
+// entry points.  The forward is a fixed sequence of kernel launches on the caller's stream; it never
+// synchronises, allocates or touches host memory, so the Python side can capture it in a CUDA graph.
+#include <stdarg.h>
+
+#include <new>
+
+#include "common.cuh"
+
+namespace m2t {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+    set_error("CUDA error %d (%s) at %s [%s:%d]", (int)e, cudaGetErrorString(e), what, file, line);
+    return M2T_E_CUDA;
+}
+
+int device_sm_count() {
+    static int cached[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cached[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+
+static int check_device() {
+    int dev = 0, major = 0, minor = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) { set_error("no CUDA device: %s", cudaGetErrorString(e)); return M2T_E_DEVICE; }
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+    if (major != 10) {
+        set_error("device %d is sm_%d%d; this library contains sm_100a code only (no fallback)", dev, major, minor);
+        return M2T_E_DEVICE;
+    }
+    return M2T_OK;
+}
+
+}  // namespace m2t
+
+using namespace m2t;
+
+struct m2t_plan {
+    m2t_cfg cfg;
+    Geom g;
+    PackedLayout L;
+    int tail_chunk;            // images per tail pass
+    // workspace byte offsets
+    size_t o_res, o_x, o_y, o_z, o_qkv, o_o, o_stats, o_munorm, o_t1, o_t2, ws_bytes;
+    int n_launches;
+};
+
+static inline int tail_r0(int scale) { return scale == 4 ? 2 : scale; }
+
+extern "C" {
+
+const char* m2t_last_error(void) { return g_err; }
+const char* m2t_version(void) { return "m2trans_b200 0.1 (sm_100a)"; }
+
+int m2t_query_device(int* sm_major, int* sm_minor, int* sm_count) {
+    int dev = 0;
+    M2T_CUDA(cudaGetDevice(&dev));
+    int v = 0;
+    if (sm_major) { M2T_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMajor, dev)); *sm_major = v; }
+    if (sm_minor) { M2T_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMinor, dev)); *sm_minor = v; }
+    if (sm_count) { M2T_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev)); *sm_count = v; }
+    return M2T_OK;
+}
+
+int m2t_num_params(int scale, int n_blocks) { return 6 + 14 * n_blocks + (scale == 4 ? 5 : 3); }
+
+size_t m2t_packed_weight_bytes(int scale, int n_blocks) {
+    PackedLayout L;
+    if (make_packed_layout(scale, n_blocks, &L) != M2T_OK) return 0;
+    return L.total;
+}
+
+size_t m2t_packed_offset(int scale, int n_blocks, const char* name) {
+    PackedLayout L;
+    if (!name || make_packed_layout(scale, n_blocks, &L) != M2T_OK) return (size_t)-1;
+    if (!strcmp(name, "head_w")) return L.head_w;
+    if (!strcmp(name, "head_b")) return L.head_b;
+    if (!strcmp(name, "t0w")) return L.t0w;
+    if (!strcmp(name, "t0b")) return L.t0b;
+    if (!strcmp(name, "tcw")) return L.tcw;
+    if (scale == 4 && !strcmp(name, "t3w")) return L.t3w;
+    if (scale == 4 && !strcmp(name, "t3b")) return L.t3b;
+    int i = -1, a = -1;
+    char what[32];
+    if (sscanf(name, "body.%d.attn%d.%31s", &i, &a, what) == 3 && i >= 0 && i < n_blocks && a >= 1 && a <= 4) {
+        const AttnW& A = L.blk[i].attn[a - 1];
+        if (!strcmp(what, "wqkv")) return A.wqkv;
+        if (!strcmp(what, "relf")) return A.relf;
+        if (!strcmp(what, "relx")) return A.relx;
+        return (size_t)-1;
+    }
+    if (sscanf(name, "body.%d.%31s", &i, what) == 2 && i >= 0 && i < n_blocks) {
+        if (!strcmp(what, "ffw")) return L.blk[i].ffw;
+        if (!strcmp(what, "ffb")) return L.blk[i].ffb;
+    }
+    return (size_t)-1;
+}
+
+int m2t_pack_weights(int scale, int n_blocks, const float* const* d_params, int n_params, void* d_packed,
+                     void* stream) {
+    if (!d_params || !d_packed) { set_error("pack_weights: null pointer"); return M2T_E_ARG; }
+    M2T_TRY(check_device());
+    PackedLayout L;
+    M2T_TRY(make_packed_layout(scale, n_blocks, &L));
+    return pack_weights_impl(L, d_params, n_params, static_cast<uint8_t*>(d_packed), (cudaStream_t)stream);
+}
+
+size_t m2t_tail_scratch_bytes(int scale, int B, int Hp, int Wp) {
+    const int r0 = tail_r0(scale);
+    size_t t1 = (size_t)B * Hp * r0 * Wp * r0 * NF * 2;
+    size_t t2 = scale == 4 ? (size_t)B * Hp * 4 * Wp * 4 * NF * 2 : 0;
+    return align_up(t1, 256) + align_up(t2, 256);
+}
+
+int m2t_plan_create(const m2t_cfg* cfg, m2t_plan** out) {
+    if (!cfg || !out) { set_error("plan_create: null pointer"); return M2T_E_ARG; }
+    *out = nullptr;
+    if (cfg->n_feats != NF) { set_error("n_feats %d: the engine is built for 64", cfg->n_feats); return M2T_E_UNSUPPORTED; }
+    if (cfg->colors != 3) { set_error("colors %d: the engine is built for 3", cfg->colors); return M2T_E_UNSUPPORTED; }
+    if (cfg->batch < 1 || cfg->height < 1 || cfg->width < 1) { set_error("bad input shape"); return M2T_E_ARG; }
+    m2t_plan* p = new (std::nothrow) m2t_plan();
+    if (!p) { set_error("out of host memory"); return M2T_E_ARG; }
+    p->cfg = *cfg;
+    int rc = make_packed_layout(cfg->scale, cfg->n_blocks, &p->L);
+    if (rc != M2T_OK) { delete p; return rc; }
+    Geom& g = p->g;
+    g.B = cfg->batch; g.H = cfg->height; g.W = cfg->width; g.scale = cfg->scale;
+    g.Hp = (g.H + 31) / 32 * 32; g.Wp = (g.W + 31) / 32 * 32;
+    // F.pad(mode='reflect') requires pad < dim (ref :85 raises otherwise)
+    if (g.Hp - g.H >= g.H || g.Wp - g.W >= g.W) {
+        set_error("reflect padding %dx%d -> %dx%d needs pad < size (the reference raises here too)", g.H, g.W, g.Hp, g.Wp);
+        delete p;
+        return M2T_E_UNSUPPORTED;
+    }
+    const size_t P = (size_t)g.B * g.Hp * g.Wp;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    p->o_res = take(P * NF * 4);
+    p->o_x = take(P * NF * 4);
+    p->o_y = take(P * NF * 2);
+    p->o_z = take(P * NB * 2);
+    p->o_qkv = take(P * NB * 3 * 2);
+    p->o_o = take(P * NB * 2);
+    p->o_stats = take((size_t)(cfg->n_blocks + 1) * g.B * NF * 2 * sizeof(double));
+    p->o_munorm = take((size_t)g.B * NF * sizeof(float2));
+    // tail scratch: process images in chunks of at most ~2 GiB of intermediates
+    const size_t per_img = m2t_tail_scratch_bytes(cfg->scale, 1, g.Hp, g.Wp);
+    int chunk = (int)(((size_t)2 << 30) / per_img);
+    if (chunk < 1) chunk = 1;
+    if (chunk > g.B) chunk = g.B;
+    p->tail_chunk = chunk;
+    const int r0 = tail_r0(cfg->scale);
+    p->o_t1 = take((size_t)chunk * g.Hp * r0 * g.Wp * r0 * NF * 2);
+    p->o_t2 = cfg->scale == 4 ? take((size_t)chunk * g.Hp * 4 * g.Wp * 4 * NF * 2) : p->o_t1;
+    p->ws_bytes = off;
+    const int tail_passes = (g.B + chunk - 1) / chunk;
+    p->n_launches = 1 /*head*/ + cfg->n_blocks * (1 + 4 * 4 + 1) + tail_passes * (cfg->scale == 4 ? 3 : 2);
+    *out = p;
+    return M2T_OK;
+}
+
+void m2t_plan_destroy(m2t_plan* plan) { delete plan; }
+size_t m2t_workspace_bytes(const m2t_plan* plan) { return plan ? plan->ws_bytes : 0; }
+int m2t_plan_num_launches(const m2t_plan* plan) { return plan ? plan->n_launches : 0; }
+int m2t_plan_padded(const m2t_plan* plan, int* Hp, int* Wp) {
+    if (!plan) { set_error("null plan"); return M2T_E_ARG; }
+    if (Hp) *Hp = plan->g.Hp;
+    if (Wp) *Wp = plan->g.Wp;
+    return M2T_OK;
+}
+size_t m2t_workspace_offset(const m2t_plan* plan, const char* name) {
+    if (!plan || !name) return (size_t)-1;
+    if (!strcmp(name, "res")) return plan->o_res;
+    if (!strcmp(name, "x")) return plan->o_x;
+    if (!strcmp(name, "y")) return plan->o_y;
+    return (size_t)-1;
+}
+
+// ---- stage dispatch ------------------------------------------------------------------------------
+static int run_qkv(uint32_t variant, const __half* Z, const __half* wqkv, __half* QKV, int M, int C, cudaStream_t s) {
+    (void)variant;
+    return launch_gemm_simt(Z, wqkv, QKV, M, 3 * C, C, s);
+}
+static int run_attn(uint32_t variant, int C, const __half* QKV, const float* relf, const __half* relx, __half* O,
+                    int B, int h, int w, cudaStream_t s) {
+    (void)variant; (void)relx;
+    return launch_attn_simt(C, QKV, relf, O, B, h, w, s);
+}
+static int run_ffconv(uint32_t variant, const __half* Y, const __half* ffw, const float* ffb, const float* Xin,
+                      float* Xout, double* stats, const Geom& g, cudaStream_t s) {
+    (void)variant;
+    return launch_ffconv_simt(Y, ffw, ffb, Xin, Xout, stats, g, s);
+}
+static int run_tail(uint32_t variant, int scale, const PackedLayout& L, const uint8_t* W, const float* X,
+                    const float* res, float* y, int B, int b0, const Geom& g, float rgb_range, uint8_t* scratch,
+                    cudaStream_t s) {
+    (void)variant;
+    const int r0 = tail_r0(scale);
+    __half* T1 = reinterpret_cast<__half*>(scratch);
+    const size_t t1_bytes = align_up((size_t)B * g.Hp * r0 * g.Wp * r0 * NF * 2, 256);
+    __half* T2 = reinterpret_cast<__half*>(scratch + t1_bytes);
+    const int hout = g.H * scale, wout = g.W * scale;
+    M2T_TRY(launch_tail_up_simt(X, res, nullptr, reinterpret_cast<const __half*>(W + L.t0w),
+                                reinterpret_cast<const float*>(W + L.t0b), T1, B, g.Hp, g.Wp, r0, s));
+    if (scale == 4) {
+        M2T_TRY(launch_tail_up_simt(nullptr, nullptr, T1, reinterpret_cast<const __half*>(W + L.t3w),
+                                    reinterpret_cast<const float*>(W + L.t3b), T2, B, g.Hp * 2, g.Wp * 2, 2, s));
+        return launch_tail_out(T2, reinterpret_cast<const __half*>(W + L.tcw), y, B, g.Hp * 4, g.Wp * 4, hout, wout,
+                               b0, g.B, rgb_range, s);
+    }
+    return launch_tail_out(T1, reinterpret_cast<const __half*>(W + L.tcw), y, B, g.Hp * r0, g.Wp * r0, hout, wout, b0,
+                           g.B, rgb_range, s);
+}
+
+int m2t_forward(const m2t_plan* plan, const void* d_packed, const float* d_x, float* d_y, void* d_workspace,
+                void* stream) {
+    if (!plan || !d_packed || !d_x || !d_y || !d_workspace) { set_error("forward: null pointer"); return M2T_E_ARG; }
+    if (((uintptr_t)d_workspace & 255) || ((uintptr_t)d_packed & 255)) {
+        set_error("forward: workspace / packed weights must be 256-byte aligned");
+        return M2T_E_ARG;
+    }
+    M2T_TRY(check_device());
+    cudaStream_t s = (cudaStream_t)stream;
+    const Geom& g = plan->g;
+    const PackedLayout& L = plan->L;
+    const uint32_t var = plan->cfg.variant;
+    const uint8_t* W = static_cast<const uint8_t*>(d_packed);
+    uint8_t* ws = static_cast<uint8_t*>(d_workspace);
+    float* res = reinterpret_cast<float*>(ws + plan->o_res);
+    float* X = reinterpret_cast<float*>(ws + plan->o_x);
+    __half* Y = reinterpret_cast<__half*>(ws + plan->o_y);
+    __half* Z = reinterpret_cast<__half*>(ws + plan->o_z);
+    __half* QKV = reinterpret_cast<__half*>(ws + plan->o_qkv);
+    __half* O = reinterpret_cast<__half*>(ws + plan->o_o);
+    double* stats = reinterpret_cast<double*>(ws + plan->o_stats);
+    float2* munorm = reinterpret_cast<float2*>(ws + plan->o_munorm);
+    const size_t stat_stride = (size_t)g.B * NF * 2;
+    const int npix = g.Hp * g.Wp;
+
+    M2T_CUDA(cudaMemsetAsync(stats, 0, (size_t)(plan->cfg.n_blocks + 1) * stat_stride * sizeof(double), s));
+    M2T_TRY(launch_head(d_x, reinterpret_cast<const float*>(W + L.head_w), reinterpret_cast<const float*>(W + L.head_b),
+                        res, stats, g, s));
+    const float* Xin = res;
+    for (int i = 0; i < plan->cfg.n_blocks; ++i) {
+        M2T_TRY(launch_stats_finalize(stats + i * stat_stride, munorm, g.B, npix, s));
+        for (int a = 0; a < 4; ++a) {
+            const int lv = branch_level(a), C = branch_ch(a);
+            const int h = g.Hp >> lv, w = g.Wp >> lv;
+            const AttnW& A = L.blk[i].attn[a];
+            M2T_TRY(launch_branch_prep(lv, a, Xin, munorm, Y, Z, g, s));
+            M2T_TRY(run_qkv(var, Z, reinterpret_cast<const __half*>(W + A.wqkv), QKV, g.B * h * w, C, s));
+            M2T_TRY(run_attn(var, C, QKV, reinterpret_cast<const float*>(W + A.relf),
+                             reinterpret_cast<const __half*>(W + A.relx), O, g.B, h, w, s));
+            M2T_TRY(launch_branch_post(lv, a, O, Xin, munorm, Y, g, s));
+        }
+        M2T_TRY(run_ffconv(var, Y, reinterpret_cast<const __half*>(W + L.blk[i].ffw),
+                           reinterpret_cast<const float*>(W + L.blk[i].ffb), Xin, X, stats + (i + 1) * stat_stride, g, s));
+        Xin = X;
+    }
+    const size_t img_stride = (size_t)npix * NF;
+    for (int b0 = 0; b0 < g.B; b0 += plan->tail_chunk) {
+        const int nb = g.B - b0 < plan->tail_chunk ? g.B - b0 : plan->tail_chunk;
+        M2T_TRY(run_tail(var, plan->cfg.scale, L, W, Xin + b0 * img_stride, res + b0 * img_stride, d_y, nb, b0, g,
+                         plan->cfg.rgb_range, ws + plan->o_t1, s));
+    }
+    return M2T_OK;
+}
+
+// ---- per-stage entry points -------------------------------------------------------------------------
+static int make_geom(Geom* g, int B, int Hp, int Wp) {
+    if (B < 1 || Hp < 32 || Wp < 32 || Hp % 32 || Wp % 32) { set_error("stage: padded frame %dx%dx%d must be multiples of 32", B, Hp, Wp); return M2T_E_ARG; }
+    g->B = B; g->H = Hp; g->W = Wp; g->Hp = Hp; g->Wp = Wp; g->scale = 0;
+    return M2T_OK;
+}
+
+int m2t_stage_head(const float* d_x, const float* d_head_w, const float* d_head_b, float* d_res, double* d_stats,
+                   int B, int H, int W, void* stream) {
+    M2T_TRY(check_device());
+    Geom g;
+    g.B = B; g.H = H; g.W = W; g.Hp = (H + 31) / 32 * 32; g.Wp = (W + 31) / 32 * 32; g.scale = 0;
+    if (g.Hp - H >= H || g.Wp - W >= W) { set_error("stage_head: reflect padding undefined for %dx%d", H, W); return M2T_E_UNSUPPORTED; }
+    return launch_head(d_x, d_head_w, d_head_b, d_res, d_stats, g, (cudaStream_t)stream);
+}
+
+int m2t_stage_stats_finalize(const double* d_stats, float* d_munorm, int B, int npix, void* stream) {
+    M2T_TRY(check_device());
+    return launch_stats_finalize(d_stats, reinterpret_cast<float2*>(d_munorm), B, npix, (cudaStream_t)stream);
+}
+
+int m2t_stage_branch_prep(int branch, const float* d_X, const float* d_munorm, const void* d_Y, void* d_Z, int B,
+                          int Hp, int Wp, void* stream) {
+    M2T_TRY(check_device());
+    if (branch < 0 || branch > 3) { set_error("branch %d", branch); return M2T_E_ARG; }
+    Geom g;
+    M2T_TRY(make_geom(&g, B, Hp, Wp));
+    return launch_branch_prep(branch_level(branch), branch, d_X, reinterpret_cast<const float2*>(d_munorm),
+                              static_cast<const __half*>(d_Y), static_cast<__half*>(d_Z), g, (cudaStream_t)stream);
+}
+
+int m2t_stage_branch_post(int branch, const void* d_O, const float* d_X, const float* d_munorm, void* d_Y, int B,
+                          int Hp, int Wp, void* stream) {
+    M2T_TRY(check_device());
+    if (branch < 0 || branch > 3) { set_error("branch %d", branch); return M2T_E_ARG; }
+    Geom g;
+    M2T_TRY(make_geom(&g, B, Hp, Wp));
+    return launch_branch_post(branch_level(branch), branch, static_cast<const __half*>(d_O), d_X,
+                              reinterpret_cast<const float2*>(d_munorm), static_cast<__half*>(d_Y), g,
+                              (cudaStream_t)stream);
+}
+
+int m2t_stage_qkv(uint32_t variant, const void* d_Z, const void* d_wqkv, void* d_QKV, int M, int C, void* stream) {
+    M2T_TRY(check_device());
+    if (C != 16 && C != 64 && C != 256) { set_error("qkv: C=%d", C); return M2T_E_UNSUPPORTED; }
+    if (M % 64) { set_error("qkv: M=%d must be a multiple of 64 (whole 8x8 blocks)", M); return M2T_E_ARG; }
+    return run_qkv(variant, static_cast<const __half*>(d_Z), static_cast<const __half*>(d_wqkv),
+                   static_cast<__half*>(d_QKV), M, C, (cudaStream_t)stream);
+}
+
+int m2t_stage_attn(uint32_t variant, int C, const void* d_QKV, const float* d_relf, const void* d_relx, void* d_O,
+                   int B, int h, int w, void* stream) {
+    M2T_TRY(check_device());
+    return run_attn(variant, C, static_cast<const __half*>(d_QKV), d_relf, static_cast<const __half*>(d_relx),
+                    static_cast<__half*>(d_O), B, h, w, (cudaStream_t)stream);
+}
+
+int m2t_stage_ffconv(uint32_t variant, const void* d_Y, const void* d_ffw, const float* d_ffb, const float* d_Xin,
+                     float* d_Xout, double* d_stats, int B, int Hp, int Wp, void* stream) {
+    M2T_TRY(check_device());
+    Geom g;
+    M2T_TRY(make_geom(&g, B, Hp, Wp));
+    return run_ffconv(variant, static_cast<const __half*>(d_Y), static_cast<const __half*>(d_ffw), d_ffb, d_Xin,
+                      d_Xout, d_stats, g, (cudaStream_t)stream);
+}
+
+int m2t_stage_tail(uint32_t variant, int scale, int n_blocks, const void* d_packed, const float* d_X,
+                   const float* d_res, float* d_y, int B, int b0, int H, int W, float rgb_range, void* d_scratch,
+                   void* stream) {
+    M2T_TRY(check_device());
+    if (!d_packed || !d_X || !d_res || !d_y || !d_scratch) { set_error("stage_tail: null pointer"); return M2T_E_ARG; }
+    PackedLayout L;
+    M2T_TRY(make_packed_layout(scale, n_blocks, &L));
+    Geom g;
+    g.B = B; g.H = H; g.W = W; g.Hp = (H + 31) / 32 * 32; g.Wp = (W + 31) / 32 * 32; g.scale = scale;
+    return run_tail(variant, scale, L, static_cast<const uint8_t*>(d_packed), d_X, d_res, d_y, B, b0, g, rgb_range,
+                    static_cast<uint8_t*>(d_scratch), (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,130 @@
+// Shared declarations for the m2trans_b200 sm_100a engine.
+#pragma once
+
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/m2trans_b200.h"
+
+namespace m2t {
+
+constexpr int NF = 64;          // n_feats (ref configs/M2Trans_x*.yml: n_feats 64)
+constexpr int NB = 16;          // channels per CFTM branch = nf/4 (ref M2Trans_network.py:137)
+constexpr int BLK = 8;          // TBlock block_size (ref :119-122)
+constexpr int WIN = 10;         // block + 2*halo
+constexpr int NKEY = WIN * WIN; // 100 keys per window
+constexpr float IN_EPS = 1e-5f; // nn.InstanceNorm2d eps (ref :127)
+
+// ---- error plumbing ---------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+#define M2T_CUDA(call)                                                        \
+    do {                                                                      \
+        cudaError_t e__ = (call);                                             \
+        if (e__ != cudaSuccess) return m2t::cuda_fail(e__, #call, __FILE__, __LINE__); \
+    } while (0)
+
+#define M2T_LAUNCH_CHECK(name)                                                \
+    do {                                                                      \
+        cudaError_t e__ = cudaGetLastError();                                 \
+        if (e__ != cudaSuccess) return m2t::cuda_fail(e__, name, __FILE__, __LINE__); \
+    } while (0)
+
+#define M2T_TRY(expr)                         \
+    do {                                      \
+        int rc__ = (expr);                    \
+        if (rc__ != M2T_OK) return rc__;      \
+    } while (0)
+
+// opt a kernel in to > 48 KB of dynamic shared memory, once per device
+#define M2T_ENSURE_SMEM(fn, bytes)                                                              \
+    do {                                                                                        \
+        static unsigned char done__[64];                                                        \
+        int dev__ = 0;                                                                          \
+        M2T_CUDA(cudaGetDevice(&dev__));                                                        \
+        if (dev__ < 0 || dev__ >= 64 || !done__[dev__]) {                                       \
+            M2T_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); \
+            if (dev__ >= 0 && dev__ < 64) done__[dev__] = 1;                                    \
+        }                                                                                       \
+    } while (0)
+
+int device_sm_count();
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// ---- packed weights ----------------------------------------------------------------
+// Byte offsets into the packed weight blob (all 256-byte aligned).
+struct AttnW {
+    size_t wqkv;   // fp16 [3C][C]   rows 0..C-1 (q) pre-multiplied by C^-1/2 (exact: power of two)
+    size_t relf;   // fp32 [20][C/2] rows 0..9 rel_h, rows 10..19 rel_w
+    size_t relx;   // fp16 [32][C]   rows 0..9 [rel_h|0], 10..19 [0|rel_w], 20..31 zero (MMA operand form)
+};
+struct BlockW {
+    AttnW attn[4];
+    size_t ffw;    // fp16 [9][64 out][64 in]
+    size_t ffb;    // fp32 [64]
+};
+struct PackedLayout {
+    int scale, n_blocks;
+    size_t head_w;   // fp32 [27][64]  index (c*9 + ky*3 + kx)*64 + o
+    size_t head_b;   // fp32 [64]
+    BlockW blk[64];
+    size_t t0w, t0b; // fp16 [N0][64], fp32 [N0]      N0 = 64*r0^2
+    size_t t3w, t3b; // x4 only: fp16 [256][64], fp32 [256]
+    size_t tcw;      // fp16 [9][8][64]  final 3x3 conv, rows 3..7 zero
+    size_t total;
+};
+int make_packed_layout(int scale, int n_blocks, PackedLayout* out);
+static inline int branch_ch(int a) { return a == 0 ? 16 : (a == 1 ? 64 : 256); }
+static inline int branch_level(int a) { return a == 0 ? 0 : (a == 1 ? 1 : 2); }
+
+// ---- stage launchers (each returns M2T_OK or an error code) ------------------------
+struct Geom {
+    int B, H, W;     // LR input
+    int Hp, Wp;      // padded to multiples of 32 (ref :78-86)
+    int scale;
+};
+
+// head.cu
+int launch_head(const float* x, const float* w, const float* b, float* res, double* stats,
+                const Geom& g, cudaStream_t s);
+int launch_stats_finalize(const double* stats, float2* munorm, int B, int npix, cudaStream_t s);
+
+// branch.cu
+int launch_branch_prep(int level, int branch, const float* X, const float2* munorm, const __half* Y,
+                       __half* Z, const Geom& g, cudaStream_t s);
+int launch_branch_post(int level, int branch, const __half* O, const float* X, const float2* munorm,
+                       __half* Y, const Geom& g, cudaStream_t s);
+int launch_dwt_nchw(const float* in, float* out, int B, int C, int H, int W, cudaStream_t s);
+int launch_iwt_nchw(const float* in, float* out, int B, int C4, int H, int W, cudaStream_t s);
+int launch_nchw_to_nhwc_half(const float* in, __half* out, int B, int C, int H, int W, cudaStream_t s);
+int launch_nhwc_half_to_nchw(const __half* in, float* out, int B, int C, int H, int W, cudaStream_t s);
+int launch_nhwc_to_nchw_f32(const float* in, float* out, int B, int C, int H, int W, cudaStream_t s);
+
+// gemm_simt.cu : out[m][n] = sum_k A[m][k] * Wt[n][k]   (fp16 in, fp32 accumulate, fp16 out)
+int launch_gemm_simt(const __half* A, const __half* Wt, __half* out, int M, int N, int K, cudaStream_t s);
+
+// attn_simt.cu : halo attention over QKV [B,h,w,3C] -> O [B,h,w,C]
+int launch_attn_simt(int C, const __half* QKV, const float* relf, __half* O, int B, int h, int w,
+                     cudaStream_t s);
+
+// conv_simt.cu : X_out = conv3x3_zero(Y) + bias + X_in, plus InstanceNorm partial sums
+int launch_ffconv_simt(const __half* Y, const __half* Wp, const float* bias, const float* Xin, float* Xout,
+                       double* stats, const Geom& g, cudaStream_t s);
+
+// tail_simt.cu
+int launch_tail_up_simt(const float* Xa, const float* Xb, const __half* Ain, const __half* Wt,
+                        const float* bias, __half* out, int B, int h, int w, int r, cudaStream_t s);
+int launch_tail_out(const __half* T, const __half* Wc, float* y, int B, int hp, int wp, int hout, int wout,
+                    int b0, int Btot, float rgb_range, cudaStream_t s);
+
+// pack.cu
+int pack_weights_impl(const PackedLayout& L, const float* const* params, int n_params, uint8_t* packed,
+                      cudaStream_t s);
+
+}  // namespace m2t

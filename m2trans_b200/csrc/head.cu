@@ -1,0 +1,118 @@
+// Head stage: frame reflect-pad (ref M2Trans_network.py:78-86) + 3->64 3x3 reflect conv + bias
+// (ref :34,:63), written as the fp32 NHWC residual stream, plus the InstanceNorm partial sums of
+// the first CFTM (ref :127,:135).  K = 27 is too thin for the tensor cores: this stage is
+// HBM-bound (12 B in, 256 B out per pixel) and runs on the CUDA cores.
+#include "common.cuh"
+
+namespace m2t {
+
+// reflect without repeating the edge, for a coordinate in [-1, n]
+__device__ __forceinline__ int reflect1(int i, int n) { return i < 0 ? -i : (i >= n ? 2 * n - 2 - i : i); }
+// frame padding: bottom/right only (ref :85)
+__device__ __forceinline__ int frame_src(int i, int n) { return i < n ? i : 2 * (n - 1) - i; }
+
+constexpr int HEAD_PX = 64;  // pixels per CTA (4 threads per pixel)
+
+__global__ void __launch_bounds__(HEAD_PX * 4)
+head_conv_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                 float* __restrict__ res, double* __restrict__ stats, int B, int H, int W, int Hp, int Wp) {
+    __shared__ float sw[27 * NF];
+    __shared__ float sb[NF];
+    __shared__ float red[2][NF];
+    const int t = threadIdx.x;
+    for (int i = t; i < 27 * NF; i += blockDim.x) sw[i] = w[i];
+    if (t < NF) { sb[t] = bias[t]; red[0][t] = 0.f; red[1][t] = 0.f; }
+    __syncthreads();
+
+    const int q = t & 3;
+    const long gp = (long)blockIdx.x * HEAD_PX + (t >> 2);
+    const int npix = Hp * Wp;
+    const int b = (int)(gp / npix);
+    const int rem = (int)(gp - (long)b * npix);
+    const int y = rem / Wp, xx = rem - y * Wp;
+
+    float acc[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float4 bv = *reinterpret_cast<const float4*>(&sb[4 * (q + 4 * j)]);
+        acc[j][0] = bv.x; acc[j][1] = bv.y; acc[j][2] = bv.z; acc[j][3] = bv.w;
+    }
+    const float* xb = x + (long)b * 3 * H * W;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            const int sy = frame_src(reflect1(y + ky - 1, Hp), H);
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int sx = frame_src(reflect1(xx + kx - 1, Wp), W);
+                const float v = __ldg(xb + ((long)c * H + sy) * W + sx);
+                const float* wr = &sw[(c * 9 + ky * 3 + kx) * NF];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float4 wv = *reinterpret_cast<const float4*>(&wr[4 * (q + 4 * j)]);
+                    acc[j][0] = fmaf(v, wv.x, acc[j][0]);
+                    acc[j][1] = fmaf(v, wv.y, acc[j][1]);
+                    acc[j][2] = fmaf(v, wv.z, acc[j][2]);
+                    acc[j][3] = fmaf(v, wv.w, acc[j][3]);
+                }
+            }
+        }
+    }
+    float* o = res + gp * NF;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<float4*>(o + 4 * (q + 4 * j)) = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+
+    // InstanceNorm partial sums: lanes with equal (lane & 3) hold the same 16 channels
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            float s = acc[j][e], s2 = acc[j][e] * acc[j][e];
+#pragma unroll
+            for (int m = 4; m < 32; m <<= 1) {
+                s += __shfl_xor_sync(0xffffffffu, s, m);
+                s2 += __shfl_xor_sync(0xffffffffu, s2, m);
+            }
+            if ((t & 31) < 4) {
+                atomicAdd(&red[0][4 * (q + 4 * j) + e], s);
+                atomicAdd(&red[1][4 * (q + 4 * j) + e], s2);
+            }
+        }
+    }
+    __syncthreads();
+    if (t < 2 * NF) {
+        const int c = t >> 1, k = t & 1;
+        atomicAdd(&stats[((long)b * NF + c) * 2 + k], (double)red[k][c]);
+    }
+}
+
+int launch_head(const float* x, const float* w, const float* b, float* res, double* stats, const Geom& g,
+                cudaStream_t s) {
+    const long total = (long)g.B * g.Hp * g.Wp;
+    head_conv_kernel<<<(unsigned)(total / HEAD_PX), HEAD_PX * 4, 0, s>>>(x, w, b, res, stats, g.B, g.H, g.W,
+                                                                         g.Hp, g.Wp);
+    M2T_LAUNCH_CHECK("head_conv_kernel");
+    return M2T_OK;
+}
+
+// (sum, sumsq) -> (mean, 1/sqrt(var+eps)), biased variance (ref :127 nn.InstanceNorm2d defaults)
+__global__ void stats_finalize_kernel(const double* __restrict__ stats, float2* __restrict__ munorm, int n,
+                                      double inv_npix) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double m = stats[2 * i] * inv_npix;
+    double var = stats[2 * i + 1] * inv_npix - m * m;
+    if (var < 0.0) var = 0.0;
+    munorm[i] = make_float2((float)m, (float)(1.0 / sqrt(var + (double)IN_EPS)));
+}
+
+int launch_stats_finalize(const double* stats, float2* munorm, int B, int npix, cudaStream_t s) {
+    const int n = B * NF;
+    stats_finalize_kernel<<<cdiv(n, 128), 128, 0, s>>>(stats, munorm, n, 1.0 / (double)npix);
+    M2T_LAUNCH_CHECK("stats_finalize_kernel");
+    return M2T_OK;
+}
+
+}  // namespace m2t

@@ -1,0 +1,125 @@
+// Weight packing: reference state_dict tensors (fp32, ref M2Trans_network.py registration order, see
+// SURVEY.md appendix B.2) -> the engine's operand layouts (common.cuh PackedLayout).  Runs once per
+// load_state_dict on the device; nothing here is on the per-forward path.
+#include "common.cuh"
+
+namespace m2t {
+
+int make_packed_layout(int scale, int n_blocks, PackedLayout* L) {
+    if (scale < 2 || scale > 4) { set_error("scale %d not in {2,3,4}", scale); return M2T_E_UNSUPPORTED; }
+    if (n_blocks < 1 || n_blocks > 64) { set_error("n_blocks %d not in 1..64", n_blocks); return M2T_E_UNSUPPORTED; }
+    memset(L, 0, sizeof(*L));
+    L->scale = scale; L->n_blocks = n_blocks;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    L->head_w = take(27 * NF * 4);
+    L->head_b = take(NF * 4);
+    for (int i = 0; i < n_blocks; ++i) {
+        for (int a = 0; a < 4; ++a) {
+            const int C = branch_ch(a);
+            L->blk[i].attn[a].wqkv = take((size_t)3 * C * C * 2);
+            L->blk[i].attn[a].relf = take((size_t)20 * (C / 2) * 4);
+            L->blk[i].attn[a].relx = take((size_t)32 * C * 2);
+        }
+        L->blk[i].ffw = take((size_t)9 * NF * NF * 2);
+        L->blk[i].ffb = take(NF * 4);
+    }
+    const int r0 = scale == 4 ? 2 : scale;
+    const int N0 = NF * r0 * r0;
+    L->t0w = take((size_t)N0 * NF * 2);
+    L->t0b = take((size_t)N0 * 4);
+    if (scale == 4) {
+        L->t3w = take((size_t)256 * NF * 2);
+        L->t3b = take((size_t)256 * 4);
+    }
+    L->tcw = take((size_t)9 * 8 * NF * 2);
+    L->total = off;
+    return M2T_OK;
+}
+
+enum PackMode {
+    PK_COPY_F32 = 0,   // dst[i] = src[i]
+    PK_CVT_F16,        // dst[i] = half(src[i] * (i < n_scaled ? scale : 1))
+    PK_HEAD_W,         // src [64][3][3][3] -> dst [(c*9+tap)][64]
+    PK_CONV3_W,        // src [O][64][3][3] -> dst [tap][Opad][64] fp16, rows >= O zero
+    PK_RELX            // src rel_h [10][C/2] (+ rel_w passed as src2) -> dst fp16 [32][C]
+};
+
+__global__ void pack_kernel(int mode, const float* __restrict__ src, const float* __restrict__ src2, void* dstv,
+                            int n, int p0, int p1, float scale) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    switch (mode) {
+        case PK_COPY_F32: reinterpret_cast<float*>(dstv)[i] = src[i]; break;
+        case PK_CVT_F16:
+            reinterpret_cast<__half*>(dstv)[i] = __float2half_rn(src[i] * (i < p0 ? scale : 1.f));
+            break;
+        case PK_HEAD_W: {   // i over dst [27][64]
+            const int o = i % NF, k = i / NF;
+            reinterpret_cast<float*>(dstv)[i] = src[o * 27 + k];
+        } break;
+        case PK_CONV3_W: {  // i over dst [9][Opad=p1][64]; p0 = real O
+            const int c = i % NF, o = (i / NF) % p1, tap = i / (NF * p1);
+            reinterpret_cast<__half*>(dstv)[i] = o < p0 ? __float2half_rn(src[(o * NF + c) * 9 + tap]) : __half(0);
+        } break;
+        case PK_RELX: {     // i over dst [32][C=p0]
+            const int C = p0, hc = C / 2, c = i % C, row = i / C;
+            float v = 0.f;
+            if (row < 10 && c < hc) v = src[row * hc + c];
+            else if (row >= 10 && row < 20 && c >= hc) v = src2[(row - 10) * hc + (c - hc)];
+            reinterpret_cast<__half*>(dstv)[i] = __float2half_rn(v);
+        } break;
+    }
+}
+
+static int run_pack(int mode, const float* src, const float* src2, void* dst, int n, int p0, int p1, float scale,
+                    cudaStream_t s) {
+    pack_kernel<<<cdiv(n, 256), 256, 0, s>>>(mode, src, src2, dst, n, p0, p1, scale);
+    M2T_LAUNCH_CHECK("pack_kernel");
+    return M2T_OK;
+}
+
+int pack_weights_impl(const PackedLayout& L, const float* const* P, int n_params, uint8_t* packed, cudaStream_t s) {
+    const int want = 6 + 14 * L.n_blocks + (L.scale == 4 ? 5 : 3);
+    if (n_params != want) {
+        set_error("pack_weights: got %d tensors, the x%d state_dict with %d blocks has %d", n_params, L.scale,
+                  L.n_blocks, want);
+        return M2T_E_ARG;
+    }
+    for (int i = 4; i < n_params; ++i)
+        if (P[i] == nullptr) { set_error("pack_weights: tensor %d is null", i); return M2T_E_ARG; }
+    // P[0..3] = sub_mean / add_mean: present in checkpoints, never used by forward (ref :30-31, :58-76)
+    M2T_TRY(run_pack(PK_HEAD_W, P[4], nullptr, packed + L.head_w, 27 * NF, 0, 0, 1.f, s));
+    M2T_TRY(run_pack(PK_COPY_F32, P[5], nullptr, packed + L.head_b, NF, 0, 0, 1.f, s));
+    for (int i = 0; i < L.n_blocks; ++i) {
+        const int base = 6 + 14 * i;
+        for (int a = 0; a < 4; ++a) {
+            const int C = branch_ch(a), hc = C / 2;
+            const float* relh = P[base + 3 * a];
+            const float* relw = P[base + 3 * a + 1];
+            const float* wq = P[base + 3 * a + 2];
+            const AttnW& A = L.blk[i].attn[a];
+            const float qscale = 1.0f / sqrtf((float)C);    // ref :311 q * head_ch^-0.5 ; C in {16,64,256}
+            M2T_TRY(run_pack(PK_CVT_F16, wq, nullptr, packed + A.wqkv, 3 * C * C, C * C, 0, qscale, s));
+            M2T_TRY(run_pack(PK_COPY_F32, relh, nullptr, packed + A.relf, 10 * hc, 0, 0, 1.f, s));
+            M2T_TRY(run_pack(PK_COPY_F32, relw, nullptr, packed + A.relf + (size_t)10 * hc * 4, 10 * hc, 0, 0, 1.f, s));
+            M2T_TRY(run_pack(PK_RELX, relh, relw, packed + A.relx, 32 * C, C, 0, 1.f, s));
+        }
+        M2T_TRY(run_pack(PK_CONV3_W, P[base + 12], nullptr, packed + L.blk[i].ffw, 9 * NF * NF, NF, NF, 1.f, s));
+        M2T_TRY(run_pack(PK_COPY_F32, P[base + 13], nullptr, packed + L.blk[i].ffb, NF, 0, 0, 1.f, s));
+    }
+    const int tb = 6 + 14 * L.n_blocks;
+    const int r0 = L.scale == 4 ? 2 : L.scale, N0 = NF * r0 * r0;
+    M2T_TRY(run_pack(PK_CVT_F16, P[tb], nullptr, packed + L.t0w, N0 * NF, 0, 0, 1.f, s));
+    M2T_TRY(run_pack(PK_COPY_F32, P[tb + 1], nullptr, packed + L.t0b, N0, 0, 0, 1.f, s));
+    if (L.scale == 4) {
+        M2T_TRY(run_pack(PK_CVT_F16, P[tb + 2], nullptr, packed + L.t3w, 256 * NF, 0, 0, 1.f, s));
+        M2T_TRY(run_pack(PK_COPY_F32, P[tb + 3], nullptr, packed + L.t3b, 256, 0, 0, 1.f, s));
+        M2T_TRY(run_pack(PK_CONV3_W, P[tb + 4], nullptr, packed + L.tcw, 9 * 8 * NF, 3, 8, 1.f, s));
+    } else {
+        M2T_TRY(run_pack(PK_CONV3_W, P[tb + 2], nullptr, packed + L.tcw, 9 * 8 * NF, 3, 8, 1.f, s));
+    }
+    return M2T_OK;
+}
+
+}  // namespace m2t

@@ -1,0 +1,128 @@
+"""Parity of the CUDA engine (through the reference-shaped nn.Module -> ctypes -> C ABI) against the
+CPU oracle and the reference-generated golden fixtures.  B200 only (`-m gpu`).
+
+Bar (BASELINE.json north_star): PSNR(ours, ref) >= 50 dB and max |ours - ref| <= 2e-3 on the [0,1] output.
+"""
+import os
+import types
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+PSNR_MIN = 50.0
+MAXABS_MAX = 2e-3
+
+
+def _args(scale, n_blocks=8, variant=0):
+    # the keys of configs/M2Trans_x{scale}_test.yml that the model reads (ref M2Trans_network.py:21-25,34)
+    return types.SimpleNamespace(scale=scale, rgb_range=1.0, colors=3, n_feats=64, num_heads=4, n_blocks=n_blocks,
+                                 kernel_variant=variant)
+
+
+def _model(scale, seed, qkv_gain=1.0, n_blocks=8, variant=0):
+    from m2trans_b200.M2Trans_network import M2Trans
+    from m2trans_b200.synthetic import reference_checkpoint
+    ckpt = reference_checkpoint(scale, seed, qkv_gain=qkv_gain, n_blocks=n_blocks)
+    model = torch.nn.DataParallel(M2Trans(_args(scale, n_blocks, variant)), device_ids=[0]).cuda()
+    model.load_state_dict(ckpt["model_state_dict"], strict=True)        # exactly ref test.py:68-70
+    return model.eval()
+
+
+def _metrics(y, ref):
+    from oracle import m2trans_oracle as O
+    return O.psnr(y, ref), O.max_abs(y, ref)
+
+
+GOLDEN = ["fwd_x2_64x64", "fwd_x3_40x50", "fwd_x4_24x40", "fwd_x4_32x32_sharp", "fwd_x4_b2_32x32_speckle"]
+
+
+@pytest.mark.parametrize("variant", [0, 0xF], ids=["default", "simt"])
+@pytest.mark.parametrize("name", GOLDEN)
+def test_forward_matches_reference_golden(golden_dir, name, variant):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    model = _model(int(g["scale"]), int(g["seed"]), float(g["qkv_gain"]), variant=variant)
+    y = model(torch.from_numpy(g["x"]).cuda()).cpu()
+    ref = torch.from_numpy(g["y"])
+    assert tuple(y.shape) == tuple(ref.shape) and y.dtype == torch.float32
+    p, m = _metrics(y, ref)
+    print(f"{name} variant={variant}: PSNR {p:.1f} dB, max-abs {m:.2e}")
+    assert p >= PSNR_MIN and m <= MAXABS_MAX
+    assert float(y.min()) >= 0.0 and float(y.max()) <= 1.0
+
+
+@pytest.mark.parametrize("scale,shape,seed", [(4, (2, 3, 64, 64), 0), (2, (1, 3, 96, 72), 1), (3, (2, 3, 33, 47), 2)])
+def test_forward_matches_oracle(scale, shape, seed):
+    from oracle import m2trans_oracle as O
+    from m2trans_b200.synthetic import synthetic_input, synthetic_state_dict
+    x = synthetic_input(shape[0], shape[2], shape[3], seed=33 + seed)
+    ref, inter = O.forward(synthetic_state_dict(scale, seed), x, return_intermediates=True)
+    model = _model(scale, seed)
+    y = model(x.cuda()).cpu()
+    p, m = _metrics(y, ref)
+    print(f"x{scale} {shape}: PSNR {p:.1f} dB, max-abs {m:.2e}")
+    assert p >= PSNR_MIN and m <= MAXABS_MAX
+    # internal tensors: head output (fp32 math, tight) and the residual stream after the last CFTM
+    res = model.module.engine_tensor(shape, "res").permute(0, 3, 1, 2).cpu()
+    assert O.max_abs(res, inter["res"]) <= 1e-5
+    xs = model.module.engine_tensor(shape, "x").permute(0, 3, 1, 2).cpu()
+    rel = (xs - inter["body7"]).abs().max().item() / inter["body7"].std().item()
+    print(f"residual stream rel err {rel:.2e}")
+    assert rel <= 2e-2
+
+
+@pytest.mark.parametrize("ch", [16, 64, 256])
+def test_tblock_matches_reference_golden(golden_dir, ch):
+    from m2trans_b200.M2Trans_network import TBlock
+    u = np.load(os.path.join(golden_dir, "units.npz"))
+    blk = TBlock(ch).cuda()
+    with torch.no_grad():
+        blk.qkv_conv.weight.copy_(torch.from_numpy(u[f"tb{ch}_wqkv"]))
+        blk.rel_h.copy_(torch.from_numpy(u[f"tb{ch}_relh"]))
+        blk.rel_w.copy_(torch.from_numpy(u[f"tb{ch}_relw"]))
+    out = blk(torch.from_numpy(u[f"tb{ch}_in"]).cuda()).cpu().numpy()
+    want = u[f"tb{ch}_out"]
+    err = np.abs(out - want).max() / want.std()
+    print(f"TBlock C={ch}: max err / std = {err:.2e}")
+    assert err <= 2e-2
+
+
+def test_rejects_cpu_and_wrong_dtype():
+    from m2trans_b200.M2Trans_network import M2Trans, M2TError
+    m = M2Trans(_args(2, n_blocks=1)).cuda()
+    with pytest.raises(M2TError):
+        m(torch.rand(1, 3, 32, 32))                       # CPU tensor: no fallback
+    with pytest.raises(M2TError):
+        m(torch.rand(1, 3, 32, 32, device="cuda").half())
+    with pytest.raises(M2TError):
+        m(torch.rand(1, 3, 8, 40, device="cuda"))         # reflect pad 8 -> 32 undefined (reference raises too)
+
+
+def test_batch_consistency_and_determinism():
+    """Images are independent (InstanceNorm is per image): image i of a batch equals a batch-of-one run."""
+    from m2trans_b200.synthetic import synthetic_input
+    model = _model(4, 0)
+    x = synthetic_input(3, 40, 56, seed=5).cuda()
+    y = model(x)
+    y2 = model(x)
+    assert (y - y2).abs().max().item() <= 1e-5
+    for i in range(3):
+        yi = model(x[i:i + 1])
+        assert (yi[0] - y[i]).abs().max().item() <= 1e-4
+
+
+def test_full_size_cfg2_properties():
+    """BASELINE configs[1] (x4, 16x3x128x128): shape, range, finiteness; first image against the oracle."""
+    from oracle import m2trans_oracle as O
+    from m2trans_b200.synthetic import synthetic_input, synthetic_state_dict
+    model = _model(4, 0)
+    x = synthetic_input(16, 128, 128, seed=33)
+    y = model(x.cuda())
+    assert tuple(y.shape) == (16, 3, 512, 512)
+    assert torch.isfinite(y).all() and float(y.min()) >= 0.0 and float(y.max()) <= 1.0
+    ref0 = O.forward(synthetic_state_dict(4, 0), x[:1])
+    p, m = _metrics(y[:1].cpu(), ref0)
+    print(f"cfg2 image 0: PSNR {p:.1f} dB, max-abs {m:.2e}")
+    assert p >= PSNR_MIN and m <= MAXABS_MAX

@@ -1,0 +1,128 @@
+"""CPU-only checks of the boundary: the C-ABI library loads and exports every declared symbol, the
+nn.Module mirror has the reference's state_dict surface and load semantics, host-side planning works
+without a GPU, and nothing silently falls back to the CPU."""
+import ctypes as C
+import os
+import re
+import types
+
+import pytest
+import torch
+
+from m2trans_b200 import _lib
+from m2trans_b200.M2Trans_network import M2Trans, M2TError, create_model
+from m2trans_b200.synthetic import reference_checkpoint, state_dict_spec, synthetic_state_dict
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _args(scale, n_blocks=8):
+    return types.SimpleNamespace(scale=scale, rgb_range=1.0, colors=3, n_feats=64, num_heads=4, n_blocks=n_blocks)
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "m2trans_b200.h")).read()
+    declared = set(re.findall(r"\b(m2t_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert b"sm_100a" in lib.m2t_version()
+
+
+def test_host_side_planning_without_gpu():
+    lib = _lib.load()
+    assert lib.m2t_num_params(4, 8) == 123 and lib.m2t_num_params(2, 8) == 121 and lib.m2t_num_params(3, 8) == 121
+    assert lib.m2t_packed_weight_bytes(4, 8) > 3_500_000 * 2
+    assert lib.m2t_packed_weight_bytes(5, 8) == 0
+    assert lib.m2t_packed_offset(4, 8, b"body.7.attn4.wqkv") < lib.m2t_packed_weight_bytes(4, 8)
+    assert lib.m2t_packed_offset(4, 8, b"nonsense") == C.c_size_t(-1).value
+    cfg = _lib.m2t_cfg(3, 64, 8, 3, 32, 200, 266, 0, 1.0)          # BASELINE configs[2]
+    plan = C.c_void_p()
+    assert lib.m2t_plan_create(C.byref(cfg), C.byref(plan)) == 0
+    hp, wp = C.c_int(), C.c_int()
+    assert lib.m2t_plan_padded(plan, C.byref(hp), C.byref(wp)) == 0
+    assert (hp.value, wp.value) == (224, 288)
+    assert lib.m2t_workspace_bytes(plan) > 32 * 224 * 288 * 64 * 4 * 2
+    assert lib.m2t_plan_num_launches(plan) > 0
+    lib.m2t_plan_destroy(plan)
+    # the reference raises for reflect pads >= the dimension (F.pad); so does the plan
+    bad = _lib.m2t_cfg(4, 64, 8, 3, 1, 8, 40, 0, 1.0)
+    assert lib.m2t_plan_create(C.byref(bad), C.byref(plan)) == -4
+    assert b"reflect" in lib.m2t_last_error()
+    bad = _lib.m2t_cfg(4, 32, 8, 3, 1, 64, 64, 0, 1.0)
+    assert lib.m2t_plan_create(C.byref(bad), C.byref(plan)) == -4
+
+
+@pytest.mark.parametrize("scale", [2, 3, 4])
+def test_module_state_dict_surface(golden_dir, scale):
+    m = create_model(_args(scale))
+    want = []
+    for line in open(os.path.join(golden_dir, "state_dict_manifest.txt")):
+        s, key, shape, dtype = line.split()
+        if s == f"x{scale}":
+            want.append((key, tuple(int(t) for t in shape.split("x")), dtype))
+    got = [(k, tuple(v.shape), str(v.dtype).replace("torch.", "")) for k, v in m.state_dict().items()]
+    assert got == want
+    assert [k for k, _ in state_dict_spec(scale)] == [k for k, _, _ in want]
+    for attr in ("scale", "window_sizes", "rgb_range", "n_blocks", "head", "body", "tail", "sub_mean", "add_mean"):
+        assert hasattr(m, attr)
+    assert m.window_sizes == [8, 16, 32]
+
+
+def test_reference_checkpoint_loads_through_dataparallel():
+    ckpt = reference_checkpoint(4, 0)
+    assert set(ckpt) == {"epoch", "model_state_dict", "optimizer_state_dict", "scheduler_state_dict", "stat_dict"}
+    model = torch.nn.DataParallel(M2Trans(_args(4)))
+    model.load_state_dict(ckpt["model_state_dict"], strict=True)    # ref test.py:70
+    sd = synthetic_state_dict(4, 0)
+    for k, v in model.module.state_dict().items():
+        assert torch.equal(v, sd[k]), k
+
+
+def test_load_state_dict_override_semantics(capsys):
+    m = M2Trans(_args(3))
+    sd2 = synthetic_state_dict(2, 0)
+    m.load_state_dict(sd2)                                           # default strict=False, as the reference
+    assert "Replace pre-trained upsampler" in capsys.readouterr().out   # tail.0 shape differs (x2 -> x3)
+    assert torch.equal(m.head.weight, sd2["head.weight"])
+    with pytest.raises(KeyError):
+        m.load_state_dict({k: v for k, v in sd2.items() if k != "head.bias"}, strict=True)
+    extra = dict(synthetic_state_dict(3, 0))
+    extra["body.0.bogus"] = torch.zeros(1)
+    with pytest.raises(KeyError):
+        m.load_state_dict(extra, strict=True)
+    extra = dict(synthetic_state_dict(3, 0))
+    extra["tail.9.weight"] = torch.zeros(1)                          # unexpected tail keys are tolerated
+    m.load_state_dict(extra, strict=True)
+    bad = dict(synthetic_state_dict(3, 0))
+    bad["head.bias"] = torch.zeros(7)
+    with pytest.raises(RuntimeError):
+        m.load_state_dict(bad)
+
+
+def test_no_cpu_fallback():
+    m = M2Trans(_args(2, n_blocks=1))
+    with pytest.raises(M2TError):
+        m(torch.rand(1, 3, 32, 32))
+    with pytest.raises(M2TError):
+        m.body[0].attn1(torch.rand(1, 16, 8, 8))
+
+
+def test_check_image_size_matches_reference_rule():
+    m = M2Trans(_args(4, n_blocks=1))
+    x = torch.rand(1, 3, 40, 50)
+    xp = m.check_image_size(x)
+    assert tuple(xp.shape) == (1, 3, 64, 64)
+    assert torch.equal(xp[:, :, :40, :50], x)
+    assert torch.equal(xp[:, :, 40, :50], x[:, :, 38, :])            # reflect without repeating the edge
+
+
+def test_product_package_does_not_import_the_oracle():
+    pkg = os.path.join(ROOT, "m2trans_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("no oracle", ""), os.path.join(dirpath, f)
