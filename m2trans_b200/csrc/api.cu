@@ -195,7 +195,8 @@ size_t m2t_workspace_offset(const m2t_plan* plan, const char* name) {
 
 // ---- stage dispatch ------------------------------------------------------------------------------
 static int run_qkv(uint32_t variant, const __half* Z, const __half* wqkv, __half* QKV, int M, int C, cudaStream_t s) {
-    (void)variant;
+    // C = 16 (branch 1) is one K step of 32-byte rows: HBM-bound, kept on the CUDA cores
+    if (!(variant & M2T_VAR_SIMT_QKV) && (C == 64 || C == 256)) return launch_qkv_umma(Z, wqkv, QKV, M, C, s);
     return launch_gemm_simt(Z, wqkv, QKV, M, 3 * C, C, s);
 }
 static int run_attn(uint32_t variant, int C, const __half* QKV, const float* relf, const __half* relx, __half* O,

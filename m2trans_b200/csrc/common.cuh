@@ -109,6 +109,9 @@ int launch_nhwc_to_nchw_f32(const float* in, float* out, int B, int C, int H, in
 // gemm_simt.cu : out[m][n] = sum_k A[m][k] * Wt[n][k]   (fp16 in, fp32 accumulate, fp16 out)
 int launch_gemm_simt(const __half* A, const __half* Wt, __half* out, int M, int N, int K, cudaStream_t s);
 
+// gemm_umma.cu : same contract on tcgen05 (C = 64 or 256; N = 3C, K = C)
+int launch_qkv_umma(const __half* Z, const __half* Wqkv, __half* QKV, int M, int C, cudaStream_t s);
+
 // attn_simt.cu : halo attention over QKV [B,h,w,3C] -> O [B,h,w,C]
 int launch_attn_simt(int C, const __half* QKV, const float* relf, __half* O, int B, int h, int w,
                      cudaStream_t s);

