@@ -206,7 +206,7 @@ static int run_attn(uint32_t variant, int C, const __half* QKV, const float* rel
 }
 static int run_ffconv(uint32_t variant, const __half* Y, const __half* ffw, const float* ffb, const float* Xin,
                       float* Xout, double* stats, const Geom& g, cudaStream_t s) {
-    (void)variant;
+    if (!(variant & M2T_VAR_SIMT_CONV)) return launch_ffconv_umma(Y, ffw, ffb, Xin, Xout, stats, g, s);
     return launch_ffconv_simt(Y, ffw, ffb, Xin, Xout, stats, g, s);
 }
 static int run_tail(uint32_t variant, int scale, const PackedLayout& L, const uint8_t* W, const float* X,

@@ -120,6 +120,10 @@ int launch_attn_simt(int C, const __half* QKV, const float* relf, __half* O, int
 int launch_ffconv_simt(const __half* Y, const __half* Wp, const float* bias, const float* Xin, float* Xout,
                        double* stats, const Geom& g, cudaStream_t s);
 
+// conv_umma.cu : same contract as an implicit GEMM on tcgen05 fed by TMA
+int launch_ffconv_umma(const __half* Y, const __half* Wp, const float* bias, const float* Xin, float* Xout,
+                       double* stats, const Geom& g, cudaStream_t s);
+
 // tail_simt.cu
 int launch_tail_up_simt(const float* Xa, const float* Xb, const __half* Ain, const __half* Wt,
                         const float* bias, __half* out, int B, int h, int w, int r, cudaStream_t s);

@@ -75,7 +75,7 @@ ffconv_simt_kernel(const __half* __restrict__ Y, const __half* __restrict__ Wp, 
 #pragma unroll
         for (int o = 0; o < NF; ++o) Os[t * EPI_LD + o] = acc[o];
         __syncthreads();
-        epilogue_residual_stats<CT_W>(Os, bias, Xin, Xout, stats, b, y0, x0, Hp, Wpx);
+        epilogue_residual_stats<CT_W, 0>(Os, bias, Xin, Xout, stats, b, y0, x0, Hp, Wpx);
     }
 }
 

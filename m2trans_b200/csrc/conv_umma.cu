@@ -1,0 +1,162 @@
+// tcgen05 implicit-GEMM form of CFTM.feed_forward + residual (ref M2Trans_network.py:124-126, :164):
+//   Xout[p][o] = sum_{tap,c} Y[p + tap][c] * W[tap][o][c] + bias[o] + Xin[p][o]        (zero padding)
+// One output tile = 16 rows x 8 pixels (M = 128), N = 64 output channels, K = 9 taps x 64 channels.
+//
+// No im2col: TMA loads ONE 18 x 10 pixel halo tile of Y (fp16 NHWC, 128 B per pixel = one 128-byte swizzle
+// row; out-of-frame pixels arrive as zeros = the conv's zero padding).  The A operand of tap (dy,dx) is the
+// same shared-memory tile addressed through a descriptor whose start is shifted by (dy*10+dx) rows and whose
+// 8-row groups are 10 rows apart (SBO = 1280 B): the 128-byte swizzle phase follows the absolute
+// shared-memory address, so shifted descriptors read exactly what TMA wrote (tests/test_probes.py pins this).
+// 36 MMAs (M=128, N=64, K=16) accumulate one tile in TMEM; two accumulators let the epilogue of tile i
+// overlap the MMAs of tile i+1.  The 9 x 64 x 64 weights stay resident in shared memory (72 KB).
+//
+// Warp roles (192 threads): warps 0-3 epilogue (TMEM -> smem staging -> coalesced +bias +residual store and
+// InstanceNorm partial sums), warp 4 TMA producer, warp 5 MMA issuer.
+// The stage is memory-bound (reads 128 B Y + 256 B X, writes 256 B X per pixel); the tensor pipe is ~half idle.
+#include "common.cuh"
+#include "epilogue.cuh"
+#include "tma.cuh"
+#include "umma.cuh"
+
+namespace m2t {
+
+constexpr int CU_TH = 16, CU_TW = 8;                                  // output tile
+constexpr int CU_HW = CU_TW + 2;                                      // halo tile width (10)
+constexpr uint32_t CU_TILE_BYTES = (CU_TH + 2) * CU_HW * 128;         // 23040
+constexpr uint32_t CU_STAGE = 23 * 1024;                              // 1024-aligned stage pitch
+constexpr int CU_STAGES = 3;
+constexpr uint32_t CU_W_BYTES = 9 * NF * 128;                         // 73728
+constexpr uint32_t CU_OFF_A = CU_W_BYTES;
+constexpr uint32_t CU_OFF_O = CU_OFF_A + CU_STAGES * CU_STAGE;
+constexpr uint32_t CU_OFF_BAR = CU_OFF_O + 128 * EPI_LD * 4;
+constexpr uint32_t CU_SMEM = 1024 + CU_OFF_BAR + 256;
+
+__global__ void __launch_bounds__(192, 1)
+ffconv_umma_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ CUtensorMap mapW,
+                   const float* __restrict__ bias, const float* Xin, float* Xout, double* __restrict__ stats, int B,
+                   int Hp, int Wp) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
+    float* Os = reinterpret_cast<float*>(sm + CU_OFF_O);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + CU_OFF_BAR);
+    uint64_t* full = bars;                       // [STAGES]
+    uint64_t* empty = bars + CU_STAGES;          // [STAGES]
+    uint64_t* wfull = bars + 2 * CU_STAGES;
+    uint64_t* tfull = bars + 2 * CU_STAGES + 1;  // [2]
+    uint64_t* tempty = bars + 2 * CU_STAGES + 3; // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * CU_STAGES + 5);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tiles_x = Wp / CU_TW, tiles_y = Hp / CU_TH;
+    const int per_img = tiles_x * tiles_y;
+    const int ntiles = B * per_img;
+
+    if (warp == 5) tmem_alloc(tmem_slot, 128);
+    if (tid == 128) {
+        for (int s = 0; s < CU_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(wfull, 1);
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+        mbar_fence_init();
+        tma_prefetch_desc(&mapY);
+        tma_prefetch_desc(&mapW);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 4) {
+        if (lane == 0) {
+            mbar_expect_tx(wfull, CU_W_BYTES);
+            for (int tap = 0; tap < 9; ++tap) tma_load_2d(sm + tap * NF * 128, &mapW, wfull, 0, tap * NF);
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+                const int b = tile / per_img, r = tile - b * per_img;
+                const int y0 = (r / tiles_x) * CU_TH, x0 = (r % tiles_x) * CU_TW;
+                const uint32_t s = it % CU_STAGES, ph = (it / CU_STAGES) & 1;
+                mbar_wait(&empty[s], ph ^ 1);
+                mbar_expect_tx(&full[s], CU_TILE_BYTES);
+                tma_load_4d(sm + CU_OFF_A + s * CU_STAGE, &mapY, &full[s], 0, x0 - 1, y0 - 1, b);
+            }
+        }
+    } else if (warp == 5) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_f16(128, NF);
+            mbar_wait(wfull, 0);
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+                const uint32_t s = it % CU_STAGES, ph = (it / CU_STAGES) & 1;
+                const uint32_t acc = it & 1, aph = (it >> 1) & 1;
+                mbar_wait(&tempty[acc], aph ^ 1);
+                mbar_wait(&full[s], ph);
+                tc_fence_after();
+                const uint32_t a_base = base + CU_OFF_A + s * CU_STAGE;
+#pragma unroll
+                for (int tap = 0; tap < 9; ++tap) {
+                    const uint32_t a_tap = a_base + ((tap / 3) * CU_HW + (tap % 3)) * 128;
+                    const uint32_t b_tap = base + tap * NF * 128;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint64_t da = umma_smem_desc(a_tap + k * 32, 16, CU_HW * 128, UMMA_LAYOUT_SW128);
+                        const uint64_t db = umma_smem_desc(b_tap + k * 32, 16, 1024, UMMA_LAYOUT_SW128);
+                        umma_f16_ss(tmem_base + acc * NF, da, db, idesc, (tap | k) ? 1u : 0u);
+                    }
+                }
+                umma_commit(&empty[s]);
+                umma_commit(&tfull[acc]);
+            }
+        }
+    } else {
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            const int b = tile / per_img, r = tile - b * per_img;
+            const int y0 = (r / tiles_x) * CU_TH, x0 = (r % tiles_x) * CU_TW;
+            const uint32_t acc = it & 1, aph = (it >> 1) & 1;
+            mbar_wait(&tfull[acc], aph);
+            tc_fence_after();
+            const int m = warp * 32 + lane;
+#pragma unroll
+            for (int c0 = 0; c0 < NF; c0 += 32) {
+                uint32_t rr[32];
+                tmem_ld32(tmem_base + acc * NF + c0 + ((uint32_t)(warp * 32) << 16), rr);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) Os[m * EPI_LD + c0 + i] = __uint_as_float(rr[i]);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);          // accumulator drained: MMA may reuse it
+            epi_sync<1>();                                     // all 128 staged rows visible
+            epilogue_residual_stats<CU_TW, 1>(Os, bias, Xin, Xout, stats, b, y0, x0, Hp, Wp);
+            epi_sync<1>();                                     // Os / red free for the next tile
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) tmem_dealloc(tmem_base, 128);
+}
+
+int launch_ffconv_umma(const __half* Y, const __half* Wpk, const float* bias, const float* Xin, float* Xout,
+                       double* stats, const Geom& g, cudaStream_t s) {
+    CUtensorMap mapY, mapW;
+    {
+        const uint64_t dims[4] = {NF, (uint64_t)g.Wp, (uint64_t)g.Hp, (uint64_t)g.B};
+        const uint64_t str[4] = {2, NF * 2, (uint64_t)g.Wp * NF * 2, (uint64_t)g.Hp * g.Wp * NF * 2};
+        const uint32_t box[4] = {NF, CU_HW, CU_TH + 2, 1};
+        M2T_TRY(make_tensor_map(&mapY, Y, 2, 4, dims, str, box, 3));
+    }
+    {
+        const uint64_t dims[2] = {NF, 9 * NF}, str[2] = {2, NF * 2};
+        const uint32_t box[2] = {NF, NF};
+        M2T_TRY(make_tensor_map(&mapW, Wpk, 2, 2, dims, str, box, 3));
+    }
+    M2T_ENSURE_SMEM(ffconv_umma_kernel, CU_SMEM);
+    const int ntiles = g.B * (g.Hp / CU_TH) * (g.Wp / CU_TW);
+    const int grid = ntiles < device_sm_count() ? ntiles : device_sm_count();
+    ffconv_umma_kernel<<<grid, 192, CU_SMEM, s>>>(mapY, mapW, bias, Xin, Xout, stats, g.B, g.Hp, g.Wp);
+    M2T_LAUNCH_CHECK("ffconv_umma_kernel");
+    return M2T_OK;
+}
+
+}  // namespace m2t

@@ -11,9 +11,16 @@ namespace m2t {
 
 constexpr int EPI_LD = NF + 1;   // fp32 words per staged pixel row (odd: conflict-free column writes)
 
-// Called by all 128 threads of the CTA.  Os holds a 128-pixel x 64-channel fp32 tile, pixel p at
-// (y0 + p / TW, x0 + p % TW).  A __syncthreads() must separate the writes to Os from this call.
-template <int TW>
+// barrier over the 128 epilogue threads: the whole CTA (BAR == 0) or named barrier BAR
+template <int BAR>
+__device__ __forceinline__ void epi_sync() {
+    if constexpr (BAR == 0) __syncthreads();
+    else asm volatile("bar.sync %0, 128;" ::"n"(BAR) : "memory");
+}
+
+// Called by threads 0..127.  Os holds a 128-pixel x 64-channel fp32 tile, pixel p at (y0 + p / TW, x0 + p % TW).
+// A barrier must separate the writes to Os from this call, and another one this call from the next writes.
+template <int TW, int BAR>
 __device__ __forceinline__ void epilogue_residual_stats(const float* Os, const float* __restrict__ bias,
                                                         const float* Xin, float* Xout,  /* may alias (in-place) */
                                                         double* __restrict__ stats, int b, int y0, int x0, int Hp,
@@ -22,15 +29,22 @@ __device__ __forceinline__ void epilogue_residual_stats(const float* Os, const f
     const int t = threadIdx.x, c4 = t & 15, lane = t & 31, wid = t >> 5;
     const float4 bv = *reinterpret_cast<const float4*>(bias + 4 * c4);
     float s[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 4
+    // all 16 residual loads first: 32 KB in flight per CTA keeps the memory system busy
+    float4 xi[16];
+#pragma unroll
     for (int it = 0; it < 16; ++it) {
         const int p = (t >> 4) + 8 * it;
         const long pix = ((long)b * Hp + (y0 + p / TW)) * Wp + (x0 + p % TW);
-        const float4 xi = *reinterpret_cast<const float4*>(Xin + pix * NF + 4 * c4);
+        xi[it] = *reinterpret_cast<const float4*>(Xin + pix * NF + 4 * c4);
+    }
+#pragma unroll
+    for (int it = 0; it < 16; ++it) {
+        const int p = (t >> 4) + 8 * it;
+        const long pix = ((long)b * Hp + (y0 + p / TW)) * Wp + (x0 + p % TW);
         const float* o = Os + p * EPI_LD + 4 * c4;
         float v[4];
-        v[0] = o[0] + bv.x + xi.x; v[1] = o[1] + bv.y + xi.y;
-        v[2] = o[2] + bv.z + xi.z; v[3] = o[3] + bv.w + xi.w;
+        v[0] = o[0] + bv.x + xi[it].x; v[1] = o[1] + bv.y + xi[it].y;
+        v[2] = o[2] + bv.z + xi[it].z; v[3] = o[3] + bv.w + xi[it].w;
         *reinterpret_cast<float4*>(Xout + pix * NF + 4 * c4) = make_float4(v[0], v[1], v[2], v[3]);
 #pragma unroll
         for (int e = 0; e < 4; ++e) { s[e] += v[e]; s2[e] = fmaf(v[e], v[e], s2[e]); }
@@ -44,7 +58,7 @@ __device__ __forceinline__ void epilogue_residual_stats(const float* Os, const f
 #pragma unroll
         for (int e = 0; e < 4; ++e) { red[wid][0][4 * c4 + e] = s[e]; red[wid][1][4 * c4 + e] = s2[e]; }
     }
-    __syncthreads();
+    epi_sync<BAR>();
     {
         const int c = t >> 1, k = t & 1;
         const double tot = (double)red[0][k][c] + (double)red[1][k][c] + (double)red[2][k][c] + (double)red[3][k][c];

@@ -149,3 +149,32 @@ def test_stage_qkv_tensor_core_vs_cuda_core(C, M):
         assert torch.isfinite(o).all()
         assert (o - want).abs().max().item() <= 2e-3 * max(1.0, want.abs().max().item())
     assert (outs[0] - outs[1]).abs().max().item() <= 2e-3 * max(1.0, want.abs().max().item())
+
+
+@pytest.mark.parametrize("B,Hp,Wp", [(1, 32, 32), (2, 64, 96), (3, 128, 128)])
+def test_stage_ffconv_tensor_core_vs_cuda_core(B, Hp, Wp):
+    """tcgen05 implicit-GEMM 3x3 conv (+bias +residual +norm sums) against the CUDA-core variant and torch."""
+    import torch.nn.functional as F
+    from m2trans_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(B * 1000 + Hp + Wp)
+    y = torch.randn(B, Hp, Wp, 64, generator=g).half().cuda()
+    xin = torch.randn(B, Hp, Wp, 64, generator=g).cuda()
+    w = (torch.randn(64, 64, 3, 3, generator=g) * 0.05).half().cuda()       # reference layout [O][C][ky][kx]
+    bias = torch.randn(64, generator=g).cuda()
+    wp = w.permute(2, 3, 0, 1).reshape(9, 64, 64).contiguous()              # packed [tap][O][C]
+    want = F.conv2d(y.float().permute(0, 3, 1, 2), w.float(), bias, padding=1).permute(0, 2, 3, 1) + xin
+    outs = []
+    for variant in (0, _lib.VAR_SIMT_CONV):
+        xo = torch.full_like(xin, float("nan"))
+        stats = torch.zeros(B, 64, 2, dtype=torch.float64, device="cuda")
+        _lib.check(lib.m2t_stage_ffconv(variant, y.data_ptr(), wp.data_ptr(), bias.data_ptr(), xin.data_ptr(),
+                                        xo.data_ptr(), stats.data_ptr(), B, Hp, Wp, None), "m2t_stage_ffconv")
+        torch.cuda.synchronize()
+        assert torch.isfinite(xo).all()
+        assert (xo - want).abs().max().item() <= 2e-3
+        s = xo.double().sum(dim=(1, 2)); s2 = (xo.double() ** 2).sum(dim=(1, 2))
+        assert torch.allclose(stats[..., 0], s, rtol=1e-6, atol=1e-3)
+        assert torch.allclose(stats[..., 1], s2, rtol=1e-6, atol=1e-3)
+        outs.append(xo)
+    assert (outs[0] - outs[1]).abs().max().item() <= 1e-3
