@@ -201,7 +201,7 @@ static int run_qkv(uint32_t variant, const __half* Z, const __half* wqkv, __half
 }
 static int run_attn(uint32_t variant, int C, const __half* QKV, const float* relf, const __half* relx, __half* O,
                     int B, int h, int w, cudaStream_t s) {
-    (void)variant; (void)relx;
+    if (!(variant & M2T_VAR_SIMT_ATTN)) return launch_attn_umma(C, QKV, relx, O, B, h, w, s);
     return launch_attn_simt(C, QKV, relf, O, B, h, w, s);
 }
 static int run_ffconv(uint32_t variant, const __half* Y, const __half* ffw, const float* ffb, const float* Xin,

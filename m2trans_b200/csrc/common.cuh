@@ -116,6 +116,10 @@ int launch_qkv_umma(const __half* Z, const __half* Wqkv, __half* QKV, int M, int
 int launch_attn_simt(int C, const __half* QKV, const float* relf, __half* O, int B, int h, int w,
                      cudaStream_t s);
 
+// attn_umma.cu : same contract on tcgen05 (relx: fp16 [32][C] MMA-operand form of the rel tables)
+int launch_attn_umma(int C, const __half* QKV, const __half* relx, __half* O, int B, int h, int w,
+                     cudaStream_t s);
+
 // conv_simt.cu : X_out = conv3x3_zero(Y) + bias + X_in, plus InstanceNorm partial sums
 int launch_ffconv_simt(const __half* Y, const __half* Wp, const float* bias, const float* Xin, float* Xout,
                        double* stats, const Geom& g, cudaStream_t s);

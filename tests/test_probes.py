@@ -244,3 +244,62 @@ def test_tma_interleave_5d():
                 want[:, r, s, :] = tn[0, y, x].reshape(8, 8)
     ok = np.array_equal(got, want.view(np.uint8).reshape(-1))
     record("tma_interleave_5d", ok, f"mismatching bytes {int((got != want.view(np.uint8).reshape(-1)).sum())}")
+
+
+def swz32(off):
+    return off ^ (((off >> 7) & 1) << 4)
+
+
+def img_rows32_sw32(mat):
+    """mat [rows][16] fp16 (32-byte rows) -> bytes with the 32-byte swizzle (16-byte chunk ^= address bit 7)."""
+    rows, K = mat.shape
+    assert K == 16
+    out = np.zeros(rows * 32, dtype=np.uint8)
+    raw = mat.view(np.uint8).reshape(rows, 32)
+    for r in range(rows):
+        for ch in range(2):
+            off = swz32(r * 32 + ch * 16)
+            out[off:off + 16] = raw[r, ch * 16: ch * 16 + 16]
+    return out
+
+
+def test_umma_sw32_c16():
+    """16-channel tensors (branch 1): 32-byte rows, SWIZZLE_32B, K-major A/B and MN-major B with N = 16."""
+    A, B = rnd((128, 16), 30), rnd((224, 16), 31)
+    got = run_umma(img_rows32_sw32(A), img_rows32_sw32(B), desc(0, 16, 256, 6), desc(0, 16, 256, 6), 0, 0, 1,
+                   idesc(128, 224), 224)
+    want = A.astype(np.float32) @ B.astype(np.float32).T
+    record("umma_sw32_kmajor_K16", close(got, want), f"maxdiff {np.nanmax(np.abs(got - want)):.4g}")
+    # row-shifted / 10-row-pitch start as for SW128
+    A2 = rnd((200, 16), 32)
+    rows = np.array([(m // 8) * 10 + m % 8 + 11 for m in range(128)])
+    got = run_umma(img_rows32_sw32(A2), img_rows32_sw32(B), desc(11 * 32, 16, 320, 6), desc(0, 16, 256, 6), 0, 0, 1,
+                   idesc(128, 224), 224)
+    want = A2[rows].astype(np.float32) @ B.astype(np.float32).T
+    record("umma_sw32_kmajor_shift", close(got, want), f"maxdiff {np.nanmax(np.abs(got - want)):.4g}")
+    # P (K-major SW128 over 64 keys) x V (MN-major, 16 channels per key row)
+    P, V = rnd((128, 64), 33), rnd((64, 16), 34)
+    got = run_umma(img_kmajor_sw128(P), img_rows32_sw32(V), desc(0, 16, 1024, 2), desc(0, 16, 256, 6), 32, 16 * 32, 4,
+                   idesc(128, 16, 0, 1), 16)
+    want = P.astype(np.float32) @ V.astype(np.float32)
+    record("umma_sw32_mnmajor_b_N16", close(got, want), f"maxdiff {np.nanmax(np.abs(got - want)):.4g}")
+
+
+def test_tma_window_sw32():
+    H, W = 12, 20
+    t = torch.from_numpy(rnd((1, H, W, 48), 35)).cuda()          # QKV of branch 1: 3C = 48 channels
+    tn = t.cpu().numpy()
+    y0, x0, c0 = -1, 11, 16                                       # the K slice
+    got = run_tma(t, (48, W, H, 1), (2, 96, W * 96, H * W * 96), (16, 10, 10, 1), 1, (c0, x0, y0, 0))
+    want = np.zeros(100 * 32, np.uint8)
+    for r in range(10):
+        for s in range(10):
+            y, x = y0 + r, x0 + s
+            px = tn[0, y, x, c0:c0 + 16] if (0 <= y < H and 0 <= x < W) else np.zeros(16, np.float16)
+            raw = np.ascontiguousarray(px).view(np.uint8)
+            p = r * 10 + s
+            for ch in range(2):
+                off = swz32(p * 32 + ch * 16)
+                want[off:off + 16] = raw[ch * 16: ch * 16 + 16]
+    ok = np.array_equal(got, want)
+    record("tma_sw32_window", ok, f"mismatching bytes {int((got != want).sum())}")
