@@ -138,13 +138,14 @@ int m2t_stage_attn(uint32_t variant, int C, const void* d_QKV, const float* d_re
 int m2t_stage_ffconv(uint32_t variant, const void* d_Y, const void* d_ffw, const float* d_ffb,
                      const float* d_Xin, float* d_Xout, double* d_stats, int B, int Hp, int Wp,
                      void* stream);
-/* tail (ref :40-56,:70-76) on B images whose NHWC streams start at d_X / d_res, written to
- * output images b0.. of d_y [*,3,H*s,W*s]; d_scratch holds m2t_tail_scratch_bytes(scale, B, Hp, Wp)
- * bytes; d_packed is the blob of m2t_pack_weights(scale, n_blocks, ...). */
+/* tail (ref :40-56,:72-76) on B images; d_XR is fp16 NHWC [B,Hp,Wp,64] = res + x (ref :70; in
+ * m2t_forward the last ff conv's epilogue writes it); output images b0.. of d_y [*,3,H*s,W*s];
+ * d_scratch holds m2t_tail_scratch_bytes(scale, B, Hp, Wp) bytes; d_packed is the blob of
+ * m2t_pack_weights(scale, n_blocks, ...). */
 size_t m2t_tail_scratch_bytes(int scale, int B, int Hp, int Wp);
-int m2t_stage_tail(uint32_t variant, int scale, int n_blocks, const void* d_packed, const float* d_X,
-                   const float* d_res, float* d_y, int B, int b0, int H, int W, float rgb_range,
-                   void* d_scratch, void* stream);
+int m2t_stage_tail(uint32_t variant, int scale, int n_blocks, const void* d_packed, const void* d_XR,
+                   float* d_y, int B, int b0, int H, int W, float rgb_range, void* d_scratch,
+                   void* stream);
 
 /* ---- hardware probes (development aids; tests/test_probes.py) ---------------------------
  * m2t_probe_umma: copies two raw shared-memory images (A, B operands), issues k_steps

@@ -58,11 +58,19 @@ struct m2t_plan {
     PackedLayout L;
     int tail_chunk;            // images per tail pass
     // workspace byte offsets
-    size_t o_res, o_x, o_y, o_z, o_qkv, o_o, o_stats, o_munorm, o_t1, o_t2, ws_bytes;
+    size_t o_res, o_x, o_y, o_z, o_qkv, o_o, o_stats, o_munorm, o_xr, o_t1, ws_bytes;
     int n_launches;
 };
 
 static inline int tail_r0(int scale) { return scale == 4 ? 2 : scale; }
+// The tensor the last 3x3 conv reads carries a 1-pixel reflected border ring (T1 for x2/x3, T2 for x4).
+static inline size_t tail_t1_bytes(int scale, int B, int Hp, int Wp) {
+    const int r0 = tail_r0(scale), pad = scale == 4 ? 0 : 1;
+    return align_up((size_t)B * (Hp * r0 + 2 * pad) * (Wp * r0 + 2 * pad) * NF * 2, 256);
+}
+static inline size_t tail_t2_bytes(int scale, int B, int Hp, int Wp) {
+    return scale == 4 ? align_up((size_t)B * (Hp * 4 + 2) * (Wp * 4 + 2) * NF * 2, 256) : 0;
+}
 
 extern "C" {
 
@@ -123,10 +131,7 @@ int m2t_pack_weights(int scale, int n_blocks, const float* const* d_params, int 
 }
 
 size_t m2t_tail_scratch_bytes(int scale, int B, int Hp, int Wp) {
-    const int r0 = tail_r0(scale);
-    size_t t1 = (size_t)B * Hp * r0 * Wp * r0 * NF * 2;
-    size_t t2 = scale == 4 ? (size_t)B * Hp * 4 * Wp * 4 * NF * 2 : 0;
-    return align_up(t1, 256) + align_up(t2, 256);
+    return tail_t1_bytes(scale, B, Hp, Wp) + tail_t2_bytes(scale, B, Hp, Wp);
 }
 
 int m2t_plan_create(const m2t_cfg* cfg, m2t_plan** out) {
@@ -166,12 +171,11 @@ int m2t_plan_create(const m2t_cfg* cfg, m2t_plan** out) {
     if (chunk < 1) chunk = 1;
     if (chunk > g.B) chunk = g.B;
     p->tail_chunk = chunk;
-    const int r0 = tail_r0(cfg->scale);
-    p->o_t1 = take((size_t)chunk * g.Hp * r0 * g.Wp * r0 * NF * 2);
-    p->o_t2 = cfg->scale == 4 ? take((size_t)chunk * g.Hp * 4 * g.Wp * 4 * NF * 2) : p->o_t1;
+    p->o_xr = take(P * NF * 2);
+    p->o_t1 = take(m2t_tail_scratch_bytes(cfg->scale, chunk, g.Hp, g.Wp));
     p->ws_bytes = off;
     const int tail_passes = (g.B + chunk - 1) / chunk;
-    p->n_launches = 1 /*head*/ + cfg->n_blocks * (1 + 4 * 4 + 1) + tail_passes * (cfg->scale == 4 ? 3 : 2);
+    p->n_launches = 1 /*head*/ + cfg->n_blocks * (1 + 4 * 4 + 1) + tail_passes * (cfg->scale == 4 ? 4 : 3);
     *out = p;
     return M2T_OK;
 }
@@ -205,29 +209,37 @@ static int run_attn(uint32_t variant, int C, const __half* QKV, const float* rel
     return launch_attn_simt(C, QKV, relf, O, B, h, w, s);
 }
 static int run_ffconv(uint32_t variant, const __half* Y, const __half* ffw, const float* ffb, const float* Xin,
-                      float* Xout, double* stats, const Geom& g, cudaStream_t s) {
-    if (!(variant & M2T_VAR_SIMT_CONV)) return launch_ffconv_umma(Y, ffw, ffb, Xin, Xout, stats, g, s);
-    return launch_ffconv_simt(Y, ffw, ffb, Xin, Xout, stats, g, s);
+                      float* Xout, double* stats, const Geom& g, cudaStream_t s, const float* res = nullptr,
+                      __half* xr = nullptr) {
+    if (!(variant & M2T_VAR_SIMT_CONV)) return launch_ffconv_umma(Y, ffw, ffb, Xin, Xout, stats, g, s, res, xr);
+    return launch_ffconv_simt(Y, ffw, ffb, Xin, Xout, stats, g, s, res, xr);
 }
-static int run_tail(uint32_t variant, int scale, const PackedLayout& L, const uint8_t* W, const float* X,
-                    const float* res, float* y, int B, int b0, const Geom& g, float rgb_range, uint8_t* scratch,
-                    cudaStream_t s) {
-    (void)variant;
+// XR = fp16(res + x) of B images (ref :70), written by the last ff conv's epilogue
+static int run_tail(uint32_t variant, int scale, const PackedLayout& L, const uint8_t* W, const __half* XR, float* y,
+                    int B, int b0, const Geom& g, float rgb_range, uint8_t* scratch, cudaStream_t s) {
+    const bool tc = !(variant & M2T_VAR_SIMT_TAIL);
     const int r0 = tail_r0(scale);
     __half* T1 = reinterpret_cast<__half*>(scratch);
-    const size_t t1_bytes = align_up((size_t)B * g.Hp * r0 * g.Wp * r0 * NF * 2, 256);
-    __half* T2 = reinterpret_cast<__half*>(scratch + t1_bytes);
+    __half* T2 = reinterpret_cast<__half*>(scratch + tail_t1_bytes(scale, B, g.Hp, g.Wp));
     const int hout = g.H * scale, wout = g.W * scale;
-    M2T_TRY(launch_tail_up_simt(X, res, nullptr, reinterpret_cast<const __half*>(W + L.t0w),
-                                reinterpret_cast<const float*>(W + L.t0b), T1, B, g.Hp, g.Wp, r0, s));
+    const __half* w0 = reinterpret_cast<const __half*>(W + L.t0w);
+    const float* b0p = reinterpret_cast<const float*>(W + L.t0b);
+    const __half* wc = reinterpret_cast<const __half*>(W + L.tcw);
+    const int pad1 = scale == 4 ? 0 : 1;
+    if (tc) M2T_TRY(launch_tail_up_umma(XR, w0, b0p, T1, B, g.Hp, g.Wp, r0, pad1, s));
+    else M2T_TRY(launch_tail_up_simt(XR, w0, b0p, T1, B, g.Hp, g.Wp, r0, pad1, s));
+    __half* Tl = T1;
+    int hl = g.Hp * r0, wl = g.Wp * r0;
     if (scale == 4) {
-        M2T_TRY(launch_tail_up_simt(nullptr, nullptr, T1, reinterpret_cast<const __half*>(W + L.t3w),
-                                    reinterpret_cast<const float*>(W + L.t3b), T2, B, g.Hp * 2, g.Wp * 2, 2, s));
-        return launch_tail_out(T2, reinterpret_cast<const __half*>(W + L.tcw), y, B, g.Hp * 4, g.Wp * 4, hout, wout,
-                               b0, g.B, rgb_range, s);
+        const __half* w3 = reinterpret_cast<const __half*>(W + L.t3w);
+        const float* b3 = reinterpret_cast<const float*>(W + L.t3b);
+        if (tc) M2T_TRY(launch_tail_up_umma(T1, w3, b3, T2, B, hl, wl, 2, 1, s));
+        else M2T_TRY(launch_tail_up_simt(T1, w3, b3, T2, B, hl, wl, 2, 1, s));
+        Tl = T2; hl *= 2; wl *= 2;
     }
-    return launch_tail_out(T1, reinterpret_cast<const __half*>(W + L.tcw), y, B, g.Hp * r0, g.Wp * r0, hout, wout, b0,
-                           g.B, rgb_range, s);
+    M2T_TRY(launch_reflect_border(Tl, B, hl, wl, s));
+    if (tc) return launch_tail_out_umma(Tl, wc, y, B, hl, wl, hout, wout, b0, rgb_range, s);
+    return launch_tail_out_simt(Tl, wc, y, B, hl, wl, hout, wout, b0, rgb_range, s);
 }
 
 int m2t_forward(const m2t_plan* plan, const void* d_packed, const float* d_x, float* d_y, void* d_workspace,
@@ -250,6 +262,7 @@ int m2t_forward(const m2t_plan* plan, const void* d_packed, const float* d_x, fl
     __half* Z = reinterpret_cast<__half*>(ws + plan->o_z);
     __half* QKV = reinterpret_cast<__half*>(ws + plan->o_qkv);
     __half* O = reinterpret_cast<__half*>(ws + plan->o_o);
+    __half* XR = reinterpret_cast<__half*>(ws + plan->o_xr);
     double* stats = reinterpret_cast<double*>(ws + plan->o_stats);
     float2* munorm = reinterpret_cast<float2*>(ws + plan->o_munorm);
     const size_t stat_stride = (size_t)g.B * NF * 2;
@@ -271,15 +284,17 @@ int m2t_forward(const m2t_plan* plan, const void* d_packed, const float* d_x, fl
                              reinterpret_cast<const __half*>(W + A.relx), O, g.B, h, w, s));
             M2T_TRY(launch_branch_post(lv, a, O, Xin, munorm, Y, g, s));
         }
+        const bool last = i == plan->cfg.n_blocks - 1;      // the last block also emits fp16(res + x) for the tail
         M2T_TRY(run_ffconv(var, Y, reinterpret_cast<const __half*>(W + L.blk[i].ffw),
-                           reinterpret_cast<const float*>(W + L.blk[i].ffb), Xin, X, stats + (i + 1) * stat_stride, g, s));
+                           reinterpret_cast<const float*>(W + L.blk[i].ffb), Xin, X, stats + (i + 1) * stat_stride, g, s,
+                           last ? res : nullptr, last ? XR : nullptr));
         Xin = X;
     }
     const size_t img_stride = (size_t)npix * NF;
     for (int b0 = 0; b0 < g.B; b0 += plan->tail_chunk) {
         const int nb = g.B - b0 < plan->tail_chunk ? g.B - b0 : plan->tail_chunk;
-        M2T_TRY(run_tail(var, plan->cfg.scale, L, W, Xin + b0 * img_stride, res + b0 * img_stride, d_y, nb, b0, g,
-                         plan->cfg.rgb_range, ws + plan->o_t1, s));
+        M2T_TRY(run_tail(var, plan->cfg.scale, L, W, XR + b0 * img_stride, d_y, nb, b0, g, plan->cfg.rgb_range,
+                         ws + plan->o_t1, s));
     }
     return M2T_OK;
 }
@@ -350,17 +365,16 @@ int m2t_stage_ffconv(uint32_t variant, const void* d_Y, const void* d_ffw, const
                       d_Xout, d_stats, g, (cudaStream_t)stream);
 }
 
-int m2t_stage_tail(uint32_t variant, int scale, int n_blocks, const void* d_packed, const float* d_X,
-                   const float* d_res, float* d_y, int B, int b0, int H, int W, float rgb_range, void* d_scratch,
-                   void* stream) {
+int m2t_stage_tail(uint32_t variant, int scale, int n_blocks, const void* d_packed, const void* d_XR, float* d_y,
+                   int B, int b0, int H, int W, float rgb_range, void* d_scratch, void* stream) {
     M2T_TRY(check_device());
-    if (!d_packed || !d_X || !d_res || !d_y || !d_scratch) { set_error("stage_tail: null pointer"); return M2T_E_ARG; }
+    if (!d_packed || !d_XR || !d_y || !d_scratch) { set_error("stage_tail: null pointer"); return M2T_E_ARG; }
     PackedLayout L;
     M2T_TRY(make_packed_layout(scale, n_blocks, &L));
     Geom g;
     g.B = B; g.H = H; g.W = W; g.Hp = (H + 31) / 32 * 32; g.Wp = (W + 31) / 32 * 32; g.scale = scale;
-    return run_tail(variant, scale, L, static_cast<const uint8_t*>(d_packed), d_X, d_res, d_y, B, b0, g, rgb_range,
-                    static_cast<uint8_t*>(d_scratch), (cudaStream_t)stream);
+    return run_tail(variant, scale, L, static_cast<const uint8_t*>(d_packed), static_cast<const __half*>(d_XR), d_y, B,
+                    b0, g, rgb_range, static_cast<uint8_t*>(d_scratch), (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -121,18 +121,30 @@ int launch_attn_umma(int C, const __half* QKV, const __half* relx, __half* O, in
                      cudaStream_t s);
 
 // conv_simt.cu : X_out = conv3x3_zero(Y) + bias + X_in, plus InstanceNorm partial sums
+// res/xr (optional): also write xr = fp16(Xout + res), the tail's first GEMM operand (ref :70)
 int launch_ffconv_simt(const __half* Y, const __half* Wp, const float* bias, const float* Xin, float* Xout,
-                       double* stats, const Geom& g, cudaStream_t s);
+                       double* stats, const Geom& g, cudaStream_t s, const float* res = nullptr,
+                       __half* xr = nullptr);
 
 // conv_umma.cu : same contract as an implicit GEMM on tcgen05 fed by TMA
 int launch_ffconv_umma(const __half* Y, const __half* Wp, const float* bias, const float* Xin, float* Xout,
-                       double* stats, const Geom& g, cudaStream_t s);
+                       double* stats, const Geom& g, cudaStream_t s, const float* res = nullptr,
+                       __half* xr = nullptr);
 
 // tail_simt.cu
-int launch_tail_up_simt(const float* Xa, const float* Xb, const __half* Ain, const __half* Wt,
-                        const float* bias, __half* out, int B, int h, int w, int r, cudaStream_t s);
-int launch_tail_out(const __half* T, const __half* Wc, float* y, int B, int hp, int wp, int hout, int wout,
-                    int b0, int Btot, float rgb_range, cudaStream_t s);
+//   tail_up : A fp16 [B,h,w,64] -> out fp16 [B, r h + 2 pad, r w + 2 pad, 64] (interior only; pad = 0 or 1)
+//   reflect_border : fills the pad ring of a [B][h+2][w+2][64] tensor
+//   tail_out: T fp16 [Bc][hp+2][wp+2][64] (ring filled) -> y fp32 NCHW images b0.. cropped to hout x wout
+int launch_tail_up_simt(const __half* Ain, const __half* Wt, const float* bias, __half* out, int B, int h, int w,
+                        int r, int pad, cudaStream_t s);
+int launch_reflect_border(__half* T, int B, int h, int w, cudaStream_t s);
+int launch_tail_out_simt(const __half* T, const __half* Wc, float* y, int Bc, int hp, int wp, int hout, int wout,
+                         int b0, float rgb_range, cudaStream_t s);
+// tail_umma.cu : the same two stages on tcgen05
+int launch_tail_up_umma(const __half* A, const __half* Wt, const float* bias, __half* out, int B, int h, int w,
+                        int r, int pad, cudaStream_t s);
+int launch_tail_out_umma(const __half* T, const __half* Wc, float* y, int Bc, int hp, int wp, int hout, int wout,
+                         int b0, float rgb_range, cudaStream_t s);
 
 // pack.cu
 int pack_weights_impl(const PackedLayout& L, const float* const* params, int n_params, uint8_t* packed,

@@ -18,7 +18,7 @@ constexpr size_t CS_BYTES = CS_O + (size_t)CT_H * CT_W * EPI_LD * 4;
 __global__ void __launch_bounds__(128, 1)
 ffconv_simt_kernel(const __half* __restrict__ Y, const __half* __restrict__ Wp, const float* __restrict__ bias,
                    const float* Xin, float* Xout, double* __restrict__ stats, int B,
-                   int Hp, int Wpx) {
+                   int Hp, int Wpx, const float* __restrict__ res, __half* __restrict__ xr) {
     extern __shared__ __align__(16) uint8_t smem[];
     float* Ws = reinterpret_cast<float*>(smem + CS_W);
     __half* Ts = reinterpret_cast<__half*>(smem + CS_T);
@@ -75,16 +75,16 @@ ffconv_simt_kernel(const __half* __restrict__ Y, const __half* __restrict__ Wp, 
 #pragma unroll
         for (int o = 0; o < NF; ++o) Os[t * EPI_LD + o] = acc[o];
         __syncthreads();
-        epilogue_residual_stats<CT_W, 0>(Os, bias, Xin, Xout, stats, b, y0, x0, Hp, Wpx);
+        epilogue_residual_stats<CT_W, 0>(Os, bias, Xin, Xout, stats, b, y0, x0, Hp, Wpx, res, xr);
     }
 }
 
 int launch_ffconv_simt(const __half* Y, const __half* Wp, const float* bias, const float* Xin, float* Xout,
-                       double* stats, const Geom& g, cudaStream_t s) {
+                       double* stats, const Geom& g, cudaStream_t s, const float* res, __half* xr) {
     M2T_ENSURE_SMEM(ffconv_simt_kernel, CS_BYTES);
     const int ntiles = g.B * (g.Hp / CT_H) * (g.Wp / CT_W);
     const int grid = ntiles < device_sm_count() ? ntiles : device_sm_count();
-    ffconv_simt_kernel<<<grid, 128, CS_BYTES, s>>>(Y, Wp, bias, Xin, Xout, stats, g.B, g.Hp, g.Wp);
+    ffconv_simt_kernel<<<grid, 128, CS_BYTES, s>>>(Y, Wp, bias, Xin, Xout, stats, g.B, g.Hp, g.Wp, res, xr);
     M2T_LAUNCH_CHECK("ffconv_simt_kernel");
     return M2T_OK;
 }

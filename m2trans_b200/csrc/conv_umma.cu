@@ -34,7 +34,7 @@ constexpr uint32_t CU_SMEM = 1024 + CU_OFF_BAR + 256;
 __global__ void __launch_bounds__(192, 1)
 ffconv_umma_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ CUtensorMap mapW,
                    const float* __restrict__ bias, const float* Xin, float* Xout, double* __restrict__ stats, int B,
-                   int Hp, int Wp) {
+                   int Hp, int Wp, const float* __restrict__ res, __half* __restrict__ xr) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
@@ -128,7 +128,7 @@ ffconv_umma_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_consta
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);          // accumulator drained: MMA may reuse it
             epi_sync<1>();                                     // all 128 staged rows visible
-            epilogue_residual_stats<CU_TW, 1>(Os, bias, Xin, Xout, stats, b, y0, x0, Hp, Wp);
+            epilogue_residual_stats<CU_TW, 1>(Os, bias, Xin, Xout, stats, b, y0, x0, Hp, Wp, res, xr);
             epi_sync<1>();                                     // Os / red free for the next tile
         }
     }
@@ -138,7 +138,7 @@ ffconv_umma_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_consta
 }
 
 int launch_ffconv_umma(const __half* Y, const __half* Wpk, const float* bias, const float* Xin, float* Xout,
-                       double* stats, const Geom& g, cudaStream_t s) {
+                       double* stats, const Geom& g, cudaStream_t s, const float* res, __half* xr) {
     CUtensorMap mapY, mapW;
     {
         const uint64_t dims[4] = {NF, (uint64_t)g.Wp, (uint64_t)g.Hp, (uint64_t)g.B};
@@ -154,7 +154,7 @@ int launch_ffconv_umma(const __half* Y, const __half* Wpk, const float* bias, co
     M2T_ENSURE_SMEM(ffconv_umma_kernel, CU_SMEM);
     const int ntiles = g.B * (g.Hp / CU_TH) * (g.Wp / CU_TW);
     const int grid = ntiles < device_sm_count() ? ntiles : device_sm_count();
-    ffconv_umma_kernel<<<grid, 192, CU_SMEM, s>>>(mapY, mapW, bias, Xin, Xout, stats, g.B, g.Hp, g.Wp);
+    ffconv_umma_kernel<<<grid, 192, CU_SMEM, s>>>(mapY, mapW, bias, Xin, Xout, stats, g.B, g.Hp, g.Wp, res, xr);
     M2T_LAUNCH_CHECK("ffconv_umma_kernel");
     return M2T_OK;
 }

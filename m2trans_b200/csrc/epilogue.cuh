@@ -24,7 +24,8 @@ template <int TW, int BAR>
 __device__ __forceinline__ void epilogue_residual_stats(const float* Os, const float* __restrict__ bias,
                                                         const float* Xin, float* Xout,  /* may alias (in-place) */
                                                         double* __restrict__ stats, int b, int y0, int x0, int Hp,
-                                                        int Wp) {
+                                                        int Wp, const float* __restrict__ res = nullptr,
+                                                        __half* __restrict__ xr = nullptr) {
     __shared__ float red[4][2][NF];
     const int t = threadIdx.x, c4 = t & 15, lane = t & 31, wid = t >> 5;
     const float4 bv = *reinterpret_cast<const float4*>(bias + 4 * c4);
@@ -46,6 +47,15 @@ __device__ __forceinline__ void epilogue_residual_stats(const float* Os, const f
         v[0] = o[0] + bv.x + xi[it].x; v[1] = o[1] + bv.y + xi[it].y;
         v[2] = o[2] + bv.z + xi[it].z; v[3] = o[3] + bv.w + xi[it].w;
         *reinterpret_cast<float4*>(Xout + pix * NF + 4 * c4) = make_float4(v[0], v[1], v[2], v[3]);
+        if (xr != nullptr) {   // last CFTM: also emit fp16(res + x), the tail's first GEMM operand (ref :70)
+            const float4 rv = *reinterpret_cast<const float4*>(res + pix * NF + 4 * c4);
+            const __half2 h0 = __floats2half2_rn(v[0] + rv.x, v[1] + rv.y);
+            const __half2 h1 = __floats2half2_rn(v[2] + rv.z, v[3] + rv.w);
+            uint2 u;
+            u.x = *reinterpret_cast<const uint32_t*>(&h0);
+            u.y = *reinterpret_cast<const uint32_t*>(&h1);
+            *reinterpret_cast<uint2*>(xr + pix * NF + 4 * c4) = u;
+        }
 #pragma unroll
         for (int e = 0; e < 4; ++e) { s[e] += v[e]; s2[e] = fmaf(v[e], v[e], s2[e]); }
     }

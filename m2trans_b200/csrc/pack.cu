@@ -32,7 +32,7 @@ int make_packed_layout(int scale, int n_blocks, PackedLayout* L) {
         L->t3w = take((size_t)256 * NF * 2);
         L->t3b = take((size_t)256 * 4);
     }
-    L->tcw = take((size_t)9 * 8 * NF * 2);
+    L->tcw = take((size_t)9 * 16 * NF * 2);
     L->total = off;
     return M2T_OK;
 }
@@ -42,7 +42,9 @@ enum PackMode {
     PK_CVT_F16,        // dst[i] = half(src[i] * (i < n_scaled ? scale : 1))
     PK_HEAD_W,         // src [64][3][3][3] -> dst [(c*9+tap)][64]
     PK_CONV3_W,        // src [O][64][3][3] -> dst [tap][Opad][64] fp16, rows >= O zero
-    PK_RELX            // src rel_h [10][C/2] (+ rel_w passed as src2) -> dst fp16 [32][C]
+    PK_RELX,           // src rel_h [10][C/2] (+ rel_w passed as src2) -> dst fp16 [32][C]
+    PK_UP_W,           // tail 1x1 conv: src [64 r^2][64] -> dst fp16 row (uv*64 + c) <- src row (c*r^2 + uv)
+    PK_UP_B            // its bias with the same row permutation (fp32)
 };
 
 __global__ void pack_kernel(int mode, const float* __restrict__ src, const float* __restrict__ src2, void* dstv,
@@ -68,6 +70,14 @@ __global__ void pack_kernel(int mode, const float* __restrict__ src, const float
             if (row < 10 && c < hc) v = src[row * hc + c];
             else if (row >= 10 && row < 20 && c >= hc) v = src2[(row - 10) * hc + (c - hc)];
             reinterpret_cast<__half*>(dstv)[i] = __float2half_rn(v);
+        } break;
+        case PK_UP_W: {     // i over dst [64 r^2][64]; p0 = r^2
+            const int k = i % NF, np = i / NF, uv = np / NF, c = np % NF;
+            reinterpret_cast<__half*>(dstv)[i] = __float2half_rn(src[(c * p0 + uv) * NF + k]);
+        } break;
+        case PK_UP_B: {     // i over dst [64 r^2]
+            const int uv = i / NF, c = i % NF;
+            reinterpret_cast<float*>(dstv)[i] = src[c * p0 + uv];
         } break;
     }
 }
@@ -110,14 +120,14 @@ int pack_weights_impl(const PackedLayout& L, const float* const* P, int n_params
     }
     const int tb = 6 + 14 * L.n_blocks;
     const int r0 = L.scale == 4 ? 2 : L.scale, N0 = NF * r0 * r0;
-    M2T_TRY(run_pack(PK_CVT_F16, P[tb], nullptr, packed + L.t0w, N0 * NF, 0, 0, 1.f, s));
-    M2T_TRY(run_pack(PK_COPY_F32, P[tb + 1], nullptr, packed + L.t0b, N0, 0, 0, 1.f, s));
+    M2T_TRY(run_pack(PK_UP_W, P[tb], nullptr, packed + L.t0w, N0 * NF, r0 * r0, 0, 1.f, s));
+    M2T_TRY(run_pack(PK_UP_B, P[tb + 1], nullptr, packed + L.t0b, N0, r0 * r0, 0, 1.f, s));
     if (L.scale == 4) {
-        M2T_TRY(run_pack(PK_CVT_F16, P[tb + 2], nullptr, packed + L.t3w, 256 * NF, 0, 0, 1.f, s));
-        M2T_TRY(run_pack(PK_COPY_F32, P[tb + 3], nullptr, packed + L.t3b, 256, 0, 0, 1.f, s));
-        M2T_TRY(run_pack(PK_CONV3_W, P[tb + 4], nullptr, packed + L.tcw, 9 * 8 * NF, 3, 8, 1.f, s));
+        M2T_TRY(run_pack(PK_UP_W, P[tb + 2], nullptr, packed + L.t3w, 256 * NF, 4, 0, 1.f, s));
+        M2T_TRY(run_pack(PK_UP_B, P[tb + 3], nullptr, packed + L.t3b, 256, 4, 0, 1.f, s));
+        M2T_TRY(run_pack(PK_CONV3_W, P[tb + 4], nullptr, packed + L.tcw, 9 * 16 * NF, 3, 16, 1.f, s));
     } else {
-        M2T_TRY(run_pack(PK_CONV3_W, P[tb + 2], nullptr, packed + L.tcw, 9 * 8 * NF, 3, 8, 1.f, s));
+        M2T_TRY(run_pack(PK_CONV3_W, P[tb + 2], nullptr, packed + L.tcw, 9 * 16 * NF, 3, 16, 1.f, s));
     }
     return M2T_OK;
 }

@@ -1,9 +1,13 @@
-// Tail (ref M2Trans_network.py:40-56, :70-76).
-//   tail_up : [global residual res + x (ref :70) ->] 1x1 conv + bias -> PixelShuffle(r) -> exact GELU,
-//             CUDA-core variant (M2T_VAR_SIMT_TAIL) writing an fp16 NHWC map at r x resolution
-//   tail_out: last 3x3 reflect conv 64->3 without bias, clamp to [0, rgb_range] (ref :74), crop to
-//             [s*H, s*W] (ref :76), written straight into the caller's fp32 NCHW output
-// PixelShuffle: out[c, r*y+u, r*x+v] = in[c*r*r + u*r + v, y, x].
+// Tail (ref M2Trans_network.py:40-56, :70-76), CUDA-core variant (M2T_VAR_SIMT_TAIL) + the border kernel
+// shared by both variants.
+//   tail_up        : 1x1 conv + bias -> PixelShuffle(r) -> exact (erff) GELU, fp16 NHWC at r x resolution
+//   reflect_border : fills the 1-pixel ring of a [B][h+2][w+2][64] tensor with the reflection of its interior
+//                    (row -1 = row 1, row h = row h-2, same for columns), i.e. padding_mode='reflect' of the
+//                    last conv (ref :48/:55) materialised once so that its loader never needs index math
+//   tail_out       : last 3x3 conv 64->3 without bias, clamp to [0, rgb_range] (ref :74), crop (ref :76),
+//                    written straight into the caller's fp32 NCHW output
+// PixelShuffle: out[c, r*y+u, r*x+v] = in[c*r*r + u*r + v, y, x]; the packed weight rows are already
+// sub-pixel-major (row (u*r+v)*64 + c), see pack.cu.
 #include "common.cuh"
 
 namespace m2t {
@@ -12,22 +16,16 @@ __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + er
 
 constexpr int TU_PX = 32;
 
-// blockDim.x = N = 64*r*r ; thread n owns output channel n of the 1x1 conv for TU_PX pixels
+// blockDim.x = N = 64*r*r ; thread n owns packed output row n of the 1x1 conv for TU_PX pixels
 __global__ void __launch_bounds__(576)
-tail_up_simt_kernel(const float* __restrict__ Xa, const float* __restrict__ Xb, const __half* __restrict__ Ain,
-                    const __half* __restrict__ Wt, const float* __restrict__ bias, __half* __restrict__ out, int h,
-                    int w, int r) {
+tail_up_simt_kernel(const __half* __restrict__ Ain, const __half* __restrict__ Wt, const float* __restrict__ bias,
+                    __half* __restrict__ out, int h, int w, int r, int pad) {
     extern __shared__ __align__(16) uint8_t smem[];
     float* As = reinterpret_cast<float*>(smem);                          // [32][64]
     __half* Os = reinterpret_cast<__half*>(smem + TU_PX * NF * 4);       // [r][32 r][64]
     const int n = threadIdx.x, N = blockDim.x;
     const long pix0 = (long)blockIdx.x * TU_PX;                          // first pixel (linear in [B,h,w])
-    for (int i = n; i < TU_PX * NF; i += N) {
-        float a;
-        if (Ain != nullptr) a = __half2float(Ain[pix0 * NF + i]);
-        else a = __half2float(__float2half_rn(Xa[pix0 * NF + i] + Xb[pix0 * NF + i]));   // fp16 GEMM operand
-        As[i] = a;
-    }
+    for (int i = n; i < TU_PX * NF; i += N) As[i] = __half2float(Ain[pix0 * NF + i]);
     float wreg[NF];
     {
         const uint4* wp = reinterpret_cast<const uint4*>(Wt + (long)n * NF);
@@ -43,8 +41,7 @@ tail_up_simt_kernel(const float* __restrict__ Xa, const float* __restrict__ Xb, 
         }
     }
     const float bn = bias[n];
-    const int r2 = r * r;
-    const int c = n / r2, uv = n - c * r2, u = uv / r, v = uv - u * r;
+    const int uv = n / NF, c = n - uv * NF, u = uv / r, v = uv - u * r;
     __syncthreads();
     for (int p = 0; p < TU_PX; ++p) {
         float acc = bn;
@@ -62,34 +59,66 @@ tail_up_simt_kernel(const float* __restrict__ Xa, const float* __restrict__ Xb, 
     const int rem = (int)(pix0 - (long)b * h * w);
     const int y = rem / w, x0 = rem - y * w;
     const int row_u4 = TU_PX * r * 8;                                    // uint4 per output row segment
+    const long opitch = (long)(w * r + 2 * pad) * NF;
     const uint4* src = reinterpret_cast<const uint4*>(Os);
     for (int i = n; i < r * row_u4; i += N) {
         const int uu = i / row_u4, k = i - uu * row_u4;
-        __half* dst = out + ((((long)b * h * r + (long)y * r + uu) * w * r) + (long)x0 * r) * NF;
+        __half* dst = out + ((long)b * (h * r + 2 * pad) + (long)y * r + uu + pad) * opitch + ((long)x0 * r + pad) * NF;
         reinterpret_cast<uint4*>(dst)[k] = src[i];
     }
 }
 
-int launch_tail_up_simt(const float* Xa, const float* Xb, const __half* Ain, const __half* Wt, const float* bias,
-                        __half* out, int B, int h, int w, int r, cudaStream_t s) {
+int launch_tail_up_simt(const __half* Ain, const __half* Wt, const float* bias, __half* out, int B, int h, int w, int r,
+                        int pad, cudaStream_t s) {
     if (w % TU_PX) { set_error("tail_up: width %d not a multiple of %d", w, TU_PX); return M2T_E_ARG; }
     if (r < 2 || r > 3) { set_error("tail_up: shuffle factor %d", r); return M2T_E_UNSUPPORTED; }
     const size_t smem = (size_t)TU_PX * NF * 4 + (size_t)r * r * TU_PX * NF * 2;
     M2T_ENSURE_SMEM(tail_up_simt_kernel, 64 * 1024);
     const long npix = (long)B * h * w;
-    tail_up_simt_kernel<<<(unsigned)(npix / TU_PX), NF * r * r, smem, s>>>(Xa, Xb, Ain, Wt, bias, out, h, w, r);
+    tail_up_simt_kernel<<<(unsigned)(npix / TU_PX), NF * r * r, smem, s>>>(Ain, Wt, bias, out, h, w, r, pad);
     M2T_LAUNCH_CHECK("tail_up_simt_kernel");
     return M2T_OK;
 }
 
-// ---- final conv ------------------------------------------------------------------------------------
+// ---- reflected border ring --------------------------------------------------------------------------------
+// One thread per (ring pixel, 16-byte chunk).  Ring pixels of a (h+2) x (w+2) frame: 2 (w+2) + 2 h.
+__global__ void reflect_border_kernel(__half* __restrict__ T, int B, int h, int w) {
+    const int ring = 2 * (w + 2) + 2 * h;
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long)B * ring * 8) return;
+    const int ch = (int)(idx & 7);
+    const long pi = idx >> 3;
+    const int b = (int)(pi / ring), k = (int)(pi - (long)b * ring);
+    int py, px;                                   // coordinates in the padded frame
+    if (k < w + 2) { py = 0; px = k; }
+    else if (k < 2 * (w + 2)) { py = h + 1; px = k - (w + 2); }
+    else if (k < 2 * (w + 2) + h) { py = k - 2 * (w + 2) + 1; px = 0; }
+    else { py = k - 2 * (w + 2) - h + 1; px = w + 1; }
+    const int iy = py - 1, ix = px - 1;           // interior coordinates in [-1, h] x [-1, w]
+    const int sy = iy < 0 ? 1 : (iy >= h ? h - 2 : iy);
+    const int sx = ix < 0 ? 1 : (ix >= w ? w - 2 : ix);
+    const long pitch = (long)(w + 2) * NF;
+    __half* base = T + (long)b * (h + 2) * pitch;
+    *reinterpret_cast<uint4*>(base + (long)py * pitch + (long)px * NF + ch * 8) =
+        *reinterpret_cast<const uint4*>(base + (long)(sy + 1) * pitch + (long)(sx + 1) * NF + ch * 8);
+}
+
+int launch_reflect_border(__half* T, int B, int h, int w, cudaStream_t s) {
+    const long total = (long)B * (2 * (w + 2) + 2 * h) * 8;
+    reflect_border_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(T, B, h, w);
+    M2T_LAUNCH_CHECK("reflect_border_kernel");
+    return M2T_OK;
+}
+
+// ---- final conv (CUDA cores) ----------------------------------------------------------------------------------
 constexpr int TO_T = 16;                 // 16x16 output pixels per CTA
 constexpr int TO_LD = NF + 8;            // halves per staged pixel
 constexpr size_t TO_SMEM = (size_t)(TO_T + 2) * (TO_T + 2) * TO_LD * 2 + 9 * 3 * NF * 4;
 
+// T: fp16 [Bc][hp+2][wp+2][64] with its reflected border ring filled; Wc packed fp16 [9][16][64] (rows 3.. zero)
 __global__ void __launch_bounds__(TO_T* TO_T)
-tail_out_kernel(const __half* __restrict__ T, const __half* __restrict__ Wc, float* __restrict__ y, int hp, int wp,
-                int hout, int wout, int b0, float rgb_range) {
+tail_out_simt_kernel(const __half* __restrict__ T, const __half* __restrict__ Wc, float* __restrict__ y, int hp, int wp,
+                     int hout, int wout, int b0, float rgb_range) {
     extern __shared__ __align__(16) uint8_t smem[];
     __half* Ts = reinterpret_cast<__half*>(smem);
     float* Ws = reinterpret_cast<float*>(smem + (size_t)(TO_T + 2) * (TO_T + 2) * TO_LD * 2);  // [9][3][64]
@@ -98,15 +127,14 @@ tail_out_kernel(const __half* __restrict__ T, const __half* __restrict__ Wc, flo
     if (y0 >= hout || x0 >= wout) return;            // tile entirely in the cropped-away padding
     for (int i = t; i < 9 * 3 * NF; i += TO_T * TO_T) {
         const int tap = i / (3 * NF), rem = i - tap * 3 * NF;
-        Ws[i] = __half2float(Wc[(tap * 8 + rem / NF) * NF + rem % NF]);     // packed [9][8][64]
+        Ws[i] = __half2float(Wc[(tap * 16 + rem / NF) * NF + rem % NF]);
     }
+    const long pitch = (long)(wp + 2) * NF;
     for (int idx = t; idx < (TO_T + 2) * (TO_T + 2) * 8; idx += TO_T * TO_T) {
         const int p = idx >> 3, ch = idx & 7;
-        int py = y0 - 1 + p / (TO_T + 2), px = x0 - 1 + p % (TO_T + 2);
-        py = py < 0 ? -py : (py >= hp ? 2 * hp - 2 - py : py);              // reflect at the PADDED frame border
-        px = px < 0 ? -px : (px >= wp ? 2 * wp - 2 - px : px);
+        const int py = y0 + p / (TO_T + 2), px = x0 + p % (TO_T + 2);       // padded-frame coordinates
         *reinterpret_cast<uint4*>(&Ts[p * TO_LD + ch * 8]) =
-            *reinterpret_cast<const uint4*>(T + (((long)bl * hp + py) * wp + px) * NF + ch * 8);
+            *reinterpret_cast<const uint4*>(T + ((long)bl * (hp + 2) + py) * pitch + (long)px * NF + ch * 8);
     }
     __syncthreads();
     const int ty = t / TO_T, tx = t % TO_T;
@@ -138,13 +166,12 @@ tail_out_kernel(const __half* __restrict__ T, const __half* __restrict__ Wc, flo
     }
 }
 
-int launch_tail_out(const __half* T, const __half* Wc, float* y, int B, int hp, int wp, int hout, int wout, int b0,
-                    int Btot, float rgb_range, cudaStream_t s) {
-    (void)Btot;
-    M2T_ENSURE_SMEM(tail_out_kernel, TO_SMEM);
-    dim3 grid(wp / TO_T, hp / TO_T, B);
-    tail_out_kernel<<<grid, TO_T * TO_T, TO_SMEM, s>>>(T, Wc, y, hp, wp, hout, wout, b0, rgb_range);
-    M2T_LAUNCH_CHECK("tail_out_kernel");
+int launch_tail_out_simt(const __half* T, const __half* Wc, float* y, int Bc, int hp, int wp, int hout, int wout,
+                         int b0, float rgb_range, cudaStream_t s) {
+    M2T_ENSURE_SMEM(tail_out_simt_kernel, TO_SMEM);
+    dim3 grid(wp / TO_T, hp / TO_T, Bc);
+    tail_out_simt_kernel<<<grid, TO_T * TO_T, TO_SMEM, s>>>(T, Wc, y, hp, wp, hout, wout, b0, rgb_range);
+    M2T_LAUNCH_CHECK("tail_out_simt_kernel");
     return M2T_OK;
 }
 
