@@ -110,6 +110,7 @@ size_t m2t_packed_offset(int scale, int n_blocks, const char* name) {
     if (sscanf(name, "body.%d.attn%d.%31s", &i, &a, what) == 3 && i >= 0 && i < n_blocks && a >= 1 && a <= 4) {
         const AttnW& A = L.blk[i].attn[a - 1];
         if (!strcmp(what, "wqkv")) return A.wqkv;
+        if (!strcmp(what, "wqkv_f")) return A.wqkv_f;
         if (!strcmp(what, "relf")) return A.relf;
         if (!strcmp(what, "relx")) return A.relx;
         return (size_t)-1;
@@ -175,7 +176,8 @@ int m2t_plan_create(const m2t_cfg* cfg, m2t_plan** out) {
     p->o_t1 = take(m2t_tail_scratch_bytes(cfg->scale, chunk, g.Hp, g.Wp));
     p->ws_bytes = off;
     const int tail_passes = (g.B + chunk - 1) / chunk;
-    p->n_launches = 1 /*head*/ + cfg->n_blocks * (1 + 4 * 4 + 1) + tail_passes * (cfg->scale == 4 ? 4 : 3);
+    const int per_block = (cfg->variant & M2T_VAR_SIMT_ATTN) ? (1 + 4 * 4 + 1) : (1 + 1 + 4 * 2 + 1);
+    p->n_launches = 1 /*head*/ + cfg->n_blocks * per_block + tail_passes * (cfg->scale == 4 ? 4 : 3);
     *out = p;
     return M2T_OK;
 }
@@ -199,8 +201,7 @@ size_t m2t_workspace_offset(const m2t_plan* plan, const char* name) {
 
 // ---- stage dispatch ------------------------------------------------------------------------------
 static int run_qkv(uint32_t variant, const __half* Z, const __half* wqkv, __half* QKV, int M, int C, cudaStream_t s) {
-    // C = 16 (branch 1) is one K step of 32-byte rows: HBM-bound, kept on the CUDA cores
-    if (!(variant & M2T_VAR_SIMT_QKV) && (C == 64 || C == 256)) return launch_qkv_umma(Z, wqkv, QKV, M, C, s);
+    if (!(variant & M2T_VAR_SIMT_QKV)) return launch_qkv_umma(Z, wqkv, QKV, M, C, s);
     return launch_gemm_simt(Z, wqkv, QKV, M, 3 * C, C, s);
 }
 static int run_attn(uint32_t variant, int C, const __half* QKV, const float* relf, const __half* relx, __half* O,
@@ -272,8 +273,27 @@ int m2t_forward(const m2t_plan* plan, const void* d_packed, const float* d_x, fl
     M2T_TRY(launch_head(d_x, reinterpret_cast<const float*>(W + L.head_w), reinterpret_cast<const float*>(W + L.head_b),
                         res, stats, g, s));
     const float* Xin = res;
+    // Default path: Haar-folded weights + branch glue fused into the attention epilogue (11 launches per CFTM).
+    // The CUDA-core attention variant keeps the explicit prep / post kernels (18 launches per CFTM).
+    const bool fused = !(var & M2T_VAR_SIMT_ATTN);
     for (int i = 0; i < plan->cfg.n_blocks; ++i) {
         M2T_TRY(launch_stats_finalize(stats + i * stat_stride, munorm, g.B, npix, s));
+        if (fused) {
+            __half* Tcur = Z;      // t_k in space-to-depth order, ping-pong between the Z and O buffers
+            __half* Tnxt = O;
+            M2T_TRY(launch_branch_prep(0, 0, Xin, munorm, Y, Tcur, g, s));          // t_1 = n_1 (ref :137-139)
+            for (int a = 0; a < 4; ++a) {
+                const int lv = branch_level(a), C = branch_ch(a);
+                const int h = g.Hp >> lv, w = g.Wp >> lv;
+                const AttnW& A = L.blk[i].attn[a];
+                M2T_TRY(run_qkv(var, Tcur, reinterpret_cast<const __half*>(W + A.wqkv_f), QKV, g.B * h * w, C, s));
+                AttnFuse fz;
+                fz.T = Tcur; fz.Y = Y; fz.X = Xin; fz.munorm = munorm; fz.Tnext = a < 3 ? Tnxt : nullptr;
+                fz.branch = a; fz.Hp = g.Hp; fz.Wp = g.Wp;
+                M2T_TRY(launch_attn_umma(C, QKV, reinterpret_cast<const __half*>(W + A.relx), nullptr, g.B, h, w, s, &fz));
+                __half* tmp = Tcur; Tcur = Tnxt; Tnxt = tmp;
+            }
+        } else
         for (int a = 0; a < 4; ++a) {
             const int lv = branch_level(a), C = branch_ch(a);
             const int h = g.Hp >> lv, w = g.Wp >> lv;

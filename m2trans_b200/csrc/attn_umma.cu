@@ -60,10 +60,11 @@ __device__ __forceinline__ WinCoord win_coord(int wi, int nwx, int per_img) {
     return c;
 }
 
-template <int C>
+template <int C, bool FUSE>
 __global__ void __launch_bounds__(192, 1)
 attn_umma_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapKV,
-                 const __grid_constant__ CUtensorMap mapR, __half* __restrict__ O, int h, int w, int nwin) {
+                 const __grid_constant__ CUtensorMap mapR, __half* __restrict__ O, int h, int w, int nwin,
+                 const AttnFuse fz) {
     using CF = AtCfg<C>;
     constexpr int CB = CF::CB, NBLK = CF::NBLK, STAGES = CF::STAGES;
     constexpr uint32_t ROWB = CF::ROWB;
@@ -244,6 +245,74 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
             const int wi = 2 * p + half;
             const bool valid = wi < nwin;
             const WinCoord wc = win_coord(valid ? wi : 2 * p, nwx, per_img);
+            if constexpr (FUSE) {
+                // Fused branch glue (ref :139-161).  With the Haar transforms folded into the qkv weights the
+                // accumulator row IS IWT^L(attention) in space-to-depth order: column s*16+k belongs to pixel
+                // s = dy*2^L + dx of this level pixel's 2^L x 2^L block.
+                //   y_k = O' + t_k            -> Y[..., 16k..16k+15]                    (ref :139,:145,:153,:161)
+                //   t_{k+1} = (n_{k+1} + y_k)/2 -> Tnext in the next level's space-to-depth order (ref :141,:147,:155)
+                constexpr int LV = C == 16 ? 0 : (C == 64 ? 1 : 2);
+                constexpr int S = 1 << LV;
+                const int ly = wc.y + (qi >> 3), lx = wc.x + (qi & 7);
+                const __half* trow = fz.T + (((long)wc.b * h + ly) * w + lx) * C;
+                const int br = fz.branch;
+                const int lvn = br == 0 ? 1 : 2, Sn = 1 << lvn, Cn = NB * Sn * Sn;
+                float mu[NB], rs[NB];
+                if (fz.Tnext != nullptr) {
+#pragma unroll
+                    for (int e = 0; e < NB; ++e) {
+                        const float2 mr = __ldg(&fz.munorm[wc.b * NF + NB * (br + 1) + e]);
+                        mu[e] = mr.x; rs[e] = mr.y;
+                    }
+                }
+#pragma unroll 1
+                for (int s = 0; s < S * S; ++s) {
+                    uint32_t r[16];
+                    tmem_ld16(tmem_base + lane_sel + TM_O + s * NB, r);
+                    uint4 tk[2];
+                    tk[0] = *reinterpret_cast<const uint4*>(trow + s * NB);
+                    tk[1] = *reinterpret_cast<const uint4*>(trow + s * NB + 8);
+                    tmem_ld_wait();
+                    if (valid) {
+                        const int fy = ly * S + s / S, fx = lx * S + s % S;
+                        const long pix = ((long)wc.b * fz.Hp + fy) * fz.Wp + fx;
+                        float yv[NB];
+                        const __half2* th = reinterpret_cast<const __half2*>(tk);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const float2 tf = __half22float2(th[e]);
+                            yv[2 * e] = fmaf(__uint_as_float(r[2 * e]), inv, tf.x);
+                            yv[2 * e + 1] = fmaf(__uint_as_float(r[2 * e + 1]), inv, tf.y);
+                        }
+                        uint4 yo[2];
+                        __half2* yh = reinterpret_cast<__half2*>(yo);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) yh[e] = __floats2half2_rn(yv[2 * e], yv[2 * e + 1]);
+                        __half* yp = fz.Y + pix * NF + NB * br;
+                        *reinterpret_cast<uint4*>(yp) = yo[0];
+                        *reinterpret_cast<uint4*>(yp + 8) = yo[1];
+                        if (fz.Tnext != nullptr) {
+                            const float4* xp = reinterpret_cast<const float4*>(fz.X + pix * NF + NB * (br + 1));
+                            uint4 to[2];
+                            __half2* tnh = reinterpret_cast<__half2*>(to);
+#pragma unroll
+                            for (int v = 0; v < 4; ++v) {
+                                const float4 xv = xp[v];
+                                const float t0 = 0.5f * ((xv.x - mu[4 * v]) * rs[4 * v] + yv[4 * v]);
+                                const float t1 = 0.5f * ((xv.y - mu[4 * v + 1]) * rs[4 * v + 1] + yv[4 * v + 1]);
+                                const float t2 = 0.5f * ((xv.z - mu[4 * v + 2]) * rs[4 * v + 2] + yv[4 * v + 2]);
+                                const float t3 = 0.5f * ((xv.w - mu[4 * v + 3]) * rs[4 * v + 3] + yv[4 * v + 3]);
+                                tnh[2 * v] = __floats2half2_rn(t0, t1);
+                                tnh[2 * v + 1] = __floats2half2_rn(t2, t3);
+                            }
+                            const int sn = (fy & (Sn - 1)) * Sn + (fx & (Sn - 1));
+                            __half* tp = fz.Tnext + ((((long)wc.b * (fz.Hp >> lvn)) + (fy >> lvn)) * (fz.Wp >> lvn) + (fx >> lvn)) * Cn + sn * NB;
+                            *reinterpret_cast<uint4*>(tp) = to[0];
+                            *reinterpret_cast<uint4*>(tp + 8) = to[1];
+                        }
+                    }
+                }
+            } else {
             __half* orow = O + (((long)wc.b * h + wc.y + (qi >> 3)) * w + wc.x + (qi & 7)) * C;
             constexpr int OCH = C < 32 ? C : 32;
 #pragma unroll 1
@@ -267,6 +336,7 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
                     }
                 }
             }
+            }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(o_empty);
@@ -278,7 +348,8 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
 }
 
 template <int C>
-static int launch_attn_umma_c(const __half* QKV, const __half* relx, __half* O, int B, int h, int w, cudaStream_t s) {
+static int launch_attn_umma_c(const __half* QKV, const __half* relx, __half* O, int B, int h, int w, cudaStream_t s,
+                              const AttnFuse* fuse) {
     using CF = AtCfg<C>;
     CUtensorMap mapQ, mapKV, mapR;
     const uint64_t dims[4] = {(uint64_t)3 * C, (uint64_t)w, (uint64_t)h, (uint64_t)B};
@@ -296,20 +367,26 @@ static int launch_attn_umma_c(const __half* QKV, const __half* relx, __half* O, 
         const uint32_t box[2] = {(uint32_t)CF::CB, 32};
         M2T_TRY(make_tensor_map(&mapR, relx, 2, 2, d2, s2, box, CF::TMA_SWZ));
     }
-    M2T_ENSURE_SMEM(attn_umma_kernel<C>, CF::SMEM);
     const int nwin = B * (h / BLK) * (w / BLK);
     const int npairs = (nwin + 1) / 2;
     const int grid = npairs < device_sm_count() ? npairs : device_sm_count();
-    attn_umma_kernel<C><<<grid, 192, CF::SMEM, s>>>(mapQ, mapKV, mapR, O, h, w, nwin);
+    if (fuse != nullptr) {
+        M2T_ENSURE_SMEM((attn_umma_kernel<C, true>), CF::SMEM);
+        attn_umma_kernel<C, true><<<grid, 192, CF::SMEM, s>>>(mapQ, mapKV, mapR, O, h, w, nwin, *fuse);
+    } else {
+        M2T_ENSURE_SMEM((attn_umma_kernel<C, false>), CF::SMEM);
+        attn_umma_kernel<C, false><<<grid, 192, CF::SMEM, s>>>(mapQ, mapKV, mapR, O, h, w, nwin, AttnFuse{});
+    }
     M2T_LAUNCH_CHECK("attn_umma_kernel");
     return M2T_OK;
 }
 
-int launch_attn_umma(int C, const __half* QKV, const __half* relx, __half* O, int B, int h, int w, cudaStream_t s) {
+int launch_attn_umma(int C, const __half* QKV, const __half* relx, __half* O, int B, int h, int w, cudaStream_t s,
+                     const AttnFuse* fuse) {
     if (h % BLK || w % BLK) { set_error("attn: %dx%d is not a multiple of the 8x8 block", h, w); return M2T_E_ARG; }
-    if (C == 16) return launch_attn_umma_c<16>(QKV, relx, O, B, h, w, s);
-    if (C == 64) return launch_attn_umma_c<64>(QKV, relx, O, B, h, w, s);
-    if (C == 256) return launch_attn_umma_c<256>(QKV, relx, O, B, h, w, s);
+    if (C == 16) return launch_attn_umma_c<16>(QKV, relx, O, B, h, w, s, fuse);
+    if (C == 64) return launch_attn_umma_c<64>(QKV, relx, O, B, h, w, s, fuse);
+    if (C == 256) return launch_attn_umma_c<256>(QKV, relx, O, B, h, w, s, fuse);
     set_error("attn: unsupported channel count %d", C);
     return M2T_E_UNSUPPORTED;
 }

@@ -61,6 +61,7 @@ static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 // Byte offsets into the packed weight blob (all 256-byte aligned).
 struct AttnW {
     size_t wqkv;   // fp16 [3C][C]   rows 0..C-1 (q) pre-multiplied by C^-1/2 (exact: power of two)
+    size_t wqkv_f; // fp16 [3C][C]   the same with the Haar DWT folded into the columns and the IWT into the v rows
     size_t relf;   // fp32 [20][C/2] rows 0..9 rel_h, rows 10..19 rel_w
     size_t relx;   // fp16 [32][C]   rows 0..9 [rel_h|0], 10..19 [0|rel_w], 20..31 zero (MMA operand form)
 };
@@ -76,7 +77,8 @@ struct PackedLayout {
     BlockW blk[64];
     size_t t0w, t0b; // fp16 [N0][64], fp32 [N0]      N0 = 64*r0^2
     size_t t3w, t3b; // x4 only: fp16 [256][64], fp32 [256]
-    size_t tcw;      // fp16 [9][8][64]  final 3x3 conv, rows 3..7 zero
+    size_t tcw;      // fp16 [9][16][64] final 3x3 conv, rows 3..15 zero
+    size_t fold_scratch;
     size_t total;
 };
 int make_packed_layout(int scale, int n_blocks, PackedLayout* out);
@@ -117,8 +119,20 @@ int launch_attn_simt(int C, const __half* QKV, const float* relf, __half* O, int
                      cudaStream_t s);
 
 // attn_umma.cu : same contract on tcgen05 (relx: fp16 [32][C] MMA-operand form of the rel tables)
+// Optional fused branch glue for the tensor-core attention epilogue (ref :139-161): instead of storing O it
+// writes y_k = O' + t_k into Y and the next branch's t_{k+1} = (n_{k+1} + y_k)/2 into Tnext.  Requires the
+// Haar-folded qkv weights (pack.cu) and space-to-depth T tensors.
+struct AttnFuse {
+    const __half* T;        // this branch's input t_k, space-to-depth fp16 [B,h,w,C]
+    __half* Y;              // cat[y1..y4] fp16 NHWC [B,Hp,Wp,64]
+    const float* X;         // residual stream fp32 NHWC [B,Hp,Wp,64]
+    const float2* munorm;   // InstanceNorm (mean, rstd) [B][64]
+    __half* Tnext;          // t_{k+1} space-to-depth at the next branch's level, or nullptr after branch 4
+    int branch;             // 0..3
+    int Hp, Wp;
+};
 int launch_attn_umma(int C, const __half* QKV, const __half* relx, __half* O, int B, int h, int w,
-                     cudaStream_t s);
+                     cudaStream_t s, const AttnFuse* fuse = nullptr);
 
 // conv_simt.cu : X_out = conv3x3_zero(Y) + bias + X_in, plus InstanceNorm partial sums
 // res/xr (optional): also write xr = fp16(Xout + res), the tail's first GEMM operand (ref :70)

@@ -1,14 +1,14 @@
-// tcgen05 GEMM for the TBlock qkv 1x1 conv (ref M2Trans_network.py:307) at C = 64 and C = 256:
+// tcgen05 GEMM for the TBlock qkv 1x1 conv (ref M2Trans_network.py:307) at C = 16, 64 and 256:
 //   QKV[m][n] = sum_k Z[m][k] * Wqkv[n][k]      Z fp16 [M][C], Wqkv fp16 [3C][C], QKV fp16 [M][3C]
 // Persistent, warp-specialised CTAs (192 threads):
 //   warp 4  : TMA producer -- the CTA's weight slab (NT x C, resident for the CTA's lifetime), then a ring of
-//             128 x 64 activation tiles (128-byte-swizzled, K-major)
+//             128-row activation tiles in 64-channel K blocks (128-byte swizzle; 32-byte swizzle for C = 16)
 //   warp 5  : single-thread tcgen05.mma issue, M=128 x N=NT x K=16 per instruction, fp32 accumulators in TMEM
 //             (two accumulators of 256 columns: the epilogue of tile i overlaps the MMAs of tile i+1)
 //   warps 0-3: epilogue -- tcgen05.ld, fp32 -> fp16, 16-byte stores
 // C = 256: the 768 output channels are split into q / k / v slabs of NT = 256; CTA c owns slab c % 3, so the
 // 128 KB slab is read from L2 once per CTA and every 64 KB activation tile feeds 16 x 128 cycles of MMA
-// (32 B/clk/SM, under the ~42 B/clk/SM L2->SM ceiling of B300_MICROARCH.md).  C = 64: one slab of 192.
+// (32 B/clk/SM, under the ~42 B/clk/SM L2->SM ceiling of B300_MICROARCH.md).  C = 64 / 16: one slab (192 / 48).
 #include "common.cuh"
 #include "tma.cuh"
 #include "umma.cuh"
@@ -17,14 +17,23 @@ namespace m2t {
 
 template <int C>
 struct QkvCfg {
-    static constexpr int NT = C == 256 ? 256 : 192;
+    static constexpr int CB = C < 64 ? C : 64;               // channels per K block
+    static constexpr int KB = C / CB;
+    static constexpr int KSTEPS = CB / 16;
+    static constexpr uint32_t ROWB = CB * 2;                  // bytes per row: 32 or 128
+    static constexpr uint64_t LAYOUT = CB == 64 ? UMMA_LAYOUT_SW128 : UMMA_LAYOUT_SW32;
+    static constexpr int TMA_SWZ = CB == 64 ? 3 : 1;
+    static constexpr uint32_t SBO = 8 * ROWB;
+    static constexpr int NT = C == 256 ? 256 : 3 * C;
     static constexpr int NCHUNK = 3 * C / NT;
-    static constexpr int KB = C / 64;                       // 64-wide K blocks (one 128-byte swizzle row each)
+    static constexpr int OCH = NT % 32 == 0 ? 32 : 16;       // epilogue column chunk
     static constexpr int STAGES = 4;
-    static constexpr uint32_t A_STAGE = 128 * 128;           // 128 rows x 128 B
-    static constexpr uint32_t B_BLOCK = NT * 128;            // NT rows x 128 B
-    static constexpr uint32_t B_BYTES = KB * B_BLOCK;
-    static constexpr uint32_t SMEM = 1024 + B_BYTES + STAGES * A_STAGE + 256;
+    static constexpr uint32_t A_STAGE = 128 * ROWB;
+    static constexpr uint32_t B_BLOCK = NT * ROWB;
+    static constexpr uint32_t B_BYTES = (KB * B_BLOCK + 1023) / 1024 * 1024;
+    static constexpr uint32_t SMEM_MIN = 1024 + B_BYTES + STAGES * A_STAGE + 256;
+    // every CTA allocates all 512 TMEM columns: never let two share an SM
+    static constexpr uint32_t SMEM = SMEM_MIN < 120 * 1024 ? 120 * 1024 : SMEM_MIN;
 };
 
 template <int C>
@@ -32,7 +41,7 @@ __global__ void __launch_bounds__(192, 1)
 qkv_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW,
                 __half* __restrict__ out, int M) {
     using CF = QkvCfg<C>;
-    constexpr int NT = CF::NT, KB = CF::KB, STAGES = CF::STAGES;
+    constexpr int NT = CF::NT, KB = CF::KB, STAGES = CF::STAGES, CB = CF::CB;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
@@ -67,15 +76,15 @@ qkv_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 
     if (warp == 4) {
         if (lane == 0) {
-            mbar_expect_tx(bfull, CF::B_BYTES);
-            for (int kb = 0; kb < KB; ++kb) tma_load_2d(sB + kb * CF::B_BLOCK, &mapW, bfull, kb * 64, chunk * NT);
+            mbar_expect_tx(bfull, KB * CF::B_BLOCK);
+            for (int kb = 0; kb < KB; ++kb) tma_load_2d(sB + kb * CF::B_BLOCK, &mapW, bfull, kb * CB, chunk * NT);
             uint32_t it = 0;
             for (int mt = first; mt < num_mt; mt += stride) {
                 for (int kb = 0; kb < KB; ++kb, ++it) {
                     const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
                     mbar_wait(&empty[s], ph ^ 1);
                     mbar_expect_tx(&full[s], CF::A_STAGE);
-                    tma_load_2d(sA + s * CF::A_STAGE, &mapA, &full[s], kb * 64, mt * 128);
+                    tma_load_2d(sA + s * CF::A_STAGE, &mapA, &full[s], kb * CB, mt * 128);
                 }
             }
         }
@@ -95,9 +104,9 @@ qkv_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                     const uint32_t a_addr = base + CF::B_BYTES + s * CF::A_STAGE;
                     const uint32_t b_addr = base + kb * CF::B_BLOCK;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const uint64_t da = umma_smem_desc(a_addr + k * 32, 16, 1024, UMMA_LAYOUT_SW128);
-                        const uint64_t db = umma_smem_desc(b_addr + k * 32, 16, 1024, UMMA_LAYOUT_SW128);
+                    for (int k = 0; k < CF::KSTEPS; ++k) {
+                        const uint64_t da = umma_smem_desc(a_addr + k * 32, 16, CF::SBO, CF::LAYOUT);
+                        const uint64_t db = umma_smem_desc(b_addr + k * 32, 16, CF::SBO, CF::LAYOUT);
                         umma_f16_ss(tmem_base + acc * 256, da, db, idesc, (kb | k) ? 1u : 0u);
                     }
                     umma_commit(&empty[s]);
@@ -113,14 +122,16 @@ qkv_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             tc_fence_after();
             const int row = mt * 128 + warp * 32 + lane;
             __half* orow = out + (long)row * (3 * C) + chunk * NT;
+            constexpr int OCH = CF::OCH;
 #pragma unroll 1
-            for (int c0 = 0; c0 < NT; c0 += 32) {
-                uint32_t r[32];
-                tmem_ld32(tmem_base + acc * 256 + c0 + ((uint32_t)(warp * 32) << 16), r);
+            for (int c0 = 0; c0 < NT; c0 += OCH) {
+                uint32_t r[OCH];
+                if constexpr (OCH == 32) tmem_ld32(tmem_base + acc * 256 + c0 + ((uint32_t)(warp * 32) << 16), r);
+                else tmem_ld16(tmem_base + acc * 256 + c0 + ((uint32_t)(warp * 32) << 16), r);
                 tmem_ld_wait();
                 if (row < M) {
 #pragma unroll
-                    for (int v = 0; v < 4; ++v) {
+                    for (int v = 0; v < OCH / 8; ++v) {
                         uint4 u;
                         uint32_t* pu = reinterpret_cast<uint32_t*>(&u);
 #pragma unroll
@@ -149,13 +160,13 @@ static int launch_qkv_umma_c(const __half* Z, const __half* Wqkv, __half* QKV, i
     CUtensorMap mapA, mapW;
     {
         const uint64_t dims[2] = {(uint64_t)C, (uint64_t)M}, str[2] = {2, (uint64_t)C * 2};
-        const uint32_t box[2] = {64, 128};
-        M2T_TRY(make_tensor_map(&mapA, Z, 2, 2, dims, str, box, 3));
+        const uint32_t box[2] = {(uint32_t)CF::CB, 128};
+        M2T_TRY(make_tensor_map(&mapA, Z, 2, 2, dims, str, box, CF::TMA_SWZ));
     }
     {
         const uint64_t dims[2] = {(uint64_t)C, (uint64_t)3 * C}, str[2] = {2, (uint64_t)C * 2};
-        const uint32_t box[2] = {64, (uint32_t)CF::NT};
-        M2T_TRY(make_tensor_map(&mapW, Wqkv, 2, 2, dims, str, box, 3));
+        const uint32_t box[2] = {(uint32_t)CF::CB, (uint32_t)CF::NT};
+        M2T_TRY(make_tensor_map(&mapW, Wqkv, 2, 2, dims, str, box, CF::TMA_SWZ));
     }
     M2T_ENSURE_SMEM(qkv_umma_kernel<C>, CF::SMEM);
     const int num_mt = (M + 127) / 128;
@@ -168,9 +179,10 @@ static int launch_qkv_umma_c(const __half* Z, const __half* Wqkv, __half* QKV, i
 }
 
 int launch_qkv_umma(const __half* Z, const __half* Wqkv, __half* QKV, int M, int C, cudaStream_t s) {
+    if (C == 16) return launch_qkv_umma_c<16>(Z, Wqkv, QKV, M, s);
     if (C == 64) return launch_qkv_umma_c<64>(Z, Wqkv, QKV, M, s);
     if (C == 256) return launch_qkv_umma_c<256>(Z, Wqkv, QKV, M, s);
-    set_error("qkv_umma: C=%d has no tensor-core variant", C);
+    set_error("qkv_umma: unsupported channel count %d", C);
     return M2T_E_UNSUPPORTED;
 }
 

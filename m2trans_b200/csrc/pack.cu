@@ -18,6 +18,7 @@ int make_packed_layout(int scale, int n_blocks, PackedLayout* L) {
         for (int a = 0; a < 4; ++a) {
             const int C = branch_ch(a);
             L->blk[i].attn[a].wqkv = take((size_t)3 * C * C * 2);
+            L->blk[i].attn[a].wqkv_f = take((size_t)3 * C * C * 2);
             L->blk[i].attn[a].relf = take((size_t)20 * (C / 2) * 4);
             L->blk[i].attn[a].relx = take((size_t)32 * C * 2);
         }
@@ -33,6 +34,7 @@ int make_packed_layout(int scale, int n_blocks, PackedLayout* L) {
         L->t3b = take((size_t)256 * 4);
     }
     L->tcw = take((size_t)9 * 16 * NF * 2);
+    L->fold_scratch = take((size_t)768 * 256 * 4);   // fp32 staging for the Haar folding at pack time
     L->total = off;
     return M2T_OK;
 }
@@ -82,6 +84,45 @@ __global__ void pack_kernel(int mode, const float* __restrict__ src, const float
     }
 }
 
+// ---- Haar folding --------------------------------------------------------------------------------------------
+// DWT and IWT (ref :203-209, :223-232) are fixed orthogonal maps on the 4^L pixels of a 2^L x 2^L block, so they
+// commute into the 1x1 qkv conv: with T the "space-to-depth" tensor (channel s*16+k = pixel s of the block,
+// s = dy*2^L + dx, base channel k) and Z = DWT^L(t) = G^T T,
+//     q,k = W_{q,k} Z = (W_{q,k} G^T) T          v' = G v = (G W_v G^T) T
+// and the attention output computed from v' is IWT^L(attention output) in space-to-depth order.  The engine
+// therefore never runs a Haar butterfly: g[s][band] = Hf[b2][P(s)] * Hf[b1][p(s)] is folded into the weights here
+// (in fp32, one fp16 rounding at the end).
+__device__ __forceinline__ float haar_g(int L, int s, int band) {
+    // Hf[band][pos], pos = dy + 2*dx (a,b,c,d of ref :204-207), without the 1/2
+    const int sgn[4][4] = {{1, 1, 1, 1}, {-1, -1, 1, 1}, {-1, 1, -1, 1}, {1, -1, -1, 1}};
+    if (L == 0) return 1.f;
+    if (L == 1) { const int dy = s >> 1, dx = s & 1; return 0.5f * sgn[band][dy + 2 * dx]; }
+    const int dy = s >> 2, dx = s & 3;
+    const int P = (dy >> 1) + 2 * (dx >> 1), p = (dy & 1) + 2 * (dx & 1);
+    return 0.25f * sgn[band >> 2][P] * sgn[band & 3][p];
+}
+
+// step 1: rows of v: tmp[(s_o,k_o)][j] = sum_band g[s_o][band] * W[2C + band*16 + k_o][j]; q,k rows copied
+__global__ void fold_rows_kernel(const float* __restrict__ W, float* __restrict__ tmp, int C, int L) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 3 * C * C) return;
+    const int n = i / C, j = i - n * C;
+    if (n < 2 * C) { tmp[i] = W[i]; return; }
+    const int nb = C / NB, so = (n - 2 * C) / NB, ko = (n - 2 * C) % NB;
+    float acc = 0.f;
+    for (int band = 0; band < nb; ++band) acc = fmaf(haar_g(L, so, band), W[(long)(2 * C + band * NB + ko) * C + j], acc);
+    tmp[i] = acc;
+}
+// step 2: columns of all rows: out[n][(s,k)] = sum_band tmp[n][band*16 + k] * g[s][band]; q rows scaled
+__global__ void fold_cols_kernel(const float* __restrict__ tmp, __half* __restrict__ out, int C, int L, float qscale) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 3 * C * C) return;
+    const int n = i / C, j = i - n * C, nb = C / NB, s = j / NB, k = j % NB;
+    float acc = 0.f;
+    for (int band = 0; band < nb; ++band) acc = fmaf(tmp[(long)n * C + band * NB + k], haar_g(L, s, band), acc);
+    out[i] = __float2half_rn(acc * (n < C ? qscale : 1.f));
+}
+
 static int run_pack(int mode, const float* src, const float* src2, void* dst, int n, int p0, int p1, float scale,
                     cudaStream_t s) {
     pack_kernel<<<cdiv(n, 256), 256, 0, s>>>(mode, src, src2, dst, n, p0, p1, scale);
@@ -111,6 +152,14 @@ int pack_weights_impl(const PackedLayout& L, const float* const* P, int n_params
             const AttnW& A = L.blk[i].attn[a];
             const float qscale = 1.0f / sqrtf((float)C);    // ref :311 q * head_ch^-0.5 ; C in {16,64,256}
             M2T_TRY(run_pack(PK_CVT_F16, wq, nullptr, packed + A.wqkv, 3 * C * C, C * C, 0, qscale, s));
+            {   // Haar-folded copy (stream order makes the shared fp32 scratch safe to reuse)
+                float* tmp = reinterpret_cast<float*>(packed + L.fold_scratch);
+                fold_rows_kernel<<<cdiv(3 * C * C, 256), 256, 0, s>>>(wq, tmp, C, branch_level(a));
+                M2T_LAUNCH_CHECK("fold_rows_kernel");
+                fold_cols_kernel<<<cdiv(3 * C * C, 256), 256, 0, s>>>(tmp, reinterpret_cast<__half*>(packed + A.wqkv_f), C,
+                                                                     branch_level(a), qscale);
+                M2T_LAUNCH_CHECK("fold_cols_kernel");
+            }
             M2T_TRY(run_pack(PK_COPY_F32, relh, nullptr, packed + A.relf, 10 * hc, 0, 0, 1.f, s));
             M2T_TRY(run_pack(PK_COPY_F32, relw, nullptr, packed + A.relf + (size_t)10 * hc * 4, 10 * hc, 0, 0, 1.f, s));
             M2T_TRY(run_pack(PK_RELX, relh, relw, packed + A.relx, 32 * C, C, 0, 1.f, s));

@@ -130,7 +130,8 @@ def test_full_size_cfg2_properties():
     assert p >= PSNR_MIN and m <= MAXABS_MAX
 
 
-@pytest.mark.parametrize("C,M", [(64, 64), (64, 4096), (64, 1984), (256, 64), (256, 1024), (256, 16384 + 192)])
+@pytest.mark.parametrize("C,M", [(16, 64), (16, 4096 + 64), (64, 64), (64, 4096), (64, 1984), (256, 64), (256, 1024),
+                                 (256, 16384 + 192)])
 def test_stage_qkv_tensor_core_vs_cuda_core(C, M):
     """tcgen05 qkv GEMM against the CUDA-core variant and torch (same fp16 operands, fp32 accumulate)."""
     from m2trans_b200 import _lib
