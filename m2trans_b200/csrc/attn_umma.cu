@@ -2,23 +2,28 @@
 //
 // One work item = a PAIR of 8x8 query windows, stacked into one M = 128 tile (rows 0-63 window A, 64-127
 // window B), so every TMEM lane / epilogue thread owns one query row.
-//   S  = [Qa;Qb] . [Ka;Kb]^T         M=128, N=224 (2 x 100 keys padded to 112), K = C     (block-diagonal use:
+//   S  = [Qa;Qb] . [Ka;Kb]^T         M=128, N=208 (2 x 100 keys padded to 104), K = C     (block-diagonal use:
 //                                     row m only reads the 100 columns of its own window)
-//   S' = [Qa;Qb] . Rel^T              N = 32 extra columns: q[:C/2].rel_h[r] (cols 224..233) and
-//                                     q[C/2:].rel_w[c] (cols 234..243): the reference adds rel to K, also at the
+//   S' = [Qa;Qb] . Rel^T              N = 32 extra columns: q[:C/2].rel_h[r] (cols 208..217) and
+//                                     q[C/2:].rel_w[c] (cols 218..227): the reference adds rel to K, also at the
 //                                     zero-padded keys (ref :322-325); q.(k+rel) = q.k + q.rel
 //   P  = exp2((S + rel terms - max) * log2e), unnormalised, fp16, written K-major/128B-swizzled to smem
-//   O  = P . [Va;Vb]                  M=128, N = C, K = 224 keys; rows scaled by 1/sum in the epilogue
+//   O  = P . [Va;Vb]                  M=128, N = C, K = 208 keys; rows scaled by 1/sum in the epilogue
 // Keys/values outside the frame are TMA out-of-bounds zero fill = F.unfold's zero padding (ref :313-317);
 // window partition / reverse (ref :310, :332) are TMA box coordinates and the store address.
-// Operands stream through one ring in 64-channel blocks (Q 128 rows + K 224 rows, then V 224 rows), so the
+// Operands stream through one ring in 64-channel blocks (Q 128 rows + K 208 rows, then V 208 rows), so the
 // C = 256 case (288 KB of Q/K/V per pair) fits and loads overlap the previous pair's softmax / PV.
 // Warp roles (192 threads): warps 0-3 softmax + epilogue (thread = query row), warp 4 TMA, warp 5 MMA issue.
+//
+// FUSE = true additionally folds the CFTM branch glue (ref :139-161) into the epilogue, see AttnFuse.
 #include "common.cuh"
 #include "tma.cuh"
 #include "umma.cuh"
 
 namespace m2t {
+
+constexpr int WR = 104;                                       // key rows per window (100 + 4 zero rows)
+constexpr int NKP = 2 * WR;                                   // 208 key rows / S columns per pair
 
 template <int C>
 struct AtCfg {
@@ -29,19 +34,22 @@ struct AtCfg {
     static constexpr int TMA_SWZ = CB == 64 ? 3 : 1;
     static constexpr uint32_t SBO = 8 * ROWB;
     static constexpr uint32_t QB = 128 * ROWB;                // Q block (two windows x 64 rows)
-    static constexpr uint32_t KVB = 224 * ROWB;               // K or V block (two windows x 112 rows)
-    static constexpr uint32_t WIN_B = 112 * ROWB;             // offset of window B's keys
+    static constexpr uint32_t KVB = NKP * ROWB;               // K or V block
+    static constexpr uint32_t WIN_B = WR * ROWB;              // offset of window B's keys
     static constexpr uint32_t STAGE = (QB + KVB + 1023) / 1024 * 1024;
     static constexpr int STAGES = C == 16 ? 4 : 3;
     static constexpr uint32_t REL_BLOCK = 32 * ROWB;
     static constexpr uint32_t OFF_P = STAGES * STAGE;
     static constexpr uint32_t OFF_REL = OFF_P + 4 * 16384;
-    static constexpr uint32_t OFF_BAR = OFF_REL + NBLK * REL_BLOCK;
-    // at least 120 KB so that two CTAs (each allocating all 512 TMEM columns) never share an SM
-    static constexpr uint32_t SMEM_MIN = 1024 + OFF_BAR + 256;
-    static constexpr uint32_t SMEM = SMEM_MIN < 120 * 1024 ? 120 * 1024 : SMEM_MIN;
+    static constexpr uint32_t OFF_BAR = OFF_REL + (NBLK * REL_BLOCK + 1023) / 1024 * 1024;
+    static constexpr uint32_t SMEM = 1024 + OFF_BAR + 256;
     static constexpr uint32_t TX_QK = 2 * 64 * ROWB + 2 * 100 * ROWB;
     static constexpr uint32_t TX_V = 2 * 100 * ROWB;
+    // TMEM columns: S [0,208) | rel [208,240) | O.  C = 16 fits 256 columns, so two CTAs can share an SM.
+    static constexpr uint32_t TM_REL = NKP;
+    static constexpr uint32_t TM_O = C == 16 ? 240 : 256;
+    static constexpr uint32_t TM_COLS = C == 16 ? 256 : 512;
+    static constexpr int MIN_CTAS = C == 16 ? 2 : 1;
 };
 
 __device__ __forceinline__ float fast_exp2(float x) {
@@ -60,8 +68,14 @@ __device__ __forceinline__ WinCoord win_coord(int wi, int nwx, int per_img) {
     return c;
 }
 
+template <int G>
+struct GluePre {       // prefetched operands of G sub-pixels of the fused glue
+    uint4 tk[2 * G];
+    float4 xv[4 * G];
+};
+
 template <int C, bool FUSE>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(192, AtCfg<C>::MIN_CTAS)
 attn_umma_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapKV,
                  const __grid_constant__ CUtensorMap mapR, __half* __restrict__ O, int h, int w, int nwin,
                  const AttnFuse fz) {
@@ -85,15 +99,15 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
     const int nwx = w / BLK, per_img = (h / BLK) * nwx;
     const int npairs = (nwin + 1) / 2;
 
-    // zero P (its off-diagonal / padding columns stay zero for ever) and the 12 padding key rows per window
+    // zero P (its off-diagonal / padding columns stay zero for ever) and the 4 padding key rows per window
     for (uint32_t i = tid * 16; i < 4 * 16384; i += 192 * 16) *reinterpret_cast<uint4*>(sm + CF::OFF_P + i) = make_uint4(0, 0, 0, 0);
     for (int s = 0; s < STAGES; ++s)
         for (int half = 0; half < 2; ++half) {
             uint8_t* pad = sm + s * CF::STAGE + CF::QB + half * CF::WIN_B + 100 * ROWB;
-            for (uint32_t i = tid * 16; i < 12 * ROWB; i += 192 * 16) *reinterpret_cast<uint4*>(pad + i) = make_uint4(0, 0, 0, 0);
+            for (uint32_t i = tid * 16; i < (WR - 100) * ROWB; i += 192 * 16) *reinterpret_cast<uint4*>(pad + i) = make_uint4(0, 0, 0, 0);
         }
     fence_proxy_async();
-    if (warp == 5) tmem_alloc(tmem_slot, 512);
+    if (warp == 5) tmem_alloc(tmem_slot, CF::TM_COLS);
     if (tid == 128) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         mbar_init(rfull, 1);
@@ -110,7 +124,7 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    constexpr uint32_t TM_S = 0, TM_REL = 224, TM_O = 256;
+    constexpr uint32_t TM_S = 0, TM_REL = CF::TM_REL, TM_O = CF::TM_O;
 
     if (warp == 4) {
         if (lane == 0) {
@@ -142,7 +156,7 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
         }
     } else if (warp == 5) {
         if (lane == 0) {
-            constexpr uint32_t id_s = umma_idesc_f16(128, 224), id_r = umma_idesc_f16(128, 32);
+            constexpr uint32_t id_s = umma_idesc_f16(128, NKP), id_r = umma_idesc_f16(128, 32);
             constexpr uint32_t id_o = umma_idesc_f16(128, CB, 0, 1);
             mbar_wait(rfull, 0);
             uint32_t g = 0, it = 0;
@@ -175,7 +189,7 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
                     tc_fence_after();
                     const uint32_t vb = base + s * CF::STAGE + CF::QB;
 #pragma unroll
-                    for (int k = 0; k < 14; ++k) {
+                    for (int k = 0; k < NKP / 16; ++k) {
                         const uint64_t dp = umma_smem_desc(base + CF::OFF_P + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024, UMMA_LAYOUT_SW128);
                         const uint64_t dv = umma_smem_desc(vb + k * 16 * ROWB, 16, CF::SBO, CF::LAYOUT);
                         umma_f16_ss(tmem_base + TM_O + nb * CB, dp, dv, id_o, k ? 1u : 0u);
@@ -197,7 +211,7 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
             uint32_t ab[24];
             {
                 uint32_t* su = reinterpret_cast<uint32_t*>(sv);
-                const uint32_t t0 = tmem_base + lane_sel + TM_S + half * 112;
+                const uint32_t t0 = tmem_base + lane_sel + TM_S + half * WR;
                 tmem_ld32(t0, su);
                 tmem_ld32(t0 + 32, su + 32);
                 tmem_ld32(t0 + 64, su + 64);
@@ -221,10 +235,10 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
             }
 #pragma unroll
             for (int j = NKEY; j < 104; ++j) sv[j] = 0.f;
-            // P row: 13 chunks of 8 keys starting at key column half*112
+            // P row: 13 chunks of 8 keys starting at key column half*104
 #pragma unroll
             for (int q = 0; q < 13; ++q) {
-                const int cg = half * 14 + q;                     // 16-byte chunk index along the 256-key row
+                const int cg = half * 13 + q;                     // 16-byte chunk index along the 256-key row
                 uint4 u;
                 uint32_t* pu = reinterpret_cast<uint32_t*>(&u);
 #pragma unroll
@@ -240,8 +254,6 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
             __syncwarp();
             if (lane == 0) mbar_arrive(p_ready);
 
-            mbar_wait(o_full, it & 1);
-            tc_fence_after();
             const int wi = 2 * p + half;
             const bool valid = wi < nwin;
             const WinCoord wc = win_coord(valid ? wi : 2 * p, nwx, per_img);
@@ -249,93 +261,121 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
                 // Fused branch glue (ref :139-161).  With the Haar transforms folded into the qkv weights the
                 // accumulator row IS IWT^L(attention) in space-to-depth order: column s*16+k belongs to pixel
                 // s = dy*2^L + dx of this level pixel's 2^L x 2^L block.
-                //   y_k = O' + t_k            -> Y[..., 16k..16k+15]                    (ref :139,:145,:153,:161)
-                //   t_{k+1} = (n_{k+1} + y_k)/2 -> Tnext in the next level's space-to-depth order (ref :141,:147,:155)
+                //   y_k = O' + t_k              -> Y[..., 16k..16k+15]                  (ref :139,:145,:153,:161)
+                //   t_{k+1} = (n_{k+1} + y_k)/2 -> Tnext, next level's space-to-depth order (ref :141,:147,:155)
+                // Operand loads are issued one group ahead (the first group before the PV MMAs finish).
                 constexpr int LV = C == 16 ? 0 : (C == 64 ? 1 : 2);
-                constexpr int S = 1 << LV;
+                constexpr int S = 1 << LV, NSUB = S * S;
+                constexpr int G = NSUB >= 2 ? 2 : 1, NG = NSUB / G;
                 const int ly = wc.y + (qi >> 3), lx = wc.x + (qi & 7);
                 const __half* trow = fz.T + (((long)wc.b * h + ly) * w + lx) * C;
                 const int br = fz.branch;
+                const bool has_next = fz.Tnext != nullptr;
                 const int lvn = br == 0 ? 1 : 2, Sn = 1 << lvn, Cn = NB * Sn * Sn;
                 float mu[NB], rs[NB];
-                if (fz.Tnext != nullptr) {
+                if (has_next) {
 #pragma unroll
                     for (int e = 0; e < NB; ++e) {
                         const float2 mr = __ldg(&fz.munorm[wc.b * NF + NB * (br + 1) + e]);
                         mu[e] = mr.x; rs[e] = mr.y;
                     }
                 }
-#pragma unroll 1
-                for (int s = 0; s < S * S; ++s) {
-                    uint32_t r[16];
-                    tmem_ld16(tmem_base + lane_sel + TM_O + s * NB, r);
-                    uint4 tk[2];
-                    tk[0] = *reinterpret_cast<const uint4*>(trow + s * NB);
-                    tk[1] = *reinterpret_cast<const uint4*>(trow + s * NB + 8);
-                    tmem_ld_wait();
-                    if (valid) {
-                        const int fy = ly * S + s / S, fx = lx * S + s % S;
-                        const long pix = ((long)wc.b * fz.Hp + fy) * fz.Wp + fx;
-                        float yv[NB];
-                        const __half2* th = reinterpret_cast<const __half2*>(tk);
+                auto pix_of = [&](int s) -> long {
+                    return ((long)wc.b * fz.Hp + (ly * S + s / S)) * fz.Wp + (lx * S + s % S);
+                };
+                auto load_group = [&](int g0, GluePre<G>& pr) {
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            const float2 tf = __half22float2(th[e]);
-                            yv[2 * e] = fmaf(__uint_as_float(r[2 * e]), inv, tf.x);
-                            yv[2 * e + 1] = fmaf(__uint_as_float(r[2 * e + 1]), inv, tf.y);
-                        }
-                        uint4 yo[2];
-                        __half2* yh = reinterpret_cast<__half2*>(yo);
+                    for (int j = 0; j < G; ++j) {
+                        const int s = g0 * G + j;
+                        pr.tk[2 * j] = *reinterpret_cast<const uint4*>(trow + s * NB);
+                        pr.tk[2 * j + 1] = *reinterpret_cast<const uint4*>(trow + s * NB + 8);
+                        if (has_next) {
+                            const float4* xp = reinterpret_cast<const float4*>(fz.X + pix_of(s) * NF + NB * (br + 1));
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) yh[e] = __floats2half2_rn(yv[2 * e], yv[2 * e + 1]);
-                        __half* yp = fz.Y + pix * NF + NB * br;
-                        *reinterpret_cast<uint4*>(yp) = yo[0];
-                        *reinterpret_cast<uint4*>(yp + 8) = yo[1];
-                        if (fz.Tnext != nullptr) {
-                            const float4* xp = reinterpret_cast<const float4*>(fz.X + pix * NF + NB * (br + 1));
-                            uint4 to[2];
-                            __half2* tnh = reinterpret_cast<__half2*>(to);
-#pragma unroll
-                            for (int v = 0; v < 4; ++v) {
-                                const float4 xv = xp[v];
-                                const float t0 = 0.5f * ((xv.x - mu[4 * v]) * rs[4 * v] + yv[4 * v]);
-                                const float t1 = 0.5f * ((xv.y - mu[4 * v + 1]) * rs[4 * v + 1] + yv[4 * v + 1]);
-                                const float t2 = 0.5f * ((xv.z - mu[4 * v + 2]) * rs[4 * v + 2] + yv[4 * v + 2]);
-                                const float t3 = 0.5f * ((xv.w - mu[4 * v + 3]) * rs[4 * v + 3] + yv[4 * v + 3]);
-                                tnh[2 * v] = __floats2half2_rn(t0, t1);
-                                tnh[2 * v + 1] = __floats2half2_rn(t2, t3);
-                            }
-                            const int sn = (fy & (Sn - 1)) * Sn + (fx & (Sn - 1));
-                            __half* tp = fz.Tnext + ((((long)wc.b * (fz.Hp >> lvn)) + (fy >> lvn)) * (fz.Wp >> lvn) + (fx >> lvn)) * Cn + sn * NB;
-                            *reinterpret_cast<uint4*>(tp) = to[0];
-                            *reinterpret_cast<uint4*>(tp + 8) = to[1];
+                            for (int v = 0; v < 4; ++v) pr.xv[4 * j + v] = xp[v];
                         }
                     }
+                };
+                GluePre<G> cur;
+                load_group(0, cur);
+                mbar_wait(o_full, it & 1);
+                tc_fence_after();
+#pragma unroll 1
+                for (int g0 = 0; g0 < NG; ++g0) {
+                    GluePre<G> nxt;
+                    if (g0 + 1 < NG) load_group(g0 + 1, nxt);
+#pragma unroll
+                    for (int j = 0; j < G; ++j) {
+                        const int s = g0 * G + j;
+                        uint32_t r[16];
+                        tmem_ld16(tmem_base + lane_sel + TM_O + s * NB, r);
+                        tmem_ld_wait();
+                        if (valid) {
+                            const int fy = ly * S + s / S, fx = lx * S + s % S;
+                            const long pix = ((long)wc.b * fz.Hp + fy) * fz.Wp + fx;
+                            float yv[NB];
+                            const __half2* th = reinterpret_cast<const __half2*>(&cur.tk[2 * j]);
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) {
+                                const float2 tf = __half22float2(th[e]);
+                                yv[2 * e] = fmaf(__uint_as_float(r[2 * e]), inv, tf.x);
+                                yv[2 * e + 1] = fmaf(__uint_as_float(r[2 * e + 1]), inv, tf.y);
+                            }
+                            uint4 yo[2];
+                            __half2* yh = reinterpret_cast<__half2*>(yo);
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) yh[e] = __floats2half2_rn(yv[2 * e], yv[2 * e + 1]);
+                            __half* yp = fz.Y + pix * NF + NB * br;
+                            *reinterpret_cast<uint4*>(yp) = yo[0];
+                            *reinterpret_cast<uint4*>(yp + 8) = yo[1];
+                            if (has_next) {
+                                uint4 to[2];
+                                __half2* tnh = reinterpret_cast<__half2*>(to);
+#pragma unroll
+                                for (int v = 0; v < 4; ++v) {
+                                    const float4 xv = cur.xv[4 * j + v];
+                                    const float t0 = 0.5f * ((xv.x - mu[4 * v]) * rs[4 * v] + yv[4 * v]);
+                                    const float t1 = 0.5f * ((xv.y - mu[4 * v + 1]) * rs[4 * v + 1] + yv[4 * v + 1]);
+                                    const float t2 = 0.5f * ((xv.z - mu[4 * v + 2]) * rs[4 * v + 2] + yv[4 * v + 2]);
+                                    const float t3 = 0.5f * ((xv.w - mu[4 * v + 3]) * rs[4 * v + 3] + yv[4 * v + 3]);
+                                    tnh[2 * v] = __floats2half2_rn(t0, t1);
+                                    tnh[2 * v + 1] = __floats2half2_rn(t2, t3);
+                                }
+                                const int sn = (fy & (Sn - 1)) * Sn + (fx & (Sn - 1));
+                                __half* tp = fz.Tnext + ((((long)wc.b * (fz.Hp >> lvn)) + (fy >> lvn)) * (fz.Wp >> lvn) + (fx >> lvn)) * Cn + sn * NB;
+                                *reinterpret_cast<uint4*>(tp) = to[0];
+                                *reinterpret_cast<uint4*>(tp + 8) = to[1];
+                            }
+                        }
+                    }
+                    if (g0 + 1 < NG) cur = nxt;
                 }
             } else {
-            __half* orow = O + (((long)wc.b * h + wc.y + (qi >> 3)) * w + wc.x + (qi & 7)) * C;
-            constexpr int OCH = C < 32 ? C : 32;
+                mbar_wait(o_full, it & 1);
+                tc_fence_after();
+                __half* orow = O + (((long)wc.b * h + wc.y + (qi >> 3)) * w + wc.x + (qi & 7)) * C;
+                constexpr int OCH = C < 32 ? C : 32;
 #pragma unroll 1
-            for (int c0 = 0; c0 < C; c0 += OCH) {
-                uint32_t r[OCH];
-                if constexpr (OCH == 32) tmem_ld32(tmem_base + lane_sel + TM_O + c0, r);
-                else tmem_ld16(tmem_base + lane_sel + TM_O + c0, r);
-                tmem_ld_wait();
-                if (valid) {
+                for (int c0 = 0; c0 < C; c0 += OCH) {
+                    uint32_t r[OCH];
+                    if constexpr (OCH == 32) tmem_ld32(tmem_base + lane_sel + TM_O + c0, r);
+                    else tmem_ld16(tmem_base + lane_sel + TM_O + c0, r);
+                    tmem_ld_wait();
+                    if (valid) {
 #pragma unroll
-                    for (int v = 0; v < OCH / 8; ++v) {
-                        uint4 u;
-                        uint32_t* pu = reinterpret_cast<uint32_t*>(&u);
+                        for (int v = 0; v < OCH / 8; ++v) {
+                            uint4 u;
+                            uint32_t* pu = reinterpret_cast<uint32_t*>(&u);
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const __half2 hv = __floats2half2_rn(__uint_as_float(r[v * 8 + 2 * e]) * inv,
-                                                                 __uint_as_float(r[v * 8 + 2 * e + 1]) * inv);
-                            pu[e] = *reinterpret_cast<const uint32_t*>(&hv);
+                            for (int e = 0; e < 4; ++e) {
+                                const __half2 hv = __floats2half2_rn(__uint_as_float(r[v * 8 + 2 * e]) * inv,
+                                                                     __uint_as_float(r[v * 8 + 2 * e + 1]) * inv);
+                                pu[e] = *reinterpret_cast<const uint32_t*>(&hv);
+                            }
+                            *reinterpret_cast<uint4*>(orow + c0 + v * 8) = u;
                         }
-                        *reinterpret_cast<uint4*>(orow + c0 + v * 8) = u;
                     }
                 }
-            }
             }
             tc_fence_before();
             __syncwarp();
@@ -344,7 +384,7 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 5) tmem_dealloc(tmem_base, 512);
+    if (warp == 5) tmem_dealloc(tmem_base, CF::TM_COLS);
 }
 
 template <int C>
@@ -369,7 +409,8 @@ static int launch_attn_umma_c(const __half* QKV, const __half* relx, __half* O, 
     }
     const int nwin = B * (h / BLK) * (w / BLK);
     const int npairs = (nwin + 1) / 2;
-    const int grid = npairs < device_sm_count() ? npairs : device_sm_count();
+    const int cap = device_sm_count() * CF::MIN_CTAS;
+    const int grid = npairs < cap ? npairs : cap;
     if (fuse != nullptr) {
         M2T_ENSURE_SMEM((attn_umma_kernel<C, true>), CF::SMEM);
         attn_umma_kernel<C, true><<<grid, 192, CF::SMEM, s>>>(mapQ, mapKV, mapR, O, h, w, nwin, *fuse);
