@@ -397,4 +397,9 @@ int m2t_stage_tail(uint32_t variant, int scale, int n_blocks, const void* d_pack
                     b0, g, rgb_range, static_cast<uint8_t*>(d_scratch), (cudaStream_t)stream);
 }
 
+int m2t_debug_attn_timing(long long* host64) {
+    if (!host64) { set_error("null pointer"); return M2T_E_ARG; }
+    return read_attn_timing(host64);
+}
+
 }  // extern "C"

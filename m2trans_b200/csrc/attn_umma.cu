@@ -1,18 +1,20 @@
 // tcgen05 halo attention (ref M2Trans_network.py:310-332; block 8, halo 1, one head) for C in {16, 64, 256}.
 //
-// One work item = a PAIR of 8x8 query windows, stacked into one M = 128 tile (rows 0-63 window A, 64-127
-// window B), so every TMEM lane / epilogue thread owns one query row.
-//   S  = [Qa;Qb] . [Ka;Kb]^T         M=128, N=208 (2 x 100 keys padded to 104), K = C     (block-diagonal use:
-//                                     row m only reads the 100 columns of its own window)
-//   S' = [Qa;Qb] . Rel^T              N = 32 extra columns: q[:C/2].rel_h[r] (cols 208..217) and
-//                                     q[C/2:].rel_w[c] (cols 218..227): the reference adds rel to K, also at the
-//                                     zero-padded keys (ref :322-325); q.(k+rel) = q.k + q.rel
-//   P  = exp2((S + rel terms - max) * log2e), unnormalised, fp16, written K-major/128B-swizzled to smem
-//   O  = P . [Va;Vb]                  M=128, N = C, K = 208 keys; rows scaled by 1/sum in the epilogue
+// One work item = a PAIR of 8x8 query windows.  Each window is an M = 64 tcgen05 accumulator; an M = 64
+// accumulator occupies TMEM lanes 0-15 of every 32-lane quadrant, so window B is placed at lane offset 16 in the
+// SAME columns (tests/test_probes.py::test_umma_m64_two_windows_interleaved): all 128 lanes / epilogue threads are
+// busy, nothing is block-diagonal, and one pair needs only 144 + C TMEM columns.
+//   S   = Q . K^T                  per window M=64, N=112 (100 keys + 12 unused), K = C
+//   S'  = Q . Rel^T                N = 32 extra columns: q[:C/2].rel_h[r] (cols 112..121), q[C/2:].rel_w[c]
+//                                  (122..131): the reference adds rel to K, also at the zero-padded keys
+//                                  (ref :322-325); q.(k+rel) = q.k + q.rel
+//   P   = exp2((S + rel terms - max) * log2e), unnormalised, fp16, K-major / 128B-swizzled in smem (zero in the
+//         12 padding key columns)
+//   O   = P . V                    per window M=64, N = C, K = 112; rows scaled by 1/sum in the epilogue
 // Keys/values outside the frame are TMA out-of-bounds zero fill = F.unfold's zero padding (ref :313-317);
 // window partition / reverse (ref :310, :332) are TMA box coordinates and the store address.
-// Operands stream through one ring in 64-channel blocks (Q 128 rows + K 208 rows, then V 208 rows), so the
-// C = 256 case (288 KB of Q/K/V per pair) fits and loads overlap the previous pair's softmax / PV.
+// Operands stream in 64-channel blocks through two rings (Q+K blocks, V blocks).  C = 16 / 64 CTAs need <= 256
+// TMEM columns and <= 110 KB of shared memory, so two CTAs share an SM and hide each other's latencies.
 // Warp roles (192 threads): warps 0-3 softmax + epilogue (thread = query row), warp 4 TMA, warp 5 MMA issue.
 //
 // FUSE = true additionally folds the CFTM branch glue (ref :139-161) into the epilogue, see AttnFuse.
@@ -22,10 +24,9 @@
 
 namespace m2t {
 
-constexpr int WR = 104;                                       // key rows per window (100 + 4 zero rows)
-constexpr int NKP = 2 * WR;                                   // 208 key rows / S columns per pair
+constexpr int WR = 112;                                       // key rows per window (100 + 12 zero rows)
 
-template <int C>
+template <int C, bool FUSE>
 struct AtCfg {
     static constexpr int CB = C < 64 ? C : 64;               // channels per streamed block
     static constexpr int NBLK = C / CB;
@@ -33,23 +34,31 @@ struct AtCfg {
     static constexpr uint64_t LAYOUT = CB == 64 ? UMMA_LAYOUT_SW128 : UMMA_LAYOUT_SW32;
     static constexpr int TMA_SWZ = CB == 64 ? 3 : 1;
     static constexpr uint32_t SBO = 8 * ROWB;
-    static constexpr uint32_t QB = 128 * ROWB;                // Q block (two windows x 64 rows)
-    static constexpr uint32_t KVB = NKP * ROWB;               // K or V block
+    static constexpr uint32_t QB = 128 * ROWB;                // Q block: two windows x 64 rows
+    static constexpr uint32_t KVB = 2 * WR * ROWB;            // K or V block: two windows x 112 rows
     static constexpr uint32_t WIN_B = WR * ROWB;              // offset of window B's keys
-    static constexpr uint32_t STAGE = (QB + KVB + 1023) / 1024 * 1024;
-    static constexpr int STAGES = C == 16 ? 4 : 3;
+    static constexpr int SQ = C == 64 ? 1 : 2;                // Q+K ring depth
+    static constexpr int SV = C == 64 ? 1 : 2;                // V ring depth
+    static constexpr bool TSTAGE = FUSE && C == 256;          // t_k rows staged through smem by TMA
+    static constexpr int ST = TSTAGE ? 2 : 0;
+    static constexpr uint32_t QK_STAGE = (QB + KVB + 1023) / 1024 * 1024;
+    static constexpr uint32_t V_STAGE = (KVB + 1023) / 1024 * 1024;
+    static constexpr uint32_t T_STAGE = QB;
     static constexpr uint32_t REL_BLOCK = 32 * ROWB;
-    static constexpr uint32_t OFF_P = STAGES * STAGE;
-    static constexpr uint32_t OFF_REL = OFF_P + 4 * 16384;
+    static constexpr uint32_t OFF_V = SQ * QK_STAGE;
+    static constexpr uint32_t OFF_P = OFF_V + SV * V_STAGE;
+    static constexpr uint32_t OFF_T = OFF_P + 2 * 16384;      // P: per window two 64-key blocks of [64 rows][128 B]
+    static constexpr uint32_t OFF_REL = OFF_T + ST * T_STAGE;
     static constexpr uint32_t OFF_BAR = OFF_REL + (NBLK * REL_BLOCK + 1023) / 1024 * 1024;
     static constexpr uint32_t SMEM = 1024 + OFF_BAR + 256;
     static constexpr uint32_t TX_QK = 2 * 64 * ROWB + 2 * 100 * ROWB;
     static constexpr uint32_t TX_V = 2 * 100 * ROWB;
-    // TMEM columns: S [0,208) | rel [208,240) | O.  C = 16 fits 256 columns, so two CTAs can share an SM.
-    static constexpr uint32_t TM_REL = NKP;
-    static constexpr uint32_t TM_O = C == 16 ? 240 : 256;
-    static constexpr uint32_t TM_COLS = C == 16 ? 256 : 512;
-    static constexpr int MIN_CTAS = C == 16 ? 2 : 1;
+    static constexpr uint32_t TX_T = 2 * 64 * ROWB;
+    // TMEM columns: S [0,112) | rel [112,144) | O
+    static constexpr uint32_t TM_REL = WR;
+    static constexpr uint32_t TM_O = C <= 64 ? 144 : 256;
+    static constexpr uint32_t TM_COLS = C <= 64 ? 256 : 512;
+    static constexpr int MIN_CTAS = C <= 64 ? 2 : 1;
 };
 
 __device__ __forceinline__ float fast_exp2(float x) {
@@ -68,48 +77,60 @@ __device__ __forceinline__ WinCoord win_coord(int wi, int nwx, int per_img) {
     return c;
 }
 
-template <int G>
-struct GluePre {       // prefetched operands of G sub-pixels of the fused glue
-    uint4 tk[2 * G];
-    float4 xv[4 * G];
-};
+#ifdef M2T_TIMING
+__device__ long long g_attn_dbg[64];
+#define M2T_T(slot) do { if (blockIdx.x == 0 && tid == 0 && it < 6) g_attn_dbg[(slot) + 8 * it] = clock64(); } while (0)
+#else
+#define M2T_T(slot) do { } while (0)
+#endif
 
 template <int C, bool FUSE>
-__global__ void __launch_bounds__(192, AtCfg<C>::MIN_CTAS)
+__global__ void __launch_bounds__(192, AtCfg<C, FUSE>::MIN_CTAS)
 attn_umma_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapKV,
-                 const __grid_constant__ CUtensorMap mapR, __half* __restrict__ O, int h, int w, int nwin,
-                 const AttnFuse fz) {
-    using CF = AtCfg<C>;
-    constexpr int CB = CF::CB, NBLK = CF::NBLK, STAGES = CF::STAGES;
+                 const __grid_constant__ CUtensorMap mapR, const __grid_constant__ CUtensorMap mapT,
+                 __half* __restrict__ O, int h, int w, int nwin, const AttnFuse fz) {
+    using CF = AtCfg<C, FUSE>;
+    constexpr int CB = CF::CB, NBLK = CF::NBLK, SQ = CF::SQ, SV = CF::SV;
     constexpr uint32_t ROWB = CF::ROWB;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + CF::OFF_BAR);
-    uint64_t* full = bars;                         // [STAGES]
-    uint64_t* empty = bars + STAGES;               // [STAGES]
-    uint64_t* rfull = bars + 2 * STAGES;           // rel tables landed
-    uint64_t* s_full = bars + 2 * STAGES + 1;      // S complete in TMEM
-    uint64_t* p_ready = bars + 2 * STAGES + 2;     // P written to smem, S consumed
-    uint64_t* o_full = bars + 2 * STAGES + 3;      // O complete in TMEM
-    uint64_t* o_empty = bars + 2 * STAGES + 4;     // O consumed
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 5);
+    uint64_t* q_full = bars;                 // [2]
+    uint64_t* q_empty = bars + 2;            // [2]
+    uint64_t* v_full = bars + 4;             // [2]
+    uint64_t* v_empty = bars + 6;            // [2]
+    uint64_t* t_full = bars + 8;             // [2]
+    uint64_t* t_empty = bars + 10;           // [2]
+    uint64_t* rfull = bars + 12;             // rel tables landed
+    uint64_t* s_full = bars + 13;            // S complete in TMEM
+    uint64_t* p_ready = bars + 14;           // P written to smem, S consumed
+    uint64_t* o_full = bars + 15;            // O complete in TMEM
+    uint64_t* o_empty = bars + 16;           // O consumed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nwx = w / BLK, per_img = (h / BLK) * nwx;
     const int npairs = (nwin + 1) / 2;
+#ifdef M2T_TIMING
+    if (blockIdx.x == 0 && tid == 0) g_attn_dbg[6] = clock64();
+#endif
 
-    // zero P (its off-diagonal / padding columns stay zero for ever) and the 4 padding key rows per window
-    for (uint32_t i = tid * 16; i < 4 * 16384; i += 192 * 16) *reinterpret_cast<uint4*>(sm + CF::OFF_P + i) = make_uint4(0, 0, 0, 0);
-    for (int s = 0; s < STAGES; ++s)
-        for (int half = 0; half < 2; ++half) {
-            uint8_t* pad = sm + s * CF::STAGE + CF::QB + half * CF::WIN_B + 100 * ROWB;
+    // zero P (the 12 padding key columns stay zero for ever) and the 12 padding rows of every V stage
+    for (uint32_t i = tid * 16; i < 2 * 16384; i += 192 * 16) *reinterpret_cast<uint4*>(sm + CF::OFF_P + i) = make_uint4(0, 0, 0, 0);
+    for (int s = 0; s < SV; ++s)
+        for (int win = 0; win < 2; ++win) {
+            uint8_t* pad = sm + CF::OFF_V + s * CF::V_STAGE + win * CF::WIN_B + 100 * ROWB;
             for (uint32_t i = tid * 16; i < (WR - 100) * ROWB; i += 192 * 16) *reinterpret_cast<uint4*>(pad + i) = make_uint4(0, 0, 0, 0);
         }
     fence_proxy_async();
     if (warp == 5) tmem_alloc(tmem_slot, CF::TM_COLS);
     if (tid == 128) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&q_full[s], 1); mbar_init(&q_empty[s], 1);
+            mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1);
+            mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], 4);
+        }
         mbar_init(rfull, 1);
         mbar_init(s_full, 1);
         mbar_init(p_ready, 4);
@@ -119,99 +140,124 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
         tma_prefetch_desc(&mapQ);
         tma_prefetch_desc(&mapKV);
         tma_prefetch_desc(&mapR);
+        if constexpr (CF::TSTAGE) tma_prefetch_desc(&mapT);
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     constexpr uint32_t TM_S = 0, TM_REL = CF::TM_REL, TM_O = CF::TM_O;
+    constexpr uint32_t LANE_B = 16u << 16;                      // TMEM lane offset of window B
+#ifdef M2T_TIMING
+    if (blockIdx.x == 0 && tid == 0) g_attn_dbg[7] = clock64();
+#endif
 
     if (warp == 4) {
         if (lane == 0) {
             mbar_expect_tx(rfull, NBLK * CF::REL_BLOCK);
             for (int kb = 0; kb < NBLK; ++kb) tma_load_2d(sm + CF::OFF_REL + kb * CF::REL_BLOCK, &mapR, rfull, kb * CB, 0);
-            uint32_t g = 0;
+            uint32_t gq = 0, gv = 0, gt = 0;
             for (int p = blockIdx.x; p < npairs; p += gridDim.x) {
                 const int wa = 2 * p, wb = (2 * p + 1 < nwin) ? 2 * p + 1 : 2 * p;
                 const WinCoord a = win_coord(wa, nwx, per_img), b = win_coord(wb, nwx, per_img);
-                for (int kb = 0; kb < NBLK; ++kb, ++g) {
-                    const uint32_t s = g % STAGES, ph = (g / STAGES) & 1;
-                    uint8_t* st = sm + s * CF::STAGE;
-                    mbar_wait(&empty[s], ph ^ 1);
-                    mbar_expect_tx(&full[s], CF::TX_QK);
-                    tma_load_4d(st, &mapQ, &full[s], kb * CB, a.x, a.y, a.b);
-                    tma_load_4d(st + 64 * ROWB, &mapQ, &full[s], kb * CB, b.x, b.y, b.b);
-                    tma_load_4d(st + CF::QB, &mapKV, &full[s], C + kb * CB, a.x - 1, a.y - 1, a.b);
-                    tma_load_4d(st + CF::QB + CF::WIN_B, &mapKV, &full[s], C + kb * CB, b.x - 1, b.y - 1, b.b);
+                for (int kb = 0; kb < NBLK; ++kb, ++gq) {
+                    const uint32_t s = gq % SQ, ph = (gq / SQ) & 1;
+                    uint8_t* st = sm + s * CF::QK_STAGE;
+                    mbar_wait(&q_empty[s], ph ^ 1);
+                    mbar_expect_tx(&q_full[s], CF::TX_QK);
+                    tma_load_4d(st, &mapQ, &q_full[s], kb * CB, a.x, a.y, a.b);
+                    tma_load_4d(st + 64 * ROWB, &mapQ, &q_full[s], kb * CB, b.x, b.y, b.b);
+                    tma_load_4d(st + CF::QB, &mapKV, &q_full[s], C + kb * CB, a.x - 1, a.y - 1, a.b);
+                    tma_load_4d(st + CF::QB + CF::WIN_B, &mapKV, &q_full[s], C + kb * CB, b.x - 1, b.y - 1, b.b);
                 }
-                for (int nb = 0; nb < NBLK; ++nb, ++g) {
-                    const uint32_t s = g % STAGES, ph = (g / STAGES) & 1;
-                    uint8_t* st = sm + s * CF::STAGE;
-                    mbar_wait(&empty[s], ph ^ 1);
-                    mbar_expect_tx(&full[s], CF::TX_V);
-                    tma_load_4d(st + CF::QB, &mapKV, &full[s], 2 * C + nb * CB, a.x - 1, a.y - 1, a.b);
-                    tma_load_4d(st + CF::QB + CF::WIN_B, &mapKV, &full[s], 2 * C + nb * CB, b.x - 1, b.y - 1, b.b);
+                for (int nb = 0; nb < NBLK; ++nb, ++gv) {
+                    const uint32_t s = gv % SV, ph = (gv / SV) & 1;
+                    uint8_t* st = sm + CF::OFF_V + s * CF::V_STAGE;
+                    mbar_wait(&v_empty[s], ph ^ 1);
+                    mbar_expect_tx(&v_full[s], CF::TX_V);
+                    tma_load_4d(st, &mapKV, &v_full[s], 2 * C + nb * CB, a.x - 1, a.y - 1, a.b);
+                    tma_load_4d(st + CF::WIN_B, &mapKV, &v_full[s], 2 * C + nb * CB, b.x - 1, b.y - 1, b.b);
+                }
+                if constexpr (CF::TSTAGE) {
+                    for (int nb = 0; nb < NBLK; ++nb, ++gt) {
+                        const uint32_t s = gt & 1, ph = (gt >> 1) & 1;
+                        uint8_t* st = sm + CF::OFF_T + s * CF::T_STAGE;
+                        mbar_wait(&t_empty[s], ph ^ 1);
+                        mbar_expect_tx(&t_full[s], CF::TX_T);
+                        tma_load_4d(st, &mapT, &t_full[s], nb * CB, a.x, a.y, a.b);
+                        tma_load_4d(st + 64 * ROWB, &mapT, &t_full[s], nb * CB, b.x, b.y, b.b);
+                    }
                 }
             }
         }
     } else if (warp == 5) {
         if (lane == 0) {
-            constexpr uint32_t id_s = umma_idesc_f16(128, NKP), id_r = umma_idesc_f16(128, 32);
-            constexpr uint32_t id_o = umma_idesc_f16(128, CB, 0, 1);
+            constexpr uint32_t id_s = umma_idesc_f16(64, WR), id_r = umma_idesc_f16(64, 32);
+            constexpr uint32_t id_o = umma_idesc_f16(64, CB, 0, 1);
             mbar_wait(rfull, 0);
-            uint32_t g = 0, it = 0;
+            uint32_t gq = 0, gv = 0, it = 0;
             for (int p = blockIdx.x; p < npairs; p += gridDim.x, ++it) {
-                // S and the rel columns
-                for (int kb = 0; kb < NBLK; ++kb, ++g) {
-                    const uint32_t s = g % STAGES, ph = (g / STAGES) & 1;
-                    mbar_wait(&full[s], ph);
+                // S and the rel columns, both windows
+                for (int kb = 0; kb < NBLK; ++kb, ++gq) {
+                    const uint32_t s = gq % SQ, ph = (gq / SQ) & 1;
+                    mbar_wait(&q_full[s], ph);
                     tc_fence_after();
-                    const uint32_t st = base + s * CF::STAGE;
+                    const uint32_t st = base + s * CF::QK_STAGE;
 #pragma unroll
                     for (int k = 0; k < CB / 16; ++k) {
-                        const uint64_t dq = umma_smem_desc(st + k * 32, 16, CF::SBO, CF::LAYOUT);
-                        const uint64_t dk = umma_smem_desc(st + CF::QB + k * 32, 16, CF::SBO, CF::LAYOUT);
                         const uint64_t dr = umma_smem_desc(base + CF::OFF_REL + kb * CF::REL_BLOCK + k * 32, 16, CF::SBO, CF::LAYOUT);
                         const uint32_t accum = (kb | k) ? 1u : 0u;
-                        umma_f16_ss(tmem_base + TM_S, dq, dk, id_s, accum);
-                        umma_f16_ss(tmem_base + TM_REL, dq, dr, id_r, accum);
+#pragma unroll
+                        for (int win = 0; win < 2; ++win) {
+                            const uint64_t dq = umma_smem_desc(st + win * 64 * ROWB + k * 32, 16, CF::SBO, CF::LAYOUT);
+                            const uint64_t dk = umma_smem_desc(st + CF::QB + win * CF::WIN_B + k * 32, 16, CF::SBO, CF::LAYOUT);
+                            umma_f16_ss(tmem_base + TM_S + win * LANE_B, dq, dk, id_s, accum);
+                            umma_f16_ss(tmem_base + TM_REL + win * LANE_B, dq, dr, id_r, accum);
+                        }
                     }
-                    umma_commit(&empty[s]);
+                    umma_commit(&q_empty[s]);
                 }
                 umma_commit(s_full);
                 // O = P . V
                 mbar_wait(p_ready, it & 1);
                 mbar_wait(o_empty, (it & 1) ^ 1);
                 tc_fence_after();
-                for (int nb = 0; nb < NBLK; ++nb, ++g) {
-                    const uint32_t s = g % STAGES, ph = (g / STAGES) & 1;
-                    mbar_wait(&full[s], ph);
+                for (int nb = 0; nb < NBLK; ++nb, ++gv) {
+                    const uint32_t s = gv % SV, ph = (gv / SV) & 1;
+                    mbar_wait(&v_full[s], ph);
                     tc_fence_after();
-                    const uint32_t vb = base + s * CF::STAGE + CF::QB;
+                    const uint32_t vb = base + CF::OFF_V + s * CF::V_STAGE;
 #pragma unroll
-                    for (int k = 0; k < NKP / 16; ++k) {
-                        const uint64_t dp = umma_smem_desc(base + CF::OFF_P + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024, UMMA_LAYOUT_SW128);
-                        const uint64_t dv = umma_smem_desc(vb + k * 16 * ROWB, 16, CF::SBO, CF::LAYOUT);
-                        umma_f16_ss(tmem_base + TM_O + nb * CB, dp, dv, id_o, k ? 1u : 0u);
+                    for (int win = 0; win < 2; ++win) {
+#pragma unroll
+                        for (int k = 0; k < WR / 16; ++k) {
+                            const uint64_t dp = umma_smem_desc(base + CF::OFF_P + win * 16384 + (k >> 2) * 8192 + (k & 3) * 32, 16, 1024, UMMA_LAYOUT_SW128);
+                            const uint64_t dv = umma_smem_desc(vb + win * CF::WIN_B + k * 16 * ROWB, 16, CF::SBO, CF::LAYOUT);
+                            umma_f16_ss(tmem_base + TM_O + nb * CB + win * LANE_B, dp, dv, id_o, k ? 1u : 0u);
+                        }
                     }
-                    umma_commit(&empty[s]);
+                    umma_commit(&v_empty[s]);
                 }
                 umma_commit(o_full);
             }
         }
     } else {
-        const int m = tid, half = m >> 6, qi = m & 63;
+        // thread (warp, lane) owns TMEM lane 32*warp + lane: window (lane >> 4), query row 16*warp + (lane & 15)
+        const int win = lane >> 4, qi = warp * 16 + (lane & 15);
         const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
-        uint8_t* prow = sm + CF::OFF_P + m * 128;
-        uint32_t it = 0;
+        uint8_t* prow = sm + CF::OFF_P + win * 16384 + qi * 128;
+        uint32_t it = 0, gt = 0;
+        (void)gt;
         for (int p = blockIdx.x; p < npairs; p += gridDim.x, ++it) {
+            M2T_T(0);
             mbar_wait(s_full, it & 1);
             tc_fence_after();
+            M2T_T(1);
             float sv[104];
             uint32_t ab[24];
             {
                 uint32_t* su = reinterpret_cast<uint32_t*>(sv);
-                const uint32_t t0 = tmem_base + lane_sel + TM_S + half * WR;
+                const uint32_t t0 = tmem_base + lane_sel + TM_S;
                 tmem_ld32(t0, su);
                 tmem_ld32(t0 + 32, su + 32);
                 tmem_ld32(t0 + 64, su + 64);
@@ -235,10 +281,9 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
             }
 #pragma unroll
             for (int j = NKEY; j < 104; ++j) sv[j] = 0.f;
-            // P row: 13 chunks of 8 keys starting at key column half*104
+            // P row: 13 chunks of 8 keys (keys 100..103 written as zeros, chunk 13 stays zero from the prologue)
 #pragma unroll
             for (int q = 0; q < 13; ++q) {
-                const int cg = half * 13 + q;                     // 16-byte chunk index along the 256-key row
                 uint4 u;
                 uint32_t* pu = reinterpret_cast<uint32_t*>(&u);
 #pragma unroll
@@ -246,15 +291,16 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
                     const __half2 hv = __floats2half2_rn(sv[q * 8 + 2 * e], sv[q * 8 + 2 * e + 1]);
                     pu[e] = *reinterpret_cast<const uint32_t*>(&hv);
                 }
-                *reinterpret_cast<uint4*>(prow + (cg >> 3) * 16384 + (((cg & 7) ^ (m & 7)) << 4)) = u;
+                *reinterpret_cast<uint4*>(prow + (q >> 3) * 8192 + (((q & 7) ^ (qi & 7)) << 4)) = u;
             }
             const float inv = 1.f / sum;
+            M2T_T(2);
             fence_proxy_async();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(p_ready);
 
-            const int wi = 2 * p + half;
+            const int wi = 2 * p + win;
             const bool valid = wi < nwin;
             const WinCoord wc = win_coord(valid ? wi : 2 * p, nwx, per_img);
             if constexpr (FUSE) {
@@ -263,12 +309,12 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
                 // s = dy*2^L + dx of this level pixel's 2^L x 2^L block.
                 //   y_k = O' + t_k              -> Y[..., 16k..16k+15]                  (ref :139,:145,:153,:161)
                 //   t_{k+1} = (n_{k+1} + y_k)/2 -> Tnext, next level's space-to-depth order (ref :141,:147,:155)
-                // Operand loads are issued one group ahead (the first group before the PV MMAs finish).
+                // t_k rows come from registers (prefetched before the PV MMAs finish; C <= 64) or from the TMA-fed
+                // T stages (C = 256); the residual-stream slice for t_{k+1} is prefetched one 64-channel block ahead.
                 constexpr int LV = C == 16 ? 0 : (C == 64 ? 1 : 2);
-                constexpr int S = 1 << LV, NSUB = S * S;
-                constexpr int G = NSUB >= 2 ? 2 : 1, NG = NSUB / G;
+                constexpr int S = 1 << LV;
+                constexpr int SPB = CB / NB;                     // sub-pixels per 64-channel block: 1 or 4
                 const int ly = wc.y + (qi >> 3), lx = wc.x + (qi & 7);
-                const __half* trow = fz.T + (((long)wc.b * h + ly) * w + lx) * C;
                 const int br = fz.branch;
                 const bool has_next = fz.Tnext != nullptr;
                 const int lvn = br == 0 ? 1 : 2, Sn = 1 << lvn, Cn = NB * Sn * Sn;
@@ -280,41 +326,54 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
                         mu[e] = mr.x; rs[e] = mr.y;
                     }
                 }
-                auto pix_of = [&](int s) -> long {
-                    return ((long)wc.b * fz.Hp + (ly * S + s / S)) * fz.Wp + (lx * S + s % S);
-                };
-                auto load_group = [&](int g0, GluePre<G>& pr) {
+                uint4 tkr[CF::TSTAGE ? 1 : 2 * SPB];            // register copy of the t_k row (C <= 64)
+                if constexpr (!CF::TSTAGE) {
+                    const __half* trow = fz.T + (((long)wc.b * h + ly) * w + lx) * C;
 #pragma unroll
-                    for (int j = 0; j < G; ++j) {
-                        const int s = g0 * G + j;
-                        pr.tk[2 * j] = *reinterpret_cast<const uint4*>(trow + s * NB);
-                        pr.tk[2 * j + 1] = *reinterpret_cast<const uint4*>(trow + s * NB + 8);
-                        if (has_next) {
-                            const float4* xp = reinterpret_cast<const float4*>(fz.X + pix_of(s) * NF + NB * (br + 1));
+                    for (int j = 0; j < 2 * SPB; ++j) tkr[j] = *reinterpret_cast<const uint4*>(trow + j * 8);
+                }
+                float4 xcur[4 * SPB], xnxt[4 * SPB];
+                auto load_x = [&](int nb, float4* dst) {
 #pragma unroll
-                            for (int v = 0; v < 4; ++v) pr.xv[4 * j + v] = xp[v];
-                        }
+                    for (int j = 0; j < SPB; ++j) {
+                        const int s = nb * SPB + j;
+                        const long pix = ((long)wc.b * fz.Hp + (ly * S + s / S)) * fz.Wp + (lx * S + s % S);
+                        const float4* xp = reinterpret_cast<const float4*>(fz.X + pix * NF + NB * (br + 1));
+#pragma unroll
+                        for (int v = 0; v < 4; ++v) dst[4 * j + v] = xp[v];
                     }
                 };
-                GluePre<G> cur;
-                load_group(0, cur);
+                if (has_next) load_x(0, xcur);
+                M2T_T(3);
                 mbar_wait(o_full, it & 1);
                 tc_fence_after();
+                M2T_T(4);
 #pragma unroll 1
-                for (int g0 = 0; g0 < NG; ++g0) {
-                    GluePre<G> nxt;
-                    if (g0 + 1 < NG) load_group(g0 + 1, nxt);
+                for (int nb = 0; nb < NBLK; ++nb) {
+                    if (has_next && nb + 1 < NBLK) load_x(nb + 1, xnxt);
+                    const uint8_t* tst = nullptr;
+                    if constexpr (CF::TSTAGE) {
+                        mbar_wait(&t_full[gt & 1], (gt >> 1) & 1);
+                        tst = sm + CF::OFF_T + (gt & 1) * CF::T_STAGE + win * 64 * ROWB + qi * 128;
+                    }
 #pragma unroll
-                    for (int j = 0; j < G; ++j) {
-                        const int s = g0 * G + j;
+                    for (int j = 0; j < SPB; ++j) {
+                        const int s = nb * SPB + j;
                         uint32_t r[16];
                         tmem_ld16(tmem_base + lane_sel + TM_O + s * NB, r);
+                        uint4 tk[2];
+                        if constexpr (CF::TSTAGE) {
+                            tk[0] = *reinterpret_cast<const uint4*>(tst + (((2 * j) ^ (qi & 7)) << 4));
+                            tk[1] = *reinterpret_cast<const uint4*>(tst + (((2 * j + 1) ^ (qi & 7)) << 4));
+                        } else {
+                            tk[0] = tkr[2 * j]; tk[1] = tkr[2 * j + 1];
+                        }
                         tmem_ld_wait();
                         if (valid) {
                             const int fy = ly * S + s / S, fx = lx * S + s % S;
                             const long pix = ((long)wc.b * fz.Hp + fy) * fz.Wp + fx;
                             float yv[NB];
-                            const __half2* th = reinterpret_cast<const __half2*>(&cur.tk[2 * j]);
+                            const __half2* th = reinterpret_cast<const __half2*>(tk);
 #pragma unroll
                             for (int e = 0; e < 8; ++e) {
                                 const float2 tf = __half22float2(th[e]);
@@ -333,7 +392,7 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
                                 __half2* tnh = reinterpret_cast<__half2*>(to);
 #pragma unroll
                                 for (int v = 0; v < 4; ++v) {
-                                    const float4 xv = cur.xv[4 * j + v];
+                                    const float4 xv = xcur[4 * j + v];
                                     const float t0 = 0.5f * ((xv.x - mu[4 * v]) * rs[4 * v] + yv[4 * v]);
                                     const float t1 = 0.5f * ((xv.y - mu[4 * v + 1]) * rs[4 * v + 1] + yv[4 * v + 1]);
                                     const float t2 = 0.5f * ((xv.z - mu[4 * v + 2]) * rs[4 * v + 2] + yv[4 * v + 2]);
@@ -348,7 +407,15 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
                             }
                         }
                     }
-                    if (g0 + 1 < NG) cur = nxt;
+                    if constexpr (CF::TSTAGE) {
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&t_empty[gt & 1]);
+                        ++gt;
+                    }
+                    if (has_next && nb + 1 < NBLK) {
+#pragma unroll
+                        for (int j = 0; j < 4 * SPB; ++j) xcur[j] = xnxt[j];
+                    }
                 }
             } else {
                 mbar_wait(o_full, it & 1);
@@ -380,6 +447,7 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(o_empty);
+            M2T_T(5);
         }
     }
     tc_fence_before();
@@ -387,11 +455,11 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
     if (warp == 5) tmem_dealloc(tmem_base, CF::TM_COLS);
 }
 
-template <int C>
-static int launch_attn_umma_c(const __half* QKV, const __half* relx, __half* O, int B, int h, int w, cudaStream_t s,
-                              const AttnFuse* fuse) {
-    using CF = AtCfg<C>;
-    CUtensorMap mapQ, mapKV, mapR;
+template <int C, bool FUSE>
+static int launch_attn_umma_cf(const __half* QKV, const __half* relx, __half* O, int B, int h, int w, cudaStream_t s,
+                               const AttnFuse& fz) {
+    using CF = AtCfg<C, FUSE>;
+    CUtensorMap mapQ, mapKV, mapR, mapT;
     const uint64_t dims[4] = {(uint64_t)3 * C, (uint64_t)w, (uint64_t)h, (uint64_t)B};
     const uint64_t str[4] = {2, (uint64_t)3 * C * 2, (uint64_t)w * 3 * C * 2, (uint64_t)h * w * 3 * C * 2};
     {
@@ -407,19 +475,29 @@ static int launch_attn_umma_c(const __half* QKV, const __half* relx, __half* O, 
         const uint32_t box[2] = {(uint32_t)CF::CB, 32};
         M2T_TRY(make_tensor_map(&mapR, relx, 2, 2, d2, s2, box, CF::TMA_SWZ));
     }
+    if (CF::TSTAGE) {
+        const uint64_t dt[4] = {(uint64_t)C, (uint64_t)w, (uint64_t)h, (uint64_t)B};
+        const uint64_t st[4] = {2, (uint64_t)C * 2, (uint64_t)w * C * 2, (uint64_t)h * w * C * 2};
+        const uint32_t box[4] = {(uint32_t)CF::CB, BLK, BLK, 1};
+        M2T_TRY(make_tensor_map(&mapT, fz.T, 2, 4, dt, st, box, CF::TMA_SWZ));
+    } else {
+        mapT = mapQ;
+    }
     const int nwin = B * (h / BLK) * (w / BLK);
     const int npairs = (nwin + 1) / 2;
     const int cap = device_sm_count() * CF::MIN_CTAS;
     const int grid = npairs < cap ? npairs : cap;
-    if (fuse != nullptr) {
-        M2T_ENSURE_SMEM((attn_umma_kernel<C, true>), CF::SMEM);
-        attn_umma_kernel<C, true><<<grid, 192, CF::SMEM, s>>>(mapQ, mapKV, mapR, O, h, w, nwin, *fuse);
-    } else {
-        M2T_ENSURE_SMEM((attn_umma_kernel<C, false>), CF::SMEM);
-        attn_umma_kernel<C, false><<<grid, 192, CF::SMEM, s>>>(mapQ, mapKV, mapR, O, h, w, nwin, AttnFuse{});
-    }
+    M2T_ENSURE_SMEM((attn_umma_kernel<C, FUSE>), CF::SMEM);
+    attn_umma_kernel<C, FUSE><<<grid, 192, CF::SMEM, s>>>(mapQ, mapKV, mapR, mapT, O, h, w, nwin, fz);
     M2T_LAUNCH_CHECK("attn_umma_kernel");
     return M2T_OK;
+}
+
+template <int C>
+static int launch_attn_umma_c(const __half* QKV, const __half* relx, __half* O, int B, int h, int w, cudaStream_t s,
+                              const AttnFuse* fuse) {
+    if (fuse != nullptr) return launch_attn_umma_cf<C, true>(QKV, relx, O, B, h, w, s, *fuse);
+    return launch_attn_umma_cf<C, false>(QKV, relx, O, B, h, w, s, AttnFuse{});
 }
 
 int launch_attn_umma(int C, const __half* QKV, const __half* relx, __half* O, int B, int h, int w, cudaStream_t s,
@@ -431,5 +509,14 @@ int launch_attn_umma(int C, const __half* QKV, const __half* relx, __half* O, in
     set_error("attn: unsupported channel count %d", C);
     return M2T_E_UNSUPPORTED;
 }
+
+#ifdef M2T_TIMING
+int read_attn_timing(long long* host64) {
+    M2T_CUDA(cudaMemcpyFromSymbol(host64, g_attn_dbg, sizeof(long long) * 64));
+    return M2T_OK;
+}
+#else
+int read_attn_timing(long long* host64) { memset(host64, 0, sizeof(long long) * 64); return M2T_OK; }
+#endif
 
 }  // namespace m2t

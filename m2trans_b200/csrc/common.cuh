@@ -134,6 +134,8 @@ struct AttnFuse {
 int launch_attn_umma(int C, const __half* QKV, const __half* relx, __half* O, int B, int h, int w,
                      cudaStream_t s, const AttnFuse* fuse = nullptr);
 
+int read_attn_timing(long long* host64);   // development aid, zeros unless built with -DM2T_TIMING
+
 // conv_simt.cu : X_out = conv3x3_zero(Y) + bias + X_in, plus InstanceNorm partial sums
 // res/xr (optional): also write xr = fp16(Xout + res), the tail's first GEMM operand (ref :70)
 int launch_ffconv_simt(const __half* Y, const __half* Wp, const float* bias, const float* Xin, float* Xout,

@@ -13,7 +13,7 @@ constexpr uint32_t PROBE_MAX_IMG = 96 * 1024;
 __global__ void __launch_bounds__(128, 1)
 probe_umma_kernel(const uint8_t* __restrict__ a_img, uint32_t a_bytes, const uint8_t* __restrict__ b_img,
                   uint32_t b_bytes, uint64_t a_desc, uint64_t b_desc, uint32_t a_step, uint32_t b_step, int k_steps,
-                  uint32_t idesc, int n_cols, float* __restrict__ out) {
+                  uint32_t idesc, int n_cols, float* __restrict__ out, uint32_t d_lane) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar;
     __shared__ uint32_t tmem_base_s;
@@ -36,7 +36,7 @@ probe_umma_kernel(const uint8_t* __restrict__ a_img, uint32_t a_bytes, const uin
         uint64_t da = umma_desc_advance(a_desc, base);
         uint64_t db = umma_desc_advance(b_desc, base + b_off);
         for (int k = 0; k < k_steps; ++k) {
-            umma_f16_ss(tmem_base, da, db, idesc, k > 0 ? 1u : 0u);
+            umma_f16_ss(tmem_base + (d_lane << 16), da, db, idesc, k > 0 ? 1u : 0u);
             da = umma_desc_advance(da, a_step);
             db = umma_desc_advance(db, b_step);
         }
@@ -94,13 +94,15 @@ extern "C" int m2t_probe_umma(const void* d_a_image, uint32_t a_bytes, const voi
         set_error("probe_umma: images must be multiples of 16 bytes and at most %u bytes", PROBE_MAX_IMG);
         return M2T_E_ARG;
     }
+    const uint32_t d_lane = ((uint32_t)n_cols >> 16) & 0xFFu;   // bits 16..23 of n_cols: TMEM lane offset of D
+    n_cols &= 0xFFFF;
     if (n_cols < 8 || n_cols > 512 || k_steps < 1 || k_steps > 64) { set_error("probe_umma: bad n_cols/k_steps"); return M2T_E_ARG; }
     // always the maximum, so that a wrong stride hypothesis reads stale shared memory instead of faulting
     const size_t smem = 200 * 1024;
     M2T_ENSURE_SMEM(probe_umma_kernel, 200 * 1024);
     probe_umma_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(
         static_cast<const uint8_t*>(d_a_image), a_bytes, static_cast<const uint8_t*>(d_b_image), b_bytes, a_desc, b_desc,
-        a_step, b_step, k_steps, idesc, n_cols, d_out);
+        a_step, b_step, k_steps, idesc, n_cols, d_out, d_lane);
     M2T_LAUNCH_CHECK("probe_umma_kernel");
     return M2T_OK;
 }

@@ -74,7 +74,7 @@ def run_umma(a_img, b_img, a_desc, b_desc, a_step, b_step, k_steps, idsc, n_cols
     pad = lambda x: np.concatenate([x, np.zeros((-len(x)) % 16, np.uint8)])
     a = torch.from_numpy(pad(a_img)).cuda()
     b = torch.from_numpy(pad(b_img)).cuda()
-    out = torch.full((128, n_cols), float("nan"), dtype=torch.float32, device="cuda")
+    out = torch.full((128, n_cols & 0xFFFF), float("nan"), dtype=torch.float32, device="cuda")
     L.check(lib.m2t_probe_umma(a.data_ptr(), a.numel(), b.data_ptr(), b.numel(), a_desc, b_desc, a_step, b_step,
                                k_steps, idsc, n_cols, out.data_ptr(), None), "m2t_probe_umma")
     torch.cuda.synchronize()
@@ -193,6 +193,24 @@ def test_umma_m64_layout():
         hit = [l for l in range(128) if np.allclose(got[l], want[m], atol=1e-3)]
         lanes.append(hit[0] if hit else -1)
     record("umma_m64_lane_of_row", all(l >= 0 for l in lanes), json.dumps(lanes))
+
+
+def test_umma_m64_two_windows_interleaved():
+    """Two M=64 accumulators in the SAME columns: the second with a TMEM lane offset of 16 (rows of window B in
+    lanes 16-31 of each 32-lane quadrant).  n_cols bits 16..23 carry the lane offset for the probe."""
+    A1, A2, B = rnd((64, 64), 40), rnd((64, 64), 41), rnd((112, 64), 42)
+    L = _lib(); lib = L.load()
+    want1 = A1.astype(np.float32) @ B.astype(np.float32).T
+    want2 = A2.astype(np.float32) @ B.astype(np.float32).T
+    got2 = run_umma(img_kmajor_sw128(A2), img_kmajor_sw128(B), desc(0, 16, 1024, 2), desc(0, 16, 1024, 2), 32, 32, 4,
+                    idesc(64, 112), 112 | (16 << 16))
+    lanes2 = [32 * (r // 16) + 16 + r % 16 for r in range(64)]
+    ok2 = np.allclose(got2[lanes2], want2, atol=1e-3)
+    got1 = run_umma(img_kmajor_sw128(A1), img_kmajor_sw128(B), desc(0, 16, 1024, 2), desc(0, 16, 1024, 2), 32, 32, 4,
+                    idesc(64, 112), 112)
+    lanes1 = [32 * (r // 16) + r % 16 for r in range(64)]
+    ok1 = np.allclose(got1[lanes1], want1, atol=1e-3)
+    record("umma_m64_lane_offset_16", ok1 and ok2, f"lane0 ok {ok1}, lane16 ok {ok2}")
 
 
 def run_tma(t, dims, strides, box, swizzle, coords):
