@@ -153,92 +153,116 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
 #endif
 
     if (warp == 4) {
-        if (lane == 0) {
+        // TMA producer: the whole warp runs the loops, one elected lane issues
+        if (elect_one_sync()) {
             mbar_expect_tx(rfull, NBLK * CF::REL_BLOCK);
             for (int kb = 0; kb < NBLK; ++kb) tma_load_2d(sm + CF::OFF_REL + kb * CF::REL_BLOCK, &mapR, rfull, kb * CB, 0);
-            uint32_t gq = 0, gv = 0, gt = 0;
-            for (int p = blockIdx.x; p < npairs; p += gridDim.x) {
-                const int wa = 2 * p, wb = (2 * p + 1 < nwin) ? 2 * p + 1 : 2 * p;
-                const WinCoord a = win_coord(wa, nwx, per_img), b = win_coord(wb, nwx, per_img);
-                for (int kb = 0; kb < NBLK; ++kb, ++gq) {
-                    const uint32_t s = gq % SQ, ph = (gq / SQ) & 1;
-                    uint8_t* st = sm + s * CF::QK_STAGE;
-                    mbar_wait(&q_empty[s], ph ^ 1);
+        }
+        uint32_t gq = 0, gv = 0, gt = 0;
+        (void)gt;
+        for (int p = blockIdx.x; p < npairs; p += gridDim.x) {
+            const int wa = 2 * p, wb = (2 * p + 1 < nwin) ? 2 * p + 1 : 2 * p;
+            const WinCoord a = win_coord(wa, nwx, per_img), b = win_coord(wb, nwx, per_img);
+            for (int kb = 0; kb < NBLK; ++kb, ++gq) {
+                const uint32_t s = gq % SQ, ph = (gq / SQ) & 1;
+                uint8_t* st = sm + s * CF::QK_STAGE;
+                mbar_wait(&q_empty[s], ph ^ 1);
+                if (elect_one_sync()) {
                     mbar_expect_tx(&q_full[s], CF::TX_QK);
                     tma_load_4d(st, &mapQ, &q_full[s], kb * CB, a.x, a.y, a.b);
                     tma_load_4d(st + 64 * ROWB, &mapQ, &q_full[s], kb * CB, b.x, b.y, b.b);
                     tma_load_4d(st + CF::QB, &mapKV, &q_full[s], C + kb * CB, a.x - 1, a.y - 1, a.b);
                     tma_load_4d(st + CF::QB + CF::WIN_B, &mapKV, &q_full[s], C + kb * CB, b.x - 1, b.y - 1, b.b);
                 }
-                for (int nb = 0; nb < NBLK; ++nb, ++gv) {
-                    const uint32_t s = gv % SV, ph = (gv / SV) & 1;
-                    uint8_t* st = sm + CF::OFF_V + s * CF::V_STAGE;
-                    mbar_wait(&v_empty[s], ph ^ 1);
-                    mbar_expect_tx(&v_full[s], CF::TX_V);
-                    tma_load_4d(st, &mapKV, &v_full[s], 2 * C + nb * CB, a.x - 1, a.y - 1, a.b);
-                    tma_load_4d(st + CF::WIN_B, &mapKV, &v_full[s], 2 * C + nb * CB, b.x - 1, b.y - 1, b.b);
-                }
+                __syncwarp();
+            }
+            // t_k rows first (their stages were released by the previous pair's epilogue), then V
+            auto load_t = [&](int nb) {
                 if constexpr (CF::TSTAGE) {
-                    for (int nb = 0; nb < NBLK; ++nb, ++gt) {
-                        const uint32_t s = gt & 1, ph = (gt >> 1) & 1;
-                        uint8_t* st = sm + CF::OFF_T + s * CF::T_STAGE;
-                        mbar_wait(&t_empty[s], ph ^ 1);
+                    const uint32_t s = gt & 1, ph = (gt >> 1) & 1;
+                    uint8_t* st = sm + CF::OFF_T + s * CF::T_STAGE;
+                    mbar_wait(&t_empty[s], ph ^ 1);
+                    if (elect_one_sync()) {
                         mbar_expect_tx(&t_full[s], CF::TX_T);
                         tma_load_4d(st, &mapT, &t_full[s], nb * CB, a.x, a.y, a.b);
                         tma_load_4d(st + 64 * ROWB, &mapT, &t_full[s], nb * CB, b.x, b.y, b.b);
                     }
+                    __syncwarp();
+                    ++gt;
                 }
+            };
+            if constexpr (CF::TSTAGE) { load_t(0); load_t(1); }
+            for (int nb = 0; nb < NBLK; ++nb, ++gv) {
+                const uint32_t s = gv % SV, ph = (gv / SV) & 1;
+                uint8_t* st = sm + CF::OFF_V + s * CF::V_STAGE;
+                mbar_wait(&v_empty[s], ph ^ 1);
+                if (elect_one_sync()) {
+                    mbar_expect_tx(&v_full[s], CF::TX_V);
+                    tma_load_4d(st, &mapKV, &v_full[s], 2 * C + nb * CB, a.x - 1, a.y - 1, a.b);
+                    tma_load_4d(st + CF::WIN_B, &mapKV, &v_full[s], 2 * C + nb * CB, b.x - 1, b.y - 1, b.b);
+                }
+                __syncwarp();
             }
+            if constexpr (CF::TSTAGE) { load_t(2); load_t(3); }
         }
     } else if (warp == 5) {
-        if (lane == 0) {
-            constexpr uint32_t id_s = umma_idesc_f16(64, WR), id_r = umma_idesc_f16(64, 32);
-            constexpr uint32_t id_o = umma_idesc_f16(64, CB, 0, 1);
-            mbar_wait(rfull, 0);
-            uint32_t gq = 0, gv = 0, it = 0;
-            for (int p = blockIdx.x; p < npairs; p += gridDim.x, ++it) {
-                // S and the rel columns, both windows
-                for (int kb = 0; kb < NBLK; ++kb, ++gq) {
-                    const uint32_t s = gq % SQ, ph = (gq / SQ) & 1;
-                    mbar_wait(&q_full[s], ph);
-                    tc_fence_after();
+        // MMA issuer: warp-uniform loops, one elected lane issues
+        constexpr uint32_t id_s = umma_idesc_f16(64, WR), id_r = umma_idesc_f16(64, 32);
+        constexpr uint32_t id_o = umma_idesc_f16(64, CB, 0, 1);
+        constexpr uint64_t tmpl = umma_smem_desc(0, 16, CF::SBO, CF::LAYOUT);
+        constexpr uint64_t tmpl_p = umma_smem_desc(0, 16, 1024, UMMA_LAYOUT_SW128);
+        mbar_wait(rfull, 0);
+        uint32_t gq = 0, gv = 0, it = 0;
+        for (int p = blockIdx.x; p < npairs; p += gridDim.x, ++it) {
+            // S and the rel columns, both windows
+            for (int kb = 0; kb < NBLK; ++kb, ++gq) {
+                const uint32_t s = gq % SQ, ph = (gq / SQ) & 1;
+                mbar_wait(&q_full[s], ph);
+                tc_fence_after();
+                if (elect_one_sync()) {
                     const uint32_t st = base + s * CF::QK_STAGE;
+                    const uint64_t dq0 = umma_desc_at(tmpl, st), dk0 = umma_desc_at(tmpl, st + CF::QB);
+                    const uint64_t dr0 = umma_desc_at(tmpl, base + CF::OFF_REL + kb * CF::REL_BLOCK);
 #pragma unroll
                     for (int k = 0; k < CB / 16; ++k) {
-                        const uint64_t dr = umma_smem_desc(base + CF::OFF_REL + kb * CF::REL_BLOCK + k * 32, 16, CF::SBO, CF::LAYOUT);
                         const uint32_t accum = (kb | k) ? 1u : 0u;
 #pragma unroll
                         for (int win = 0; win < 2; ++win) {
-                            const uint64_t dq = umma_smem_desc(st + win * 64 * ROWB + k * 32, 16, CF::SBO, CF::LAYOUT);
-                            const uint64_t dk = umma_smem_desc(st + CF::QB + win * CF::WIN_B + k * 32, 16, CF::SBO, CF::LAYOUT);
+                            const uint64_t dq = dq0 + (uint64_t)((win * 64 * ROWB + k * 32) >> 4);
+                            const uint64_t dk = dk0 + (uint64_t)((win * CF::WIN_B + k * 32) >> 4);
                             umma_f16_ss(tmem_base + TM_S + win * LANE_B, dq, dk, id_s, accum);
-                            umma_f16_ss(tmem_base + TM_REL + win * LANE_B, dq, dr, id_r, accum);
+                            umma_f16_ss(tmem_base + TM_REL + win * LANE_B, dq, dr0 + 2 * k, id_r, accum);
                         }
                     }
                     umma_commit(&q_empty[s]);
+                    if (kb == NBLK - 1) umma_commit(s_full);
                 }
-                umma_commit(s_full);
-                // O = P . V
-                mbar_wait(p_ready, it & 1);
-                mbar_wait(o_empty, (it & 1) ^ 1);
+                __syncwarp();
+            }
+            // O = P . V
+            mbar_wait(p_ready, it & 1);
+            mbar_wait(o_empty, (it & 1) ^ 1);
+            tc_fence_after();
+            for (int nb = 0; nb < NBLK; ++nb, ++gv) {
+                const uint32_t s = gv % SV, ph = (gv / SV) & 1;
+                mbar_wait(&v_full[s], ph);
                 tc_fence_after();
-                for (int nb = 0; nb < NBLK; ++nb, ++gv) {
-                    const uint32_t s = gv % SV, ph = (gv / SV) & 1;
-                    mbar_wait(&v_full[s], ph);
-                    tc_fence_after();
-                    const uint32_t vb = base + CF::OFF_V + s * CF::V_STAGE;
+                if (elect_one_sync()) {
+                    const uint64_t dv0 = umma_desc_at(tmpl, base + CF::OFF_V + s * CF::V_STAGE);
+                    const uint64_t dp0 = umma_desc_at(tmpl_p, base + CF::OFF_P);
 #pragma unroll
                     for (int win = 0; win < 2; ++win) {
 #pragma unroll
                         for (int k = 0; k < WR / 16; ++k) {
-                            const uint64_t dp = umma_smem_desc(base + CF::OFF_P + win * 16384 + (k >> 2) * 8192 + (k & 3) * 32, 16, 1024, UMMA_LAYOUT_SW128);
-                            const uint64_t dv = umma_smem_desc(vb + win * CF::WIN_B + k * 16 * ROWB, 16, CF::SBO, CF::LAYOUT);
+                            const uint64_t dp = dp0 + (uint64_t)((win * 16384 + (k >> 2) * 8192 + (k & 3) * 32) >> 4);
+                            const uint64_t dv = dv0 + (uint64_t)((win * CF::WIN_B + k * 16 * ROWB) >> 4);
                             umma_f16_ss(tmem_base + TM_O + nb * CB + win * LANE_B, dp, dv, id_o, k ? 1u : 0u);
                         }
                     }
                     umma_commit(&v_empty[s]);
+                    if (nb == NBLK - 1) umma_commit(o_full);
                 }
-                umma_commit(o_full);
+                __syncwarp();
             }
         }
     } else {

@@ -67,45 +67,52 @@ ffconv_umma_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_consta
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 4) {
-        if (lane == 0) {
+        // TMA producer: the whole warp runs the loop, one elected lane issues
+        if (elect_one_sync()) {
             mbar_expect_tx(wfull, CU_W_BYTES);
             for (int tap = 0; tap < 9; ++tap) tma_load_2d(sm + tap * NF * 128, &mapW, wfull, 0, tap * NF);
-            uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-                const int b = tile / per_img, r = tile - b * per_img;
-                const int y0 = (r / tiles_x) * CU_TH, x0 = (r % tiles_x) * CU_TW;
-                const uint32_t s = it % CU_STAGES, ph = (it / CU_STAGES) & 1;
-                mbar_wait(&empty[s], ph ^ 1);
+        }
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            const int b = tile / per_img, r = tile - b * per_img;
+            const int y0 = (r / tiles_x) * CU_TH, x0 = (r % tiles_x) * CU_TW;
+            const uint32_t s = it % CU_STAGES, ph = (it / CU_STAGES) & 1;
+            mbar_wait(&empty[s], ph ^ 1);
+            if (elect_one_sync()) {
                 mbar_expect_tx(&full[s], CU_TILE_BYTES);
                 tma_load_4d(sm + CU_OFF_A + s * CU_STAGE, &mapY, &full[s], 0, x0 - 1, y0 - 1, b);
             }
+            __syncwarp();
         }
     } else if (warp == 5) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_f16(128, NF);
-            mbar_wait(wfull, 0);
-            uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-                const uint32_t s = it % CU_STAGES, ph = (it / CU_STAGES) & 1;
-                const uint32_t acc = it & 1, aph = (it >> 1) & 1;
-                mbar_wait(&tempty[acc], aph ^ 1);
-                mbar_wait(&full[s], ph);
-                tc_fence_after();
-                const uint32_t a_base = base + CU_OFF_A + s * CU_STAGE;
+        // MMA issuer: warp-uniform loop, one elected lane issues the 36 MMAs of a tile and the two commits
+        constexpr uint32_t idesc = umma_idesc_f16(128, NF);
+        constexpr uint64_t tmpl_a = umma_smem_desc(0, 16, CU_HW * 128, UMMA_LAYOUT_SW128);
+        constexpr uint64_t tmpl_b = umma_smem_desc(0, 16, 1024, UMMA_LAYOUT_SW128);
+        mbar_wait(wfull, 0);
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            const uint32_t s = it % CU_STAGES, ph = (it / CU_STAGES) & 1;
+            const uint32_t acc = it & 1, aph = (it >> 1) & 1;
+            mbar_wait(&tempty[acc], aph ^ 1);
+            mbar_wait(&full[s], ph);
+            tc_fence_after();
+            if (elect_one_sync()) {
+                const uint64_t da0 = umma_desc_at(tmpl_a, base + CU_OFF_A + s * CU_STAGE);
+                const uint64_t db0 = umma_desc_at(tmpl_b, base);
 #pragma unroll
                 for (int tap = 0; tap < 9; ++tap) {
-                    const uint32_t a_tap = a_base + ((tap / 3) * CU_HW + (tap % 3)) * 128;
-                    const uint32_t b_tap = base + tap * NF * 128;
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        const uint64_t da = umma_smem_desc(a_tap + k * 32, 16, CU_HW * 128, UMMA_LAYOUT_SW128);
-                        const uint64_t db = umma_smem_desc(b_tap + k * 32, 16, 1024, UMMA_LAYOUT_SW128);
+                        const uint64_t da = da0 + (uint64_t)((((tap / 3) * CU_HW + (tap % 3)) * 128 + k * 32) >> 4);
+                        const uint64_t db = db0 + (uint64_t)((tap * NF * 128 + k * 32) >> 4);
                         umma_f16_ss(tmem_base + acc * NF, da, db, idesc, (tap | k) ? 1u : 0u);
                     }
                 }
                 umma_commit(&empty[s]);
                 umma_commit(&tfull[acc]);
             }
+            __syncwarp();
         }
     } else {
         uint32_t it = 0;

@@ -75,43 +75,47 @@ qkv_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 4) {
-        if (lane == 0) {
+        // TMA producer: warp-uniform loop, one elected lane issues
+        if (elect_one_sync()) {
             mbar_expect_tx(bfull, KB * CF::B_BLOCK);
             for (int kb = 0; kb < KB; ++kb) tma_load_2d(sB + kb * CF::B_BLOCK, &mapW, bfull, kb * CB, chunk * NT);
-            uint32_t it = 0;
-            for (int mt = first; mt < num_mt; mt += stride) {
-                for (int kb = 0; kb < KB; ++kb, ++it) {
-                    const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
-                    mbar_wait(&empty[s], ph ^ 1);
+        }
+        uint32_t it = 0;
+        for (int mt = first; mt < num_mt; mt += stride) {
+            for (int kb = 0; kb < KB; ++kb, ++it) {
+                const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+                mbar_wait(&empty[s], ph ^ 1);
+                if (elect_one_sync()) {
                     mbar_expect_tx(&full[s], CF::A_STAGE);
                     tma_load_2d(sA + s * CF::A_STAGE, &mapA, &full[s], kb * CB, mt * 128);
                 }
+                __syncwarp();
             }
         }
     } else if (warp == 5) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_f16(128, NT);
-            mbar_wait(bfull, 0);
-            uint32_t it = 0, t = 0;
-            for (int mt = first; mt < num_mt; mt += stride, ++t) {
-                const uint32_t acc = t & 1, aph = (t >> 1) & 1;
-                mbar_wait(&tempty[acc], aph ^ 1);
+        // MMA issuer: warp-uniform loop, one elected lane issues
+        constexpr uint32_t idesc = umma_idesc_f16(128, NT);
+        constexpr uint64_t tmpl = umma_smem_desc(0, 16, CF::SBO, CF::LAYOUT);
+        mbar_wait(bfull, 0);
+        uint32_t it = 0, t = 0;
+        for (int mt = first; mt < num_mt; mt += stride, ++t) {
+            const uint32_t acc = t & 1, aph = (t >> 1) & 1;
+            mbar_wait(&tempty[acc], aph ^ 1);
+            tc_fence_after();
+            for (int kb = 0; kb < KB; ++kb, ++it) {
+                const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+                mbar_wait(&full[s], ph);
                 tc_fence_after();
-                for (int kb = 0; kb < KB; ++kb, ++it) {
-                    const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
-                    mbar_wait(&full[s], ph);
-                    tc_fence_after();
-                    const uint32_t a_addr = base + CF::B_BYTES + s * CF::A_STAGE;
-                    const uint32_t b_addr = base + kb * CF::B_BLOCK;
+                if (elect_one_sync()) {
+                    const uint64_t da0 = umma_desc_at(tmpl, base + CF::B_BYTES + s * CF::A_STAGE);
+                    const uint64_t db0 = umma_desc_at(tmpl, base + kb * CF::B_BLOCK);
 #pragma unroll
-                    for (int k = 0; k < CF::KSTEPS; ++k) {
-                        const uint64_t da = umma_smem_desc(a_addr + k * 32, 16, CF::SBO, CF::LAYOUT);
-                        const uint64_t db = umma_smem_desc(b_addr + k * 32, 16, CF::SBO, CF::LAYOUT);
-                        umma_f16_ss(tmem_base + acc * 256, da, db, idesc, (kb | k) ? 1u : 0u);
-                    }
+                    for (int k = 0; k < CF::KSTEPS; ++k)
+                        umma_f16_ss(tmem_base + acc * 256, da0 + 2 * k, db0 + 2 * k, idesc, (kb | k) ? 1u : 0u);
                     umma_commit(&empty[s]);
+                    if (kb == KB - 1) umma_commit(&tfull[acc]);
                 }
-                umma_commit(&tfull[acc]);
+                __syncwarp();
             }
         }
     } else {

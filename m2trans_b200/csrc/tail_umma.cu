@@ -78,40 +78,44 @@ tail_up_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 4) {
-        if (lane == 0) {
+        // TMA producer: warp-uniform loop, one elected lane issues
+        if (elect_one_sync()) {
             mbar_expect_tx(wfull, CF::W_BYTES);
             for (int ch = 0; ch < NCH; ++ch) tma_load_2d(sm + ch * NT * 128, &mapW, wfull, 0, ch * NT);
-            uint32_t it = 0;
-            for (int mt = blockIdx.x; mt < num_mt; mt += gridDim.x, ++it) {
-                const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
-                mbar_wait(&empty[s], ph ^ 1);
+        }
+        uint32_t it = 0;
+        for (int mt = blockIdx.x; mt < num_mt; mt += gridDim.x, ++it) {
+            const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+            mbar_wait(&empty[s], ph ^ 1);
+            if (elect_one_sync()) {
                 mbar_expect_tx(&full[s], CF::A_STAGE);
                 tma_load_2d(sm + CF::OFF_A + s * CF::A_STAGE, &mapA, &full[s], 0, mt * 128);
             }
+            __syncwarp();
         }
     } else if (warp == 5) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_f16(128, NT);
-            mbar_wait(wfull, 0);
-            uint32_t it = 0, u = 0;
-            for (int mt = blockIdx.x; mt < num_mt; mt += gridDim.x, ++it) {
-                const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
-                mbar_wait(&full[s], ph);
+        // MMA issuer: warp-uniform loop, one elected lane issues
+        constexpr uint32_t idesc = umma_idesc_f16(128, NT);
+        constexpr uint64_t tmpl = umma_smem_desc(0, 16, 1024, UMMA_LAYOUT_SW128);
+        mbar_wait(wfull, 0);
+        uint32_t it = 0, u = 0;
+        for (int mt = blockIdx.x; mt < num_mt; mt += gridDim.x, ++it) {
+            const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+            mbar_wait(&full[s], ph);
+            tc_fence_after();
+            const uint64_t da0 = umma_desc_at(tmpl, base + CF::OFF_A + s * CF::A_STAGE);
+            for (int ch = 0; ch < NCH; ++ch, ++u) {
+                const uint32_t acc = u & 1, aph = (u >> 1) & 1;
+                mbar_wait(&tempty[acc], aph ^ 1);
                 tc_fence_after();
-                const uint32_t a_addr = base + CF::OFF_A + s * CF::A_STAGE;
-                for (int ch = 0; ch < NCH; ++ch, ++u) {
-                    const uint32_t acc = u & 1, aph = (u >> 1) & 1;
-                    mbar_wait(&tempty[acc], aph ^ 1);
-                    tc_fence_after();
+                if (elect_one_sync()) {
+                    const uint64_t db0 = umma_desc_at(tmpl, base + ch * NT * 128);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const uint64_t da = umma_smem_desc(a_addr + k * 32, 16, 1024, UMMA_LAYOUT_SW128);
-                        const uint64_t db = umma_smem_desc(base + ch * NT * 128 + k * 32, 16, 1024, UMMA_LAYOUT_SW128);
-                        umma_f16_ss(tmem_base + acc * 256, da, db, idesc, k ? 1u : 0u);
-                    }
+                    for (int k = 0; k < 4; ++k) umma_f16_ss(tmem_base + acc * 256, da0 + 2 * k, db0 + 2 * k, idesc, k ? 1u : 0u);
                     umma_commit(&tfull[acc]);
+                    if (ch == NCH - 1) umma_commit(&empty[s]);
                 }
-                umma_commit(&empty[s]);
+                __syncwarp();
             }
         }
     } else {
@@ -241,45 +245,53 @@ tail_out_umma_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_cons
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 4) {
-        if (lane == 0) {
+        // TMA producer: warp-uniform loop, one elected lane issues
+        if (elect_one_sync()) {
             mbar_expect_tx(wfull, TO_W_BYTES);
             tma_load_2d(sm, &mapW, wfull, 0, 0);
-            uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-                const int bl = tile / per_img, r = tile - bl * per_img;
-                const int y0 = (r / tiles_x) * TO_TH, x0 = (r % tiles_x) * TO_TW;
-                const uint32_t s = it % TO_STAGES, ph = (it / TO_STAGES) & 1;
-                mbar_wait(&empty[s], ph ^ 1);
+        }
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            const int bl = tile / per_img, r = tile - bl * per_img;
+            const int y0 = (r / tiles_x) * TO_TH, x0 = (r % tiles_x) * TO_TW;
+            const uint32_t s = it % TO_STAGES, ph = (it / TO_STAGES) & 1;
+            mbar_wait(&empty[s], ph ^ 1);
+            if (elect_one_sync()) {
                 mbar_expect_tx(&full[s], TO_TILE_BYTES);
                 // the tensor has a 1-pixel border: halo origin (y0-1, x0-1) is (y0, x0) in its coordinates
                 tma_load_4d(sm + TO_OFF_A + s * TO_STAGE, &mapT, &full[s], 0, x0, y0, bl);
             }
+            __syncwarp();
         }
     } else if (warp == 5) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_f16(128, TO_N);
-            mbar_wait(wfull, 0);
-            uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-                const uint32_t s = it % TO_STAGES, ph = (it / TO_STAGES) & 1;
-                const uint32_t acc = it & 1, aph = (it >> 1) & 1;
-                mbar_wait(&tempty[acc], aph ^ 1);
-                mbar_wait(&full[s], ph);
-                tc_fence_after();
-                const uint32_t a_base = base + TO_OFF_A + s * TO_STAGE;
+        // MMA issuer: warp-uniform loop, one elected lane issues
+        constexpr uint32_t idesc = umma_idesc_f16(128, TO_N);
+        constexpr uint64_t tmpl_a = umma_smem_desc(0, 16, TO_HW * 128, UMMA_LAYOUT_SW128);
+        constexpr uint64_t tmpl_b = umma_smem_desc(0, 16, 1024, UMMA_LAYOUT_SW128);
+        mbar_wait(wfull, 0);
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            const uint32_t s = it % TO_STAGES, ph = (it / TO_STAGES) & 1;
+            const uint32_t acc = it & 1, aph = (it >> 1) & 1;
+            mbar_wait(&tempty[acc], aph ^ 1);
+            mbar_wait(&full[s], ph);
+            tc_fence_after();
+            if (elect_one_sync()) {
+                const uint64_t da0 = umma_desc_at(tmpl_a, base + TO_OFF_A + s * TO_STAGE);
+                const uint64_t db0 = umma_desc_at(tmpl_b, base);
 #pragma unroll
                 for (int tap = 0; tap < 9; ++tap) {
-                    const uint32_t a_tap = a_base + ((tap / 3) * TO_HW + (tap % 3)) * 128;
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        const uint64_t da = umma_smem_desc(a_tap + k * 32, 16, TO_HW * 128, UMMA_LAYOUT_SW128);
-                        const uint64_t db = umma_smem_desc(base + tap * TO_N * 128 + k * 32, 16, 1024, UMMA_LAYOUT_SW128);
+                        const uint64_t da = da0 + (uint64_t)((((tap / 3) * TO_HW + (tap % 3)) * 128 + k * 32) >> 4);
+                        const uint64_t db = db0 + (uint64_t)((tap * TO_N * 128 + k * 32) >> 4);
                         umma_f16_ss(tmem_base + acc * TO_N, da, db, idesc, (tap | k) ? 1u : 0u);
                     }
                 }
                 umma_commit(&empty[s]);
                 umma_commit(&tfull[acc]);
             }
+            __syncwarp();
         }
     } else {
         uint32_t it = 0;

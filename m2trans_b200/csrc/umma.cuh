@@ -12,6 +12,20 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return (uint32_t)__cvta_generic_to_shared(p);
 }
 
+// One lane of a converged warp.  The TMA / MMA warps run their loops warp-uniformly and issue the
+// uniform-datapath instructions (UTMALDG, UTCHMMA, commits) under this predicate: issuing them from an
+// `if (lane == 0)` region instead makes ptxas wrap every one in a divergence loop (~13 SASS instructions per MMA).
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred = 0, laneid = 0;
+    asm volatile(
+        "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+        "elect.sync rx|px, 0xffffffff;\n\t"
+        "@px mov.s32 %1, 1;\n\t"
+        "mov.s32 %0, rx;\n\t}"
+        : "+r"(laneid), "+r"(pred));
+    return pred != 0;
+}
+
 // ---- mbarrier -------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -159,6 +173,9 @@ __host__ __device__ constexpr uint64_t umma_smem_desc(uint32_t start_bytes, uint
     return (uint64_t)((start_bytes >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
            ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | (layout << 61);
 }
+// Same descriptor from a template with start = 0 and a shared-memory byte address (< 256 KB, so address >> 4
+// never carries out of the 14-bit field): one shift + one add per MMA on the issuing thread.
+__device__ __forceinline__ uint64_t umma_desc_at(uint64_t tmpl, uint32_t addr) { return tmpl + (uint64_t)(addr >> 4); }
 // add a byte offset (multiple of 16) to the start-address field
 __device__ __forceinline__ uint64_t umma_desc_advance(uint64_t desc, uint32_t bytes) {
     const uint32_t lo = (uint32_t)desc;
