@@ -2,6 +2,7 @@
 // entry points.  The forward is a fixed sequence of kernel launches on the caller's stream; it never
 // synchronises, allocates or touches host memory, so the Python side can capture it in a CUDA graph.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <new>
 
@@ -33,6 +34,15 @@ int device_sm_count() {
         cached[dev] = n;
     }
     return cached[dev];
+}
+
+bool pdl_enabled() {
+    static int cached = -1;
+    if (cached < 0) {
+        const char* e = getenv("M2T_NO_PDL");      // development switch for A/B timing
+        cached = (e && e[0] == '1') ? 0 : 1;
+    }
+    return cached == 1;
 }
 
 static int check_device() {

@@ -148,16 +148,18 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
     const uint32_t tmem_base = *tmem_slot;
     constexpr uint32_t TM_S = 0, TM_REL = CF::TM_REL, TM_O = CF::TM_O;
     constexpr uint32_t LANE_B = 16u << 16;                      // TMEM lane offset of window B
+    pdl_trigger();
 #ifdef M2T_TIMING
     if (blockIdx.x == 0 && tid == 0) g_attn_dbg[7] = clock64();
 #endif
 
     if (warp == 4) {
         // TMA producer: the whole warp runs the loops, one elected lane issues
-        if (elect_one_sync()) {
+        if (elect_one_sync()) {      // rel tables are constants: loaded while the previous kernel drains
             mbar_expect_tx(rfull, NBLK * CF::REL_BLOCK);
             for (int kb = 0; kb < NBLK; ++kb) tma_load_2d(sm + CF::OFF_REL + kb * CF::REL_BLOCK, &mapR, rfull, kb * CB, 0);
         }
+        pdl_wait();
         uint32_t gq = 0, gv = 0, gt = 0;
         (void)gt;
         for (int p = blockIdx.x; p < npairs; p += gridDim.x) {
@@ -272,6 +274,7 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
         uint8_t* prow = sm + CF::OFF_P + win * 16384 + qi * 128;
         uint32_t it = 0, gt = 0;
         (void)gt;
+        pdl_wait();
         for (int p = blockIdx.x; p < npairs; p += gridDim.x, ++it) {
             M2T_T(0);
             mbar_wait(s_full, it & 1);
@@ -512,8 +515,7 @@ static int launch_attn_umma_cf(const __half* QKV, const __half* relx, __half* O,
     const int cap = device_sm_count() * CF::MIN_CTAS;
     const int grid = npairs < cap ? npairs : cap;
     M2T_ENSURE_SMEM((attn_umma_kernel<C, FUSE>), CF::SMEM);
-    attn_umma_kernel<C, FUSE><<<grid, 192, CF::SMEM, s>>>(mapQ, mapKV, mapR, mapT, O, h, w, nwin, fz);
-    M2T_LAUNCH_CHECK("attn_umma_kernel");
+    M2T_CUDA(launch_pdl(attn_umma_kernel<C, FUSE>, dim3(grid), dim3(192), CF::SMEM, s, mapQ, mapKV, mapR, mapT, O, h, w, nwin, fz));
     return M2T_OK;
 }
 

@@ -73,6 +73,8 @@ branch_prep_kernel(int branch, const float* __restrict__ X, const float2* __rest
     constexpr int S = 1 << L;             // full-res pixels per level pixel, per axis
     constexpr int C = NB << (2 * L);      // channels at this level
     const int hl = Hp >> L, wl = Wp >> L;
+    pdl_trigger();
+    pdl_wait();
     const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
     const long total = (long)B * hl * wl * 4;
     if (tid >= total) return;
@@ -183,10 +185,9 @@ int launch_branch_prep(int level, int branch, const float* X, const float2* muno
                        const Geom& g, cudaStream_t s) {
     const long total = (long)g.B * (g.Hp >> level) * (g.Wp >> level) * 4;
     const unsigned grid = (unsigned)((total + 127) / 128);
-    if (level == 0) branch_prep_kernel<0><<<grid, 128, 0, s>>>(branch, X, munorm, Y, Z, g.B, g.Hp, g.Wp);
-    else if (level == 1) branch_prep_kernel<1><<<grid, 128, 0, s>>>(branch, X, munorm, Y, Z, g.B, g.Hp, g.Wp);
-    else branch_prep_kernel<2><<<grid, 128, 0, s>>>(branch, X, munorm, Y, Z, g.B, g.Hp, g.Wp);
-    M2T_LAUNCH_CHECK("branch_prep_kernel");
+    if (level == 0) M2T_CUDA(launch_pdl(branch_prep_kernel<0>, dim3(grid), dim3(128), 0, s, branch, X, munorm, Y, Z, g.B, g.Hp, g.Wp));
+    else if (level == 1) M2T_CUDA(launch_pdl(branch_prep_kernel<1>, dim3(grid), dim3(128), 0, s, branch, X, munorm, Y, Z, g.B, g.Hp, g.Wp));
+    else M2T_CUDA(launch_pdl(branch_prep_kernel<2>, dim3(grid), dim3(128), 0, s, branch, X, munorm, Y, Z, g.B, g.Hp, g.Wp));
     return M2T_OK;
 }
 

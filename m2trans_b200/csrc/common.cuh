@@ -54,6 +54,29 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 
 int device_sm_count();
 
+// ---- programmatic dependent launch ---------------------------------------------------------------------
+// Every kernel of the forward is launched with programmatic stream serialisation: its CTAs may start while
+// the previous kernel drains, run their prologue (barrier init, TMEM alloc, weight loads: nothing that depends
+// on the previous kernel) and then block in pdl_wait() until the previous grid has completed and flushed.
+// Rule: no thread reads activations or writes ANY global memory before pdl_wait().
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                              Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 

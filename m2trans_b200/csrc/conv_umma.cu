@@ -65,13 +65,15 @@ ffconv_umma_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_trigger();                              // the next kernel may start its own prologue
 
     if (warp == 4) {
         // TMA producer: the whole warp runs the loop, one elected lane issues
         if (elect_one_sync()) {
-            mbar_expect_tx(wfull, CU_W_BYTES);
+            mbar_expect_tx(wfull, CU_W_BYTES);   // weights are constants: loaded while the previous kernel drains
             for (int tap = 0; tap < 9; ++tap) tma_load_2d(sm + tap * NF * 128, &mapW, wfull, 0, tap * NF);
         }
+        pdl_wait();
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             const int b = tile / per_img, r = tile - b * per_img;
@@ -115,6 +117,7 @@ ffconv_umma_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_consta
             __syncwarp();
         }
     } else {
+        pdl_wait();
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             const int b = tile / per_img, r = tile - b * per_img;
@@ -161,8 +164,8 @@ int launch_ffconv_umma(const __half* Y, const __half* Wpk, const float* bias, co
     M2T_ENSURE_SMEM(ffconv_umma_kernel, CU_SMEM);
     const int ntiles = g.B * (g.Hp / CU_TH) * (g.Wp / CU_TW);
     const int grid = ntiles < device_sm_count() ? ntiles : device_sm_count();
-    ffconv_umma_kernel<<<grid, 192, CU_SMEM, s>>>(mapY, mapW, bias, Xin, Xout, stats, g.B, g.Hp, g.Wp, res, xr);
-    M2T_LAUNCH_CHECK("ffconv_umma_kernel");
+    M2T_CUDA(launch_pdl(ffconv_umma_kernel, dim3(grid), dim3(192), CU_SMEM, s, mapY, mapW, bias, Xin, Xout, stats, g.B, g.Hp,
+                        g.Wp, res, xr));
     return M2T_OK;
 }
 

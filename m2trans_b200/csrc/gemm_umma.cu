@@ -73,13 +73,15 @@ qkv_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_trigger();
 
     if (warp == 4) {
         // TMA producer: warp-uniform loop, one elected lane issues
-        if (elect_one_sync()) {
+        if (elect_one_sync()) {      // the weight slab is constant: loaded while the previous kernel drains
             mbar_expect_tx(bfull, KB * CF::B_BLOCK);
             for (int kb = 0; kb < KB; ++kb) tma_load_2d(sB + kb * CF::B_BLOCK, &mapW, bfull, kb * CB, chunk * NT);
         }
+        pdl_wait();
         uint32_t it = 0;
         for (int mt = first; mt < num_mt; mt += stride) {
             for (int kb = 0; kb < KB; ++kb, ++it) {
@@ -119,6 +121,7 @@ qkv_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             }
         }
     } else {
+        pdl_wait();
         uint32_t t = 0;
         for (int mt = first; mt < num_mt; mt += stride, ++t) {
             const uint32_t acc = t & 1, aph = (t >> 1) & 1;
@@ -177,8 +180,7 @@ static int launch_qkv_umma_c(const __half* Z, const __half* Wqkv, __half* QKV, i
     int per_chunk = device_sm_count() / CF::NCHUNK;
     if (per_chunk > num_mt) per_chunk = num_mt;
     if (per_chunk < 1) per_chunk = 1;
-    qkv_umma_kernel<C><<<per_chunk * CF::NCHUNK, 192, CF::SMEM, s>>>(mapA, mapW, QKV, M);
-    M2T_LAUNCH_CHECK("qkv_umma_kernel");
+    M2T_CUDA(launch_pdl(qkv_umma_kernel<C>, dim3(per_chunk * CF::NCHUNK), dim3(192), CF::SMEM, s, mapA, mapW, QKV, M));
     return M2T_OK;
 }
 

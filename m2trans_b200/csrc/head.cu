@@ -22,6 +22,8 @@ head_conv_kernel(const float* __restrict__ x, const float* __restrict__ w, const
     const int t = threadIdx.x;
     for (int i = t; i < 27 * NF; i += blockDim.x) sw[i] = w[i];
     if (t < NF) sb[t] = bias[t];
+    pdl_trigger();
+    pdl_wait();          // weights above are constants; everything below touches activations / statistics
     __syncthreads();
 
     const int q = t & 3;
@@ -94,15 +96,16 @@ head_conv_kernel(const float* __restrict__ x, const float* __restrict__ w, const
 int launch_head(const float* x, const float* w, const float* b, float* res, double* stats, const Geom& g,
                 cudaStream_t s) {
     const long total = (long)g.B * g.Hp * g.Wp;
-    head_conv_kernel<<<(unsigned)(total / HEAD_PX), HEAD_PX * 4, 0, s>>>(x, w, b, res, stats, g.B, g.H, g.W,
-                                                                         g.Hp, g.Wp);
-    M2T_LAUNCH_CHECK("head_conv_kernel");
+    M2T_CUDA(launch_pdl(head_conv_kernel, dim3((unsigned)(total / HEAD_PX)), dim3(HEAD_PX * 4), 0, s, x, w, b, res, stats,
+                        g.B, g.H, g.W, g.Hp, g.Wp));
     return M2T_OK;
 }
 
 // (sum, sumsq) -> (mean, 1/sqrt(var+eps)), biased variance (ref :127 nn.InstanceNorm2d defaults)
 __global__ void stats_finalize_kernel(const double* __restrict__ stats, float2* __restrict__ munorm, int n,
                                       double inv_npix) {
+    pdl_trigger();
+    pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const double m = stats[2 * i] * inv_npix;
@@ -113,8 +116,7 @@ __global__ void stats_finalize_kernel(const double* __restrict__ stats, float2* 
 
 int launch_stats_finalize(const double* stats, float2* munorm, int B, int npix, cudaStream_t s) {
     const int n = B * NF;
-    stats_finalize_kernel<<<cdiv(n, 128), 128, 0, s>>>(stats, munorm, n, 1.0 / (double)npix);
-    M2T_LAUNCH_CHECK("stats_finalize_kernel");
+    M2T_CUDA(launch_pdl(stats_finalize_kernel, dim3(cdiv(n, 128)), dim3(128), 0, s, stats, munorm, n, 1.0 / (double)npix));
     return M2T_OK;
 }
 

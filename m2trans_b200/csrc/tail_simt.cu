@@ -84,6 +84,8 @@ int launch_tail_up_simt(const __half* Ain, const __half* Wt, const float* bias, 
 // One thread per (ring pixel, 16-byte chunk).  Ring pixels of a (h+2) x (w+2) frame: 2 (w+2) + 2 h.
 __global__ void reflect_border_kernel(__half* __restrict__ T, int B, int h, int w) {
     const int ring = 2 * (w + 2) + 2 * h;
+    pdl_trigger();
+    pdl_wait();
     const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long)B * ring * 8) return;
     const int ch = (int)(idx & 7);
@@ -105,8 +107,7 @@ __global__ void reflect_border_kernel(__half* __restrict__ T, int B, int h, int 
 
 int launch_reflect_border(__half* T, int B, int h, int w, cudaStream_t s) {
     const long total = (long)B * (2 * (w + 2) + 2 * h) * 8;
-    reflect_border_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(T, B, h, w);
-    M2T_LAUNCH_CHECK("reflect_border_kernel");
+    M2T_CUDA(launch_pdl(reflect_border_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, T, B, h, w));
     return M2T_OK;
 }
 

@@ -76,6 +76,7 @@ tail_up_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_trigger();
 
     if (warp == 4) {
         // TMA producer: warp-uniform loop, one elected lane issues
@@ -83,6 +84,7 @@ tail_up_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
             mbar_expect_tx(wfull, CF::W_BYTES);
             for (int ch = 0; ch < NCH; ++ch) tma_load_2d(sm + ch * NT * 128, &mapW, wfull, 0, ch * NT);
         }
+        pdl_wait();
         uint32_t it = 0;
         for (int mt = blockIdx.x; mt < num_mt; mt += gridDim.x, ++it) {
             const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
@@ -121,6 +123,7 @@ tail_up_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     } else {
         const int hr = h * R, wr = w * R;
         const long orow_pitch = (long)(wr + 2 * pad) * NF;
+        pdl_wait();
         uint32_t u = 0;
         for (int mt = blockIdx.x; mt < num_mt; mt += gridDim.x) {
             const int gp = mt * 128 + tid;
@@ -186,8 +189,7 @@ static int launch_tail_up_umma_r(const __half* A, const __half* Wt, const float*
     M2T_ENSURE_SMEM(tail_up_umma_kernel<R>, CF::SMEM);
     const int num_mt = M / 128;
     const int grid = num_mt < device_sm_count() ? num_mt : device_sm_count();
-    tail_up_umma_kernel<R><<<grid, 192, CF::SMEM, s>>>(mapA, mapW, bias, out, M, h, w, pad);
-    M2T_LAUNCH_CHECK("tail_up_umma_kernel");
+    M2T_CUDA(launch_pdl(tail_up_umma_kernel<R>, dim3(grid), dim3(192), CF::SMEM, s, mapA, mapW, bias, out, M, h, w, pad));
     return M2T_OK;
 }
 
@@ -243,6 +245,7 @@ tail_out_umma_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_cons
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_trigger();
 
     if (warp == 4) {
         // TMA producer: warp-uniform loop, one elected lane issues
@@ -250,6 +253,7 @@ tail_out_umma_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_cons
             mbar_expect_tx(wfull, TO_W_BYTES);
             tma_load_2d(sm, &mapW, wfull, 0, 0);
         }
+        pdl_wait();
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             const int bl = tile / per_img, r = tile - bl * per_img;
@@ -294,6 +298,7 @@ tail_out_umma_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_cons
             __syncwarp();
         }
     } else {
+        pdl_wait();
         uint32_t it = 0;
         const long plane = (long)hout * wout;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
@@ -338,8 +343,7 @@ int launch_tail_out_umma(const __half* T, const __half* Wc, float* y, int Bc, in
     M2T_ENSURE_SMEM(tail_out_umma_kernel, TO_SMEM_U);
     const int ntiles = Bc * ((hout + TO_TH - 1) / TO_TH) * ((wout + TO_TW - 1) / TO_TW);
     const int grid = ntiles < device_sm_count() ? ntiles : device_sm_count();
-    tail_out_umma_kernel<<<grid, 192, TO_SMEM_U, s>>>(mapT, mapW, y, Bc, hout, wout, b0, rgb_range);
-    M2T_LAUNCH_CHECK("tail_out_umma_kernel");
+    M2T_CUDA(launch_pdl(tail_out_umma_kernel, dim3(grid), dim3(192), TO_SMEM_U, s, mapT, mapW, y, Bc, hout, wout, b0, rgb_range));
     return M2T_OK;
 }
 
