@@ -68,7 +68,7 @@ struct m2t_plan {
     PackedLayout L;
     int tail_chunk;            // images per tail pass
     // workspace byte offsets
-    size_t o_res, o_x, o_y, o_z, o_qkv, o_o, o_stats, o_munorm, o_xr, o_t1, ws_bytes;
+    size_t o_res, o_x, o_y, o_z, o_qkv, o_o, o_h3, o_h4, o_stats, o_munorm, o_xr, o_t1, ws_bytes;
     int n_launches;
 };
 
@@ -174,6 +174,8 @@ int m2t_plan_create(const m2t_cfg* cfg, m2t_plan** out) {
     p->o_z = take(P * NB * 2);
     p->o_qkv = take(P * NB * 3 * 2);
     p->o_o = take(P * NB * 2);
+    p->o_h3 = take(P * NB * 2);
+    p->o_h4 = take(P * NB * 2);
     p->o_stats = take((size_t)(cfg->n_blocks + 1) * g.B * NF * 2 * sizeof(double));
     p->o_munorm = take((size_t)g.B * NF * sizeof(float2));
     // tail scratch: process images in chunks of at most ~2 GiB of intermediates
@@ -289,19 +291,18 @@ int m2t_forward(const m2t_plan* plan, const void* d_packed, const float* d_x, fl
     for (int i = 0; i < plan->cfg.n_blocks; ++i) {
         M2T_TRY(launch_stats_finalize(stats + i * stat_stride, munorm, g.B, npix, s));
         if (fused) {
-            __half* Tcur = Z;      // t_k in space-to-depth order, ping-pong between the Z and O buffers
-            __half* Tnxt = O;
-            M2T_TRY(launch_branch_prep(0, 0, Xin, munorm, Y, Tcur, g, s));          // t_1 = n_1 (ref :137-139)
+            // t_1 = n_1 and n_k/2 (k = 2..4) in their consumers' space-to-depth layouts, one pass over X (ref :135-137)
+            __half* Tb[4] = {Z, O, reinterpret_cast<__half*>(ws + plan->o_h3), reinterpret_cast<__half*>(ws + plan->o_h4)};
+            M2T_TRY(launch_branch_prep_all(Xin, munorm, Tb[0], Tb[1], Tb[2], Tb[3], g, s));
             for (int a = 0; a < 4; ++a) {
                 const int lv = branch_level(a), C = branch_ch(a);
                 const int h = g.Hp >> lv, w = g.Wp >> lv;
                 const AttnW& A = L.blk[i].attn[a];
-                M2T_TRY(run_qkv(var, Tcur, reinterpret_cast<const __half*>(W + A.wqkv_f), QKV, g.B * h * w, C, s));
+                M2T_TRY(run_qkv(var, Tb[a], reinterpret_cast<const __half*>(W + A.wqkv_f), QKV, g.B * h * w, C, s));
                 AttnFuse fz;
-                fz.T = Tcur; fz.Y = Y; fz.X = Xin; fz.munorm = munorm; fz.Tnext = a < 3 ? Tnxt : nullptr;
+                fz.T = Tb[a]; fz.Y = Y; fz.Tnext = a < 3 ? Tb[a + 1] : nullptr;
                 fz.branch = a; fz.Hp = g.Hp; fz.Wp = g.Wp;
                 M2T_TRY(launch_attn_umma(C, QKV, reinterpret_cast<const __half*>(W + A.relx), nullptr, g.B, h, w, s, &fz));
-                __half* tmp = Tcur; Tcur = Tnxt; Tnxt = tmp;
             }
         } else
         for (int a = 0; a < 4; ++a) {

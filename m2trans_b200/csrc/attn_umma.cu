@@ -78,8 +78,8 @@ __device__ __forceinline__ WinCoord win_coord(int wi, int nwx, int per_img) {
 }
 
 #ifdef M2T_TIMING
-__device__ long long g_attn_dbg[64];
-#define M2T_T(slot) do { if (blockIdx.x == 0 && tid == 0 && it < 6) g_attn_dbg[(slot) + 8 * it] = clock64(); } while (0)
+__device__ long long g_attn_dbg[4 * 64];   // one 64-entry record per branch (fused) / record 0 (plain)
+#define M2T_T(slot) do { if (blockIdx.x == 0 && tid == 0 && it < 6) g_attn_dbg[64 * fz.branch + (slot) + 8 * it] = clock64(); } while (0)
 #else
 #define M2T_T(slot) do { } while (0)
 #endif
@@ -113,7 +113,7 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
     const int nwx = w / BLK, per_img = (h / BLK) * nwx;
     const int npairs = (nwin + 1) / 2;
 #ifdef M2T_TIMING
-    if (blockIdx.x == 0 && tid == 0) g_attn_dbg[6] = clock64();
+    if (blockIdx.x == 0 && tid == 0) g_attn_dbg[64 * fz.branch + 6] = clock64();
 #endif
 
     // zero P (the 12 padding key columns stay zero for ever) and the 12 padding rows of every V stage
@@ -150,7 +150,7 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
     constexpr uint32_t LANE_B = 16u << 16;                      // TMEM lane offset of window B
     pdl_trigger();
 #ifdef M2T_TIMING
-    if (blockIdx.x == 0 && tid == 0) g_attn_dbg[7] = clock64();
+    if (blockIdx.x == 0 && tid == 0) g_attn_dbg[64 * fz.branch + 7] = clock64();
 #endif
 
     if (warp == 4) {
@@ -334,10 +334,11 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
                 // Fused branch glue (ref :139-161).  With the Haar transforms folded into the qkv weights the
                 // accumulator row IS IWT^L(attention) in space-to-depth order: column s*16+k belongs to pixel
                 // s = dy*2^L + dx of this level pixel's 2^L x 2^L block.
-                //   y_k = O' + t_k              -> Y[..., 16k..16k+15]                  (ref :139,:145,:153,:161)
-                //   t_{k+1} = (n_{k+1} + y_k)/2 -> Tnext, next level's space-to-depth order (ref :141,:147,:155)
-                // t_k rows come from registers (prefetched before the PV MMAs finish; C <= 64) or from the TMA-fed
-                // T stages (C = 256); the residual-stream slice for t_{k+1} is prefetched one 64-channel block ahead.
+                //   y_k = O' + t_k                 -> Y[..., 16k..16k+15]               (ref :139,:145,:153,:161)
+                //   t_{k+1} = n_{k+1}/2 + y_k/2    -> Tnext, updated in place (branch_prep_all pre-filled n_{k+1}/2 in
+                //                                     the next level's space-to-depth order)  (ref :141,:147,:155)
+                // t_k rows come from registers (C <= 64, loaded before the PV MMAs finish) or from the TMA-fed T
+                // stages (C = 256); the Tnext segments are prefetched one 64-channel block ahead.
                 constexpr int LV = C == 16 ? 0 : (C == 64 ? 1 : 2);
                 constexpr int S = 1 << LV;
                 constexpr int SPB = CB / NB;                     // sub-pixels per 64-channel block: 1 or 4
@@ -345,39 +346,34 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
                 const int br = fz.branch;
                 const bool has_next = fz.Tnext != nullptr;
                 const int lvn = br == 0 ? 1 : 2, Sn = 1 << lvn, Cn = NB * Sn * Sn;
-                float mu[NB], rs[NB];
-                if (has_next) {
-#pragma unroll
-                    for (int e = 0; e < NB; ++e) {
-                        const float2 mr = __ldg(&fz.munorm[wc.b * NF + NB * (br + 1) + e]);
-                        mu[e] = mr.x; rs[e] = mr.y;
-                    }
-                }
+                auto tnext_ptr = [&](int s) -> __half* {
+                    const int fy = ly * S + s / S, fx = lx * S + s % S;
+                    const int sn = (fy & (Sn - 1)) * Sn + (fx & (Sn - 1));
+                    return fz.Tnext + ((((long)wc.b * (fz.Hp >> lvn)) + (fy >> lvn)) * (fz.Wp >> lvn) + (fx >> lvn)) * Cn + sn * NB;
+                };
                 uint4 tkr[CF::TSTAGE ? 1 : 2 * SPB];            // register copy of the t_k row (C <= 64)
                 if constexpr (!CF::TSTAGE) {
                     const __half* trow = fz.T + (((long)wc.b * h + ly) * w + lx) * C;
 #pragma unroll
                     for (int j = 0; j < 2 * SPB; ++j) tkr[j] = *reinterpret_cast<const uint4*>(trow + j * 8);
                 }
-                float4 xcur[4 * SPB], xnxt[4 * SPB];
-                auto load_x = [&](int nb, float4* dst) {
+                uint4 hcur[2 * SPB], hnxt[2 * SPB];             // n_{k+1}/2 segments of the current / next block
+                auto load_h = [&](int nb, uint4* dst) {
 #pragma unroll
                     for (int j = 0; j < SPB; ++j) {
-                        const int s = nb * SPB + j;
-                        const long pix = ((long)wc.b * fz.Hp + (ly * S + s / S)) * fz.Wp + (lx * S + s % S);
-                        const float4* xp = reinterpret_cast<const float4*>(fz.X + pix * NF + NB * (br + 1));
-#pragma unroll
-                        for (int v = 0; v < 4; ++v) dst[4 * j + v] = xp[v];
+                        const __half* hp = tnext_ptr(nb * SPB + j);
+                        dst[2 * j] = *reinterpret_cast<const uint4*>(hp);
+                        dst[2 * j + 1] = *reinterpret_cast<const uint4*>(hp + 8);
                     }
                 };
-                if (has_next) load_x(0, xcur);
+                if (has_next) load_h(0, hcur);
                 M2T_T(3);
                 mbar_wait(o_full, it & 1);
                 tc_fence_after();
                 M2T_T(4);
 #pragma unroll 1
                 for (int nb = 0; nb < NBLK; ++nb) {
-                    if (has_next && nb + 1 < NBLK) load_x(nb + 1, xnxt);
+                    if (has_next && nb + 1 < NBLK) load_h(nb + 1, hnxt);
                     const uint8_t* tst = nullptr;
                     if constexpr (CF::TSTAGE) {
                         mbar_wait(&t_full[gt & 1], (gt >> 1) & 1);
@@ -417,18 +413,13 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
                             if (has_next) {
                                 uint4 to[2];
                                 __half2* tnh = reinterpret_cast<__half2*>(to);
+                                const __half2* hh = reinterpret_cast<const __half2*>(&hcur[2 * j]);
 #pragma unroll
-                                for (int v = 0; v < 4; ++v) {
-                                    const float4 xv = xcur[4 * j + v];
-                                    const float t0 = 0.5f * ((xv.x - mu[4 * v]) * rs[4 * v] + yv[4 * v]);
-                                    const float t1 = 0.5f * ((xv.y - mu[4 * v + 1]) * rs[4 * v + 1] + yv[4 * v + 1]);
-                                    const float t2 = 0.5f * ((xv.z - mu[4 * v + 2]) * rs[4 * v + 2] + yv[4 * v + 2]);
-                                    const float t3 = 0.5f * ((xv.w - mu[4 * v + 3]) * rs[4 * v + 3] + yv[4 * v + 3]);
-                                    tnh[2 * v] = __floats2half2_rn(t0, t1);
-                                    tnh[2 * v + 1] = __floats2half2_rn(t2, t3);
+                                for (int e = 0; e < 8; ++e) {
+                                    const float2 hf = __half22float2(hh[e]);
+                                    tnh[e] = __floats2half2_rn(fmaf(0.5f, yv[2 * e], hf.x), fmaf(0.5f, yv[2 * e + 1], hf.y));
                                 }
-                                const int sn = (fy & (Sn - 1)) * Sn + (fx & (Sn - 1));
-                                __half* tp = fz.Tnext + ((((long)wc.b * (fz.Hp >> lvn)) + (fy >> lvn)) * (fz.Wp >> lvn) + (fx >> lvn)) * Cn + sn * NB;
+                                __half* tp = tnext_ptr(s);
                                 *reinterpret_cast<uint4*>(tp) = to[0];
                                 *reinterpret_cast<uint4*>(tp + 8) = to[1];
                             }
@@ -441,7 +432,7 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
                     }
                     if (has_next && nb + 1 < NBLK) {
 #pragma unroll
-                        for (int j = 0; j < 4 * SPB; ++j) xcur[j] = xnxt[j];
+                        for (int j = 0; j < 2 * SPB; ++j) hcur[j] = hnxt[j];
                     }
                 }
             } else {
@@ -538,11 +529,11 @@ int launch_attn_umma(int C, const __half* QKV, const __half* relx, __half* O, in
 
 #ifdef M2T_TIMING
 int read_attn_timing(long long* host64) {
-    M2T_CUDA(cudaMemcpyFromSymbol(host64, g_attn_dbg, sizeof(long long) * 64));
+    M2T_CUDA(cudaMemcpyFromSymbol(host64, g_attn_dbg, sizeof(long long) * 256));
     return M2T_OK;
 }
 #else
-int read_attn_timing(long long* host64) { memset(host64, 0, sizeof(long long) * 64); return M2T_OK; }
+int read_attn_timing(long long* host64) { memset(host64, 0, sizeof(long long) * 256); return M2T_OK; }
 #endif
 
 }  // namespace m2t

@@ -143,17 +143,18 @@ int launch_attn_simt(int C, const __half* QKV, const float* relf, __half* O, int
 
 // attn_umma.cu : same contract on tcgen05 (relx: fp16 [32][C] MMA-operand form of the rel tables)
 // Optional fused branch glue for the tensor-core attention epilogue (ref :139-161): instead of storing O it
-// writes y_k = O' + t_k into Y and the next branch's t_{k+1} = (n_{k+1} + y_k)/2 into Tnext.  Requires the
-// Haar-folded qkv weights (pack.cu) and space-to-depth T tensors.
+// writes y_k = O' + t_k into Y and completes the next branch's input in place,
+// Tnext = n_{k+1}/2 (pre-filled by branch_prep_all) + y_k/2 = t_{k+1}.  Requires the Haar-folded qkv weights
+// (pack.cu) and space-to-depth T tensors.
 struct AttnFuse {
     const __half* T;        // this branch's input t_k, space-to-depth fp16 [B,h,w,C]
     __half* Y;              // cat[y1..y4] fp16 NHWC [B,Hp,Wp,64]
-    const float* X;         // residual stream fp32 NHWC [B,Hp,Wp,64]
-    const float2* munorm;   // InstanceNorm (mean, rstd) [B][64]
-    __half* Tnext;          // t_{k+1} space-to-depth at the next branch's level, or nullptr after branch 4
+    __half* Tnext;          // next branch's space-to-depth tensor holding n_{k+1}/2, or nullptr after branch 4
     int branch;             // 0..3
     int Hp, Wp;
 };
+int launch_branch_prep_all(const float* X, const float2* munorm, __half* T1, __half* H2, __half* H3, __half* H4,
+                           const Geom& g, cudaStream_t s);
 int launch_attn_umma(int C, const __half* QKV, const __half* relx, __half* O, int B, int h, int w,
                      cudaStream_t s, const AttnFuse* fuse = nullptr);
 
