@@ -188,7 +188,7 @@ int m2t_plan_create(const m2t_cfg* cfg, m2t_plan** out) {
     p->o_t1 = take(m2t_tail_scratch_bytes(cfg->scale, chunk, g.Hp, g.Wp));
     p->ws_bytes = off;
     const int tail_passes = (g.B + chunk - 1) / chunk;
-    const int per_block = (cfg->variant & M2T_VAR_SIMT_ATTN) ? (1 + 4 * 4 + 1) : (1 + 1 + 4 * 2 + 1);
+    const int per_block = (cfg->variant & M2T_VAR_SIMT_ATTN) ? (1 + 4 * 4 + 1) : (1 + 4 * 2 + 1);
     p->n_launches = 1 /*head*/ + cfg->n_blocks * per_block + tail_passes * (cfg->scale == 4 ? 4 : 3);
     *out = p;
     return M2T_OK;
@@ -289,11 +289,11 @@ int m2t_forward(const m2t_plan* plan, const void* d_packed, const float* d_x, fl
     // The CUDA-core attention variant keeps the explicit prep / post kernels (18 launches per CFTM).
     const bool fused = !(var & M2T_VAR_SIMT_ATTN);
     for (int i = 0; i < plan->cfg.n_blocks; ++i) {
-        M2T_TRY(launch_stats_finalize(stats + i * stat_stride, munorm, g.B, npix, s));
+        if (!fused) M2T_TRY(launch_stats_finalize(stats + i * stat_stride, munorm, g.B, npix, s));
         if (fused) {
             // t_1 = n_1 and n_k/2 (k = 2..4) in their consumers' space-to-depth layouts, one pass over X (ref :135-137)
             __half* Tb[4] = {Z, O, reinterpret_cast<__half*>(ws + plan->o_h3), reinterpret_cast<__half*>(ws + plan->o_h4)};
-            M2T_TRY(launch_branch_prep_all(Xin, munorm, Tb[0], Tb[1], Tb[2], Tb[3], g, s));
+            M2T_TRY(launch_branch_prep_all(Xin, stats + i * stat_stride, Tb[0], Tb[1], Tb[2], Tb[3], g, s));
             for (int a = 0; a < 4; ++a) {
                 const int lv = branch_level(a), C = branch_ch(a);
                 const int h = g.Hp >> lv, w = g.Wp >> lv;

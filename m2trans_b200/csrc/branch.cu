@@ -187,45 +187,65 @@ branch_post_kernel(int branch, const __half* __restrict__ O, const float* __rest
 //   H2 = n_2 / 2                  fp16 space-to-depth level 1 [B,Hp/2,Wp/2,64]
 //   H3 = n_3 / 2, H4 = n_4 / 2    fp16 space-to-depth level 2 [B,Hp/4,Wp/4,256]
 // The attention epilogue of branch k then completes t_{k+1} = H_{k+1} + y_k / 2 in place, reading and writing
-// the same 32-byte segments, so it never touches the fp32 stream.  One thread per (pixel, 4 channels).
+// the same 32-byte segments, so it never touches the fp32 stream.
+// One thread per (pixel, 16-channel branch group): 64-byte loads, 32-byte stores.  The InstanceNorm statistics
+// (mean, rstd; biased variance, ref :127) are finalised here from the fp64 sums the producer accumulated, so no
+// separate finalise pass is needed on this path.  A CTA covers 64 consecutive pixels of one image.
 __global__ void __launch_bounds__(256)
-branch_prep_all_kernel(const float* __restrict__ X, const float2* __restrict__ munorm, __half* __restrict__ T1,
+branch_prep_all_kernel(const float* __restrict__ X, const double* __restrict__ stats, __half* __restrict__ T1,
                        __half* __restrict__ H2, __half* __restrict__ H3, __half* __restrict__ H4, int B, int Hp,
                        int Wp) {
+    __shared__ float smu[NF], srs[NF];
     pdl_trigger();
     pdl_wait();
-    const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long total = (long)B * Hp * Wp * 16;
-    if (tid >= total) return;
-    const int c4 = (int)(tid & 15);                 // channels 4*c4 .. 4*c4+3
-    const long pix = tid >> 4;
-    const int b = (int)(pix / ((long)Hp * Wp));
-    const int r = (int)(pix - (long)b * Hp * Wp);
+    const int t = threadIdx.x;
+    const long pix = (long)blockIdx.x * 64 + (t >> 2);
+    const int npix = Hp * Wp;
+    const int b = (int)(pix / npix);
+    const int r = (int)(pix - (long)b * npix);
     const int y = r / Wp, x = r - y * Wp;
-    const float4 xv = *reinterpret_cast<const float4*>(X + pix * NF + 4 * c4);
-    const float2 m0 = __ldg(&munorm[b * NF + 4 * c4]), m1 = __ldg(&munorm[b * NF + 4 * c4 + 1]);
-    const float2 m2 = __ldg(&munorm[b * NF + 4 * c4 + 2]), m3 = __ldg(&munorm[b * NF + 4 * c4 + 3]);
-    const int branch = c4 >> 2, q = c4 & 3;
+    if (t < NF) {
+        const double inv = 1.0 / (double)npix;
+        const double m = stats[((long)b * NF + t) * 2] * inv;
+        double var = stats[((long)b * NF + t) * 2 + 1] * inv - m * m;
+        if (var < 0.0) var = 0.0;
+        smu[t] = (float)m;
+        srs[t] = (float)(1.0 / sqrt(var + (double)IN_EPS));
+    }
+    __syncthreads();
+    const int branch = t & 3;
     const float sc = branch == 0 ? 1.f : 0.5f;
-    F4 n;
-    n.v[0] = (xv.x - m0.x) * m0.y * sc; n.v[1] = (xv.y - m1.x) * m1.y * sc;
-    n.v[2] = (xv.z - m2.x) * m2.y * sc; n.v[3] = (xv.w - m3.x) * m3.y * sc;
+    const float4* xp = reinterpret_cast<const float4*>(X + pix * NF + NB * branch);
+    float4 xv[4];
+#pragma unroll
+    for (int v = 0; v < 4; ++v) xv[v] = xp[v];
+    uint4 o[2];
+    __half2* oh = reinterpret_cast<__half2*>(o);
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+        const int c = NB * branch + 4 * v;
+        oh[2 * v] = __floats2half2_rn((xv[v].x - smu[c]) * srs[c] * sc, (xv[v].y - smu[c + 1]) * srs[c + 1] * sc);
+        oh[2 * v + 1] = __floats2half2_rn((xv[v].z - smu[c + 2]) * srs[c + 2] * sc, (xv[v].w - smu[c + 3]) * srs[c + 3] * sc);
+    }
+    __half* dst;
     if (branch == 0) {
-        store_h4(T1 + pix * NB + 4 * q, n);
+        dst = T1 + pix * NB;
     } else if (branch == 1) {
         const long lp = ((long)b * (Hp >> 1) + (y >> 1)) * (Wp >> 1) + (x >> 1);
-        store_h4(H2 + lp * 64 + ((y & 1) * 2 + (x & 1)) * NB + 4 * q, n);
+        dst = H2 + lp * 64 + ((y & 1) * 2 + (x & 1)) * NB;
     } else {
         const long lp = ((long)b * (Hp >> 2) + (y >> 2)) * (Wp >> 2) + (x >> 2);
-        store_h4((branch == 2 ? H3 : H4) + lp * 256 + ((y & 3) * 4 + (x & 3)) * NB + 4 * q, n);
+        dst = (branch == 2 ? H3 : H4) + lp * 256 + ((y & 3) * 4 + (x & 3)) * NB;
     }
+    *reinterpret_cast<uint4*>(dst) = o[0];
+    *reinterpret_cast<uint4*>(dst + 8) = o[1];
 }
 
-int launch_branch_prep_all(const float* X, const float2* munorm, __half* T1, __half* H2, __half* H3, __half* H4,
+int launch_branch_prep_all(const float* X, const double* stats, __half* T1, __half* H2, __half* H3, __half* H4,
                            const Geom& g, cudaStream_t s) {
-    const long total = (long)g.B * g.Hp * g.Wp * 16;
-    M2T_CUDA(launch_pdl(branch_prep_all_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, X, munorm, T1, H2,
-                        H3, H4, g.B, g.Hp, g.Wp));
+    const long npx = (long)g.B * g.Hp * g.Wp;
+    M2T_CUDA(launch_pdl(branch_prep_all_kernel, dim3((unsigned)(npx / 64)), dim3(256), 0, s, X, stats, T1, H2, H3, H4, g.B,
+                        g.Hp, g.Wp));
     return M2T_OK;
 }
 

@@ -153,7 +153,7 @@ struct AttnFuse {
     int branch;             // 0..3
     int Hp, Wp;
 };
-int launch_branch_prep_all(const float* X, const float2* munorm, __half* T1, __half* H2, __half* H3, __half* H4,
+int launch_branch_prep_all(const float* X, const double* stats, __half* T1, __half* H2, __half* H3, __half* H4,
                            const Geom& g, cudaStream_t s);
 int launch_attn_umma(int C, const __half* QKV, const __half* relx, __half* O, int B, int h, int w,
                      cudaStream_t s, const AttnFuse* fuse = nullptr);

@@ -16,15 +16,16 @@ namespace m2t {
 
 __device__ __forceinline__ float gelu_fast(float x) {
     const float z = fabsf(x) * 0.70710678118654752f;
-    const float t = __fdividef(1.f, fmaf(0.3275911f, z, 1.f));
-    float e;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-z * z * 1.4426950408889634f));
+    float t, e;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.f)));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * z * -1.4426950408889634f));
     float p = fmaf(1.061405429f, t, -1.453152027f);
     p = fmaf(p, t, 1.421413741f);
     p = fmaf(p, t, -0.284496736f);
     p = fmaf(p, t, 0.254829592f);
-    const float erf_abs = fmaf(-p * t, e, 1.f);
-    return 0.5f * x * (1.f + copysignf(erf_abs, x));
+    const float erf_abs = fmaf(-p * t, e, 1.f);          // erf(|x|/sqrt 2)
+    const float hx = 0.5f * x;
+    return fmaf(fabsf(hx), erf_abs, hx);                 // 0.5 x (1 + sign(x) erf_abs) = hx + |hx| erf_abs
 }
 
 template <int R>
@@ -42,8 +43,10 @@ struct TuCfg {
     static constexpr uint32_t SMEM = 1024 + OFF_BAR + 256;
 };
 
+constexpr int TU_THREADS = 320;   // warps 0-3 + 6-9 epilogue, warp 4 TMA, warp 5 MMA
+
 template <int R>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(TU_THREADS, 1)
 tail_up_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW,
                     const float* __restrict__ bias, __half* __restrict__ out, int M, int h, int w, int pad) {
     using CF = TuCfg<R>;
@@ -62,12 +65,12 @@ tail_up_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int num_mt = M / 128;
-    for (int i = tid; i < CF::N; i += 192) sbias[i] = bias[i];
+    for (int i = tid; i < CF::N; i += TU_THREADS) sbias[i] = bias[i];
     if (warp == 5) tmem_alloc(tmem_slot, 512);
     if (tid == 128) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         mbar_init(wfull, 1);
-        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 8); }
         mbar_fence_init();
         tma_prefetch_desc(&mapA);
         tma_prefetch_desc(&mapW);
@@ -121,12 +124,17 @@ tail_up_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
             }
         }
     } else {
+        // Two epilogue warpgroups (warps 0-3 and 6-9) share every accumulator: the GELU epilogue is issue-bound,
+        // so each TMEM lane quadrant (warp % 4) is served by two warps that split the sub-pixels between them.
         const int hr = h * R, wr = w * R;
         const long orow_pitch = (long)(wr + 2 * pad) * NF;
+        const int quad = warp & 3, wg = warp >= 6 ? 1 : 0;
+        constexpr int SPLIT = (SUB + 1) / 2;
+        const int sp_lo = wg == 0 ? 0 : SPLIT, sp_hi = wg == 0 ? SPLIT : SUB;
         pdl_wait();
         uint32_t u = 0;
         for (int mt = blockIdx.x; mt < num_mt; mt += gridDim.x) {
-            const int gp = mt * 128 + tid;
+            const int gp = mt * 128 + quad * 32 + lane;
             const int b = gp / (h * w), rem = gp - b * (h * w);
             const int y = rem / w, x = rem - y * w;
             __half* obase = out + ((long)b * (hr + 2 * pad) + (long)y * R + pad) * orow_pitch + ((long)x * R + pad) * NF;
@@ -135,14 +143,14 @@ tail_up_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                 mbar_wait(&tfull[acc], aph);
                 tc_fence_after();
 #pragma unroll 1
-                for (int sp = 0; sp < SUB; ++sp) {
+                for (int sp = sp_lo; sp < sp_hi; ++sp) {
                     const int uv = ch * SUB + sp;
                     __half* op = obase + (long)(uv / R) * orow_pitch + (uv % R) * NF;
                     const float* bs = sbias + uv * NF;
 #pragma unroll
                     for (int c0 = 0; c0 < NF; c0 += 32) {
                         uint32_t r[32];
-                        tmem_ld32(tmem_base + acc * 256 + sp * NF + c0 + ((uint32_t)(warp * 32) << 16), r);
+                        tmem_ld32(tmem_base + acc * 256 + sp * NF + c0 + ((uint32_t)(quad * 32) << 16), r);
                         tmem_ld_wait();
 #pragma unroll
                         for (int v = 0; v < 4; ++v) {
@@ -189,7 +197,7 @@ static int launch_tail_up_umma_r(const __half* A, const __half* Wt, const float*
     M2T_ENSURE_SMEM(tail_up_umma_kernel<R>, CF::SMEM);
     const int num_mt = M / 128;
     const int grid = num_mt < device_sm_count() ? num_mt : device_sm_count();
-    M2T_CUDA(launch_pdl(tail_up_umma_kernel<R>, dim3(grid), dim3(192), CF::SMEM, s, mapA, mapW, bias, out, M, h, w, pad));
+    M2T_CUDA(launch_pdl(tail_up_umma_kernel<R>, dim3(grid), dim3(TU_THREADS), CF::SMEM, s, mapA, mapW, bias, out, M, h, w, pad));
     return M2T_OK;
 }
 
