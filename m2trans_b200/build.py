@@ -23,6 +23,8 @@ FLAGS = [
     "-Xcompiler", "-fPIC",
     "--expt-relaxed-constexpr",
 ]
+if os.environ.get("M2T_CONV_WGS"):          # tuning switch: epilogue warpgroups of the ff conv (1 or 2)
+    FLAGS.append("-DM2T_CONV_WGS=" + os.environ["M2T_CONV_WGS"])
 if os.environ.get("M2T_TIMING") == "1":      # development builds: clock64 stamps in the attention kernel
     FLAGS.append("-DM2T_TIMING")
 

@@ -196,7 +196,6 @@ branch_prep_all_kernel(const float* __restrict__ X, const double* __restrict__ s
                        __half* __restrict__ H2, __half* __restrict__ H3, __half* __restrict__ H4, int B, int Hp,
                        int Wp) {
     __shared__ float smu[NF], srs[NF];
-    pdl_trigger();
     pdl_wait();
     const int t = threadIdx.x;
     const long pix = (long)blockIdx.x * 64 + (t >> 2);
@@ -239,6 +238,9 @@ branch_prep_all_kernel(const float* __restrict__ X, const double* __restrict__ s
     }
     *reinterpret_cast<uint4*>(dst) = o[0];
     *reinterpret_cast<uint4*>(dst + 8) = o[1];
+    // multi-wave grid: let the next kernel's CTAs in only when this CTA is done, or they would take the SMs that
+    // this grid's later waves still need
+    pdl_trigger();
 }
 
 int launch_branch_prep_all(const float* X, const double* stats, __half* T1, __half* H2, __half* H3, __half* H4,

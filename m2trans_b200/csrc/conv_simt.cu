@@ -23,6 +23,7 @@ ffconv_simt_kernel(const __half* __restrict__ Y, const __half* __restrict__ Wp, 
     float* Ws = reinterpret_cast<float*>(smem + CS_W);
     __half* Ts = reinterpret_cast<__half*>(smem + CS_T);
     float* Os = reinterpret_cast<float*>(smem + CS_O);
+    __shared__ float red[4][2][NF];
     const int t = threadIdx.x;
     for (int i = t; i < 9 * NF * NF; i += 128) Ws[i] = __half2float(Wp[i]);
 
@@ -75,7 +76,12 @@ ffconv_simt_kernel(const __half* __restrict__ Y, const __half* __restrict__ Wp, 
 #pragma unroll
         for (int o = 0; o < NF; ++o) Os[t * EPI_LD + o] = acc[o];
         __syncthreads();
-        epilogue_residual_stats<CT_W, 0>(Os, bias, Xin, Xout, stats, b, y0, x0, Hp, Wpx, res, xr);
+        float4 xi[16];
+        EpiStats st;
+        st.clear();
+        epilogue_load_residual<CT_W>(t, Xin, b, y0, x0, Hp, Wpx, xi);
+        epilogue_apply<CT_W>(Os, t, xi, bias, Xout, st, b, y0, x0, Hp, Wpx, res, xr);
+        epilogue_flush_stats<0>(red, t, st, stats, b);
     }
 }
 

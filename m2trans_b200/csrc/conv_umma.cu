@@ -28,17 +28,23 @@ constexpr int CU_STAGES = 3;
 constexpr uint32_t CU_W_BYTES = 9 * NF * 128;                         // 73728
 constexpr uint32_t CU_OFF_A = CU_W_BYTES;
 constexpr uint32_t CU_OFF_O = CU_OFF_A + CU_STAGES * CU_STAGE;
-constexpr uint32_t CU_OFF_BAR = CU_OFF_O + 128 * EPI_LD * 4;
+constexpr uint32_t CU_O_BYTES = 128 * EPI_LD * 4;                      // one fp32 staging tile per epilogue warpgroup
+constexpr uint32_t CU_OFF_RED = CU_OFF_O + 2 * CU_O_BYTES;            // 2 x float [4][2][64]
+constexpr uint32_t CU_OFF_BAR = CU_OFF_RED + 2 * 4 * 2 * NF * 4;
 constexpr uint32_t CU_SMEM = 1024 + CU_OFF_BAR + 256;
+#ifndef M2T_CONV_WGS
+#define M2T_CONV_WGS 1
+#endif
+constexpr int CU_WGS = M2T_CONV_WGS;   // epilogue warpgroups (A/B switch for tuning)
+constexpr int CU_THREADS = CU_WGS == 2 ? 320 : 192;   // warps 0-3: epilogue (even tiles), 4: TMA, 5: MMA, 6-9: epilogue of odd tiles
 
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(CU_THREADS, 1)
 ffconv_umma_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ CUtensorMap mapW,
                    const float* __restrict__ bias, const float* Xin, float* Xout, double* __restrict__ stats, int B,
                    int Hp, int Wp, const float* __restrict__ res, __half* __restrict__ xr) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
-    float* Os = reinterpret_cast<float*>(sm + CU_OFF_O);
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + CU_OFF_BAR);
     uint64_t* full = bars;                       // [STAGES]
     uint64_t* empty = bars + CU_STAGES;          // [STAGES]
@@ -51,6 +57,10 @@ ffconv_umma_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_consta
     const int tiles_x = Wp / CU_TW, tiles_y = Hp / CU_TH;
     const int per_img = tiles_x * tiles_y;
     const int ntiles = B * per_img;
+    // contiguous tile range per CTA: neighbouring tiles share halo rows in L2 and mostly belong to one image,
+    // so the InstanceNorm partial sums are flushed once or twice per CTA instead of once per tile
+    const int tile_lo = (int)((long)blockIdx.x * ntiles / gridDim.x);
+    const int tile_hi = (int)((long)(blockIdx.x + 1) * ntiles / gridDim.x);
 
     if (warp == 5) tmem_alloc(tmem_slot, 128);
     if (tid == 128) {
@@ -75,7 +85,7 @@ ffconv_umma_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_consta
         }
         pdl_wait();
         uint32_t it = 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        for (int tile = tile_lo; tile < tile_hi; ++tile, ++it) {
             const int b = tile / per_img, r = tile - b * per_img;
             const int y0 = (r / tiles_x) * CU_TH, x0 = (r % tiles_x) * CU_TW;
             const uint32_t s = it % CU_STAGES, ph = (it / CU_STAGES) & 1;
@@ -93,7 +103,7 @@ ffconv_umma_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_consta
         constexpr uint64_t tmpl_b = umma_smem_desc(0, 16, 1024, UMMA_LAYOUT_SW128);
         mbar_wait(wfull, 0);
         uint32_t it = 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        for (int tile = tile_lo; tile < tile_hi; ++tile, ++it) {
             const uint32_t s = it % CU_STAGES, ph = (it / CU_STAGES) & 1;
             const uint32_t acc = it & 1, aph = (it >> 1) & 1;
             mbar_wait(&tempty[acc], aph ^ 1);
@@ -117,30 +127,47 @@ ffconv_umma_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_consta
             __syncwarp();
         }
     } else {
+        // Two epilogue warpgroups: wg 0 (warps 0-3) drains accumulator 0 = even tiles, wg 1 (warps 6-9) accumulator 1
+        // = odd tiles, each with its own staging tile and named barrier.  The residual rows of a tile are requested
+        // before its accumulator is complete, so up to 64 KB of loads per SM overlap the MMAs and the other group.
+        const int wg = warp >= 6 ? 1 : 0, quad = warp & 3;
+        const int t = quad * 32 + lane;                         // 0..127 inside the warpgroup = TMEM lane = tile pixel
+        float* Os = reinterpret_cast<float*>(sm + CU_OFF_O + wg * CU_O_BYTES);
+        float (*red)[2][NF] = reinterpret_cast<float (*)[2][NF]>(sm + CU_OFF_RED + wg * 4 * 2 * NF * 4);
         pdl_wait();
+        EpiStats st;
+        st.clear();
+        int cur_b = -1;
         uint32_t it = 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        for (int tile = tile_lo; tile < tile_hi; ++tile, ++it) {
+            if (CU_WGS == 2 && (int)(it & 1) != wg) continue;
             const int b = tile / per_img, r = tile - b * per_img;
             const int y0 = (r / tiles_x) * CU_TH, x0 = (r % tiles_x) * CU_TW;
             const uint32_t acc = it & 1, aph = (it >> 1) & 1;
+            float4 xi[16];
+            epilogue_load_residual<CU_TW>(t, Xin, b, y0, x0, Hp, Wp, xi);
+            if (b != cur_b) {                                  // image changed: publish the finished image's sums
+                if (cur_b >= 0) { if (wg == 0) epilogue_flush_stats<1>(red, t, st, stats, cur_b); else epilogue_flush_stats<2>(red, t, st, stats, cur_b); }
+                cur_b = b;
+            }
             mbar_wait(&tfull[acc], aph);
             tc_fence_after();
-            const int m = warp * 32 + lane;
 #pragma unroll
             for (int c0 = 0; c0 < NF; c0 += 32) {
                 uint32_t rr[32];
-                tmem_ld32(tmem_base + acc * NF + c0 + ((uint32_t)(warp * 32) << 16), rr);
+                tmem_ld32(tmem_base + acc * NF + c0 + ((uint32_t)(quad * 32) << 16), rr);
                 tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 32; ++i) Os[m * EPI_LD + c0 + i] = __uint_as_float(rr[i]);
+                for (int i = 0; i < 32; ++i) Os[t * EPI_LD + c0 + i] = __uint_as_float(rr[i]);
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);          // accumulator drained: MMA may reuse it
-            epi_sync<1>();                                     // all 128 staged rows visible
-            epilogue_residual_stats<CU_TW, 1>(Os, bias, Xin, Xout, stats, b, y0, x0, Hp, Wp, res, xr);
-            epi_sync<1>();                                     // Os / red free for the next tile
+            if (wg == 0) epi_sync<1>(); else epi_sync<2>();    // all 128 staged rows visible
+            epilogue_apply<CU_TW>(Os, t, xi, bias, Xout, st, b, y0, x0, Hp, Wp, res, xr);
+            if (wg == 0) epi_sync<1>(); else epi_sync<2>();    // Os free for the next tile
         }
+        if (cur_b >= 0) { if (wg == 0) epilogue_flush_stats<1>(red, t, st, stats, cur_b); else epilogue_flush_stats<2>(red, t, st, stats, cur_b); }
     }
     tc_fence_before();
     __syncthreads();
@@ -164,7 +191,7 @@ int launch_ffconv_umma(const __half* Y, const __half* Wpk, const float* bias, co
     M2T_ENSURE_SMEM(ffconv_umma_kernel, CU_SMEM);
     const int ntiles = g.B * (g.Hp / CU_TH) * (g.Wp / CU_TW);
     const int grid = ntiles < device_sm_count() ? ntiles : device_sm_count();
-    M2T_CUDA(launch_pdl(ffconv_umma_kernel, dim3(grid), dim3(192), CU_SMEM, s, mapY, mapW, bias, Xin, Xout, stats, g.B, g.Hp,
+    M2T_CUDA(launch_pdl(ffconv_umma_kernel, dim3(grid), dim3(CU_THREADS), CU_SMEM, s, mapY, mapW, bias, Xin, Xout, stats, g.B, g.Hp,
                         g.Wp, res, xr));
     return M2T_OK;
 }
