@@ -147,6 +147,20 @@ int m2t_stage_tail(uint32_t variant, int scale, int n_blocks, const void* d_pack
                    float* d_y, int B, int b0, int H, int W, float rgb_range, void* d_scratch,
                    void* stream);
 
+/* ---- rlutrans.TransBlock -------------------------------------------------
+ * Replaces util/rlutrans.py TransBlock.forward (ref util/rlutrans.py:82-87; EffAttention.forward
+ * :46-66; Mlp.forward :20-27):  y = x1 + fc2(ReLU(fc1(LN2(x1)))),  x1 = x + proj(attn(qkv(reduce(LN1(x))))),
+ * attention with 8 heads and softmax restricted to chunks of N/16 consecutive tokens.
+ * d_x, d_y: fp32 [B][N][dim] (d_y may not alias d_x); d_params: HOST array of the 12 DEVICE fp32
+ * tensors of TransBlock.state_dict() in registration order (atten.reduce.weight, atten.qkv.weight,
+ * atten.proj.weight, atten.proj.bias, norm1.weight, norm1.bias, mlp.fc1.weight, mlp.fc1.bias,
+ * mlp.fc2.weight, mlp.fc2.bias, norm2.weight, norm2.bias).  dim must be 64 and num_heads 8 (the
+ * constructor defaults; M2T_E_UNSUPPORTED otherwise); N < 16 is M2T_E_ARG (the reference raises).
+ * d_workspace: m2t_transblock_workspace_bytes(B, N, dim) bytes, 16-byte aligned. */
+size_t m2t_transblock_workspace_bytes(int B, int N, int dim);
+int m2t_transblock_forward(const float* d_x, float* d_y, const float* const* d_params, int n_params,
+                           int B, int N, int dim, int num_heads, void* d_workspace, void* stream);
+
 /* ---- hardware probes (development aids; tests/test_probes.py) ---------------------------
  * m2t_probe_umma: copies two raw shared-memory images (A, B operands), issues k_steps
  * tcgen05.mma (kind::f16, cta_group::1, M=128) with the given 64-bit shared-memory

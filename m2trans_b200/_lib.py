@@ -61,6 +61,8 @@ SIGNATURES = {
     "m2t_stage_ffconv": (_i, [_u32, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "m2t_tail_scratch_bytes": (_sz, [_i, _i, _i, _i]),
     "m2t_stage_tail": (_i, [_u32, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp]),
+    "m2t_transblock_workspace_bytes": (_sz, [_i, _i, _i]),
+    "m2t_transblock_forward": (_i, [_vp, _vp, C.POINTER(_vp), _i, _i, _i, _i, _i, _vp, _vp]),
     "m2t_probe_umma": (_i, [_vp, _u32, _vp, _u32, _u64, _u64, _u32, _u32, _i, _u32, _i, _vp, _vp]),
     "m2t_debug_attn_timing": (_i, [C.POINTER(C.c_longlong)]),
     "m2t_probe_tma": (_i, [_vp, _i, _i, C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u32), _i,

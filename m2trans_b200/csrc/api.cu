@@ -45,7 +45,7 @@ bool pdl_enabled() {
     return cached == 1;
 }
 
-static int check_device() {
+int check_device() {
     int dev = 0, major = 0, minor = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) { set_error("no CUDA device: %s", cudaGetErrorString(e)); return M2T_E_DEVICE; }

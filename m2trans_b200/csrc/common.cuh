@@ -53,6 +53,7 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
     } while (0)
 
 int device_sm_count();
+int check_device();   // M2T_OK on an sm_100 device, M2T_E_DEVICE otherwise (api.cu)
 
 // ---- programmatic dependent launch ---------------------------------------------------------------------
 // Every kernel of the forward is launched with programmatic stream serialisation: its CTAs may start while

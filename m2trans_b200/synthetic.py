@@ -113,3 +113,43 @@ def synthetic_input(batch: int, h: int, w: int, seed: int = 33, kind: str = "uni
         sp = torch.rand(batch, 3, h, w, generator=g)
         return (base * (0.35 + 0.65 * sp)).clamp(0.0, 1.0).float()
     raise ValueError(kind)
+
+
+# ---- rlutrans.TransBlock -------------------------------------------------
+def transblock_state_dict_spec(dim: int = 64):
+    """(key, shape) in TransBlock.state_dict() registration order (ref util/rlutrans.py:70-81)."""
+    return [("atten.reduce.weight", (dim, dim)), ("atten.qkv.weight", (3 * dim, dim)),
+            ("atten.proj.weight", (dim, dim)), ("atten.proj.bias", (dim,)),
+            ("norm1.weight", (dim,)), ("norm1.bias", (dim,)),
+            ("mlp.fc1.weight", (dim // 4, dim)), ("mlp.fc1.bias", (dim // 4,)),
+            ("mlp.fc2.weight", (dim, dim // 4)), ("mlp.fc2.bias", (dim,)),
+            ("norm2.weight", (dim,)), ("norm2.bias", (dim,))]
+
+
+def synthetic_transblock_state_dict(seed: int = 0, dim: int = 64, qkv_gain: float = 3.0) -> "OrderedDict[str, torch.Tensor]":
+    """Seeded TransBlock parameters.  Linear weights/biases follow nn.Linear's default U(-1/sqrt(fan_in), +);
+    LayerNorm affines are perturbed away from (1, 0) and the qkv weight is scaled by `qkv_gain` so that the
+    softmax is not near-uniform (at default init the logits have std ~0.05 and every chunk is an average)."""
+    g = torch.Generator(device="cpu")
+    g.manual_seed(1000 + seed)
+    sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+    for key, shape in transblock_state_dict_spec(dim):
+        if key.startswith("norm"):
+            t = torch.randn(shape, generator=g) * (0.2 if key.endswith("weight") else 0.1)
+            if key.endswith("weight"):
+                t = t + 1.0
+        else:
+            fan_in = shape[1] if len(shape) == 2 else {"atten.proj.bias": dim, "mlp.fc1.bias": dim, "mlp.fc2.bias": dim // 4}[key]
+            bound = 1.0 / math.sqrt(fan_in)
+            t = (torch.rand(shape, generator=g) * 2.0 - 1.0) * bound
+            if key == "atten.qkv.weight":
+                t = t * qkv_gain
+        sd[key] = t.float().contiguous()
+    return sd
+
+
+def synthetic_tokens(batch: int, n: int, dim: int = 64, seed: int = 33) -> torch.Tensor:
+    """Token features [B, N, dim] ~ N(0.3, 1): a non-zero mean so LayerNorm's centring is exercised."""
+    g = torch.Generator(device="cpu")
+    g.manual_seed(seed)
+    return (torch.randn(batch, n, dim, generator=g) + 0.3).float()
