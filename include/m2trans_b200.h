@@ -49,6 +49,7 @@ extern "C" {
 #define M2T_VAR_SIMT_TAIL (1u << 2)  /* tail on CUDA cores instead of tcgen05          */
 #define M2T_VAR_SIMT_ATTN (1u << 3)  /* attention on CUDA cores instead of tcgen05     */
 #define M2T_VAR_SIMT_ALL  0xFu
+#define M2T_VAR_UNFUSED_TAIL (1u << 4) /* x2/x4: tail_up + border + tail_out instead of the fused last stage */
 
 typedef struct m2t_plan m2t_plan;
 

@@ -20,6 +20,7 @@ VAR_SIMT_QKV = 1 << 1
 VAR_SIMT_TAIL = 1 << 2
 VAR_SIMT_ATTN = 1 << 3
 VAR_SIMT_ALL = 0xF
+VAR_UNFUSED_TAIL = 1 << 4
 
 
 class M2TError(RuntimeError):

@@ -189,7 +189,10 @@ int m2t_plan_create(const m2t_cfg* cfg, m2t_plan** out) {
     p->ws_bytes = off;
     const int tail_passes = (g.B + chunk - 1) / chunk;
     const int per_block = (cfg->variant & M2T_VAR_SIMT_ATTN) ? (1 + 4 * 4 + 1) : (1 + 4 * 2 + 1);
-    p->n_launches = 1 /*head*/ + cfg->n_blocks * per_block + tail_passes * (cfg->scale == 4 ? 4 : 3);
+    // tail per image chunk: x3 and the unfused variants run up [, up], border, out; otherwise [up,] fused
+    const bool tail_fused = cfg->scale != 3 && !(cfg->variant & (M2T_VAR_SIMT_TAIL | M2T_VAR_UNFUSED_TAIL));
+    const int per_tail = tail_fused ? (cfg->scale == 4 ? 2 : 1) : (cfg->scale == 4 ? 4 : 3);
+    p->n_launches = 1 /*head*/ + cfg->n_blocks * per_block + tail_passes * per_tail;
     *out = p;
     return M2T_OK;
 }
@@ -239,6 +242,13 @@ static int run_tail(uint32_t variant, int scale, const PackedLayout& L, const ui
     const float* b0p = reinterpret_cast<const float*>(W + L.t0b);
     const __half* wc = reinterpret_cast<const __half*>(W + L.tcw);
     const int pad1 = scale == 4 ? 0 : 1;
+    if (tc && scale != 3 && !(variant & M2T_VAR_UNFUSED_TAIL)) {
+        // last PixelShuffle(2) stage + GELU + 3x3 conv + clamp + crop in one kernel (tail_fused.cu)
+        if (scale == 2) return launch_tail_fused(XR, w0, b0p, wc, y, B, g.Hp, g.Wp, hout, wout, b0, rgb_range, s);
+        M2T_TRY(launch_tail_up_umma(XR, w0, b0p, T1, B, g.Hp, g.Wp, 2, 0, s));
+        return launch_tail_fused(T1, reinterpret_cast<const __half*>(W + L.t3w), reinterpret_cast<const float*>(W + L.t3b),
+                                 wc, y, B, 2 * g.Hp, 2 * g.Wp, hout, wout, b0, rgb_range, s);
+    }
     if (tc) M2T_TRY(launch_tail_up_umma(XR, w0, b0p, T1, B, g.Hp, g.Wp, r0, pad1, s));
     else M2T_TRY(launch_tail_up_simt(XR, w0, b0p, T1, B, g.Hp, g.Wp, r0, pad1, s));
     __half* Tl = T1;

@@ -191,6 +191,10 @@ int launch_tail_up_umma(const __half* A, const __half* Wt, const float* bias, __
 int launch_tail_out_umma(const __half* T, const __half* Wc, float* y, int Bc, int hp, int wp, int hout, int wout,
                          int b0, float rgb_range, cudaStream_t s);
 
+// tail_fused.cu : last PixelShuffle(2) stage (1x1 conv + bias + shuffle + GELU) + 3x3 reflect conv + clamp + crop
+int launch_tail_fused(const __half* A, const __half* W1, const float* bias, const __half* Wc, float* y, int Bc, int h,
+                      int w, int hout, int wout, int b0, float rgb_range, cudaStream_t s);
+
 // pack.cu
 int pack_weights_impl(const PackedLayout& L, const float* const* params, int n_params, uint8_t* packed,
                       cudaStream_t s);

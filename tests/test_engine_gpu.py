@@ -179,3 +179,18 @@ def test_stage_ffconv_tensor_core_vs_cuda_core(B, Hp, Wp):
         assert torch.allclose(stats[..., 1], s2, rtol=1e-6, atol=1e-3)
         outs.append(xo)
     assert (outs[0] - outs[1]).abs().max().item() <= 1e-3
+
+
+@pytest.mark.parametrize("scale,shape", [(4, (2, 3, 40, 72)), (2, (1, 3, 96, 72)), (4, (1, 3, 128, 128)), (2, (3, 3, 33, 100))])
+def test_fused_tail_equals_two_kernel_tail(scale, shape):
+    """x2/x4 default: the last PixelShuffle stage + 3x3 conv run as one kernel (tail_fused.cu); the unfused
+    variant keeps the 4x-resolution tensor in HBM.  Same operands and roundings, only the fp32 summation order of
+    the 9 taps differs."""
+    from m2trans_b200 import _lib
+    from m2trans_b200.synthetic import synthetic_input
+    x = synthetic_input(shape[0], shape[2], shape[3], seed=5).cuda()
+    y_f = _model(scale, 3)(x)
+    y_u = _model(scale, 3, variant=_lib.VAR_UNFUSED_TAIL)(x)
+    d = float((y_f - y_u).abs().max())
+    print(f"x{scale} {shape}: fused vs unfused tail max-abs {d:.2e}")
+    assert d <= 2e-6
