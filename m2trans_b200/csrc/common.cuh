@@ -163,7 +163,8 @@ int launch_branch_prep_all(const float* X, const double* stats, __half* T1, __ha
 int launch_attn_umma(int C, const __half* QKV, const __half* relx, __half* O, int B, int h, int w,
                      cudaStream_t s, const AttnFuse* fuse = nullptr);
 
-int read_attn_timing(long long* host64);   // development aid, zeros unless built with -DM2T_TIMING
+int read_attn_timing(long long* host64);   // development aid, zeros unless built with -DM2T_TIMING (256 values)
+int read_tail_timing(long long* host64);   // the same for the fused tail kernel (64 values)
 
 // conv_simt.cu : X_out = conv3x3_zero(Y) + bias + X_in, plus InstanceNorm partial sums
 // res/xr (optional): also write xr = fp16(Xout + res), the tail's first GEMM operand (ref :70)

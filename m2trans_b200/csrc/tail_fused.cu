@@ -7,7 +7,7 @@
 // One work item = a 16 x 12 tile of A pixels plus a 1-pixel halo (18 x 14 = 252 rows, ONE TMA box, OOB -> 0):
 //   1. GEMM-1 on tcgen05: 2 M-tiles x 2 N-halves (sub-pixel rows) of M128 x N128 x K64, accumulators
 //      double-buffered in TMEM.
-//   2. epilogue 1 (8 warps): TMEM -> bias + GELU (packed fp32x2) -> fp16 -> the 36 x 28-pixel U tile in shared
+//   2. epilogue 1 (16 warps): TMEM -> bias + GELU (packed fp32x2) -> fp16 -> the 36 x 28-pixel U tile in shared
 //      memory, 128-B-swizzled rows (PixelShuffle = the row address).  Pixels on rows/cols 1 and size-2 are also
 //      stored at -1 / size: the reflected ring the conv needs is built in place.
 //   3. conv as ONE GEMM per 128 U pixels: D[px][tap*3+c] = sum_k U[px][k] * W[tap][c][k]  (N = 27 -> 32, K = 64).
@@ -36,10 +36,18 @@ constexpr uint32_t TF_OFF_WC = TF_OFF_U + TF_UPX * 128;
 constexpr uint32_t TF_OFF_BIAS = TF_OFF_WC + TF_NC * 128;
 constexpr uint32_t TF_OFF_BAR = TF_OFF_BIAS + 256 * 4;
 constexpr uint32_t TF_SMEM = 1024 + TF_OFF_BAR + 256;
-constexpr int TF_THREADS = 320;                        // warps 0-3 and 6-9 epilogue, warp 4 TMA, warp 5 MMA
+constexpr int TF_EPI = 512;                            // 16 epilogue warps: the GELU epilogue is latency-bound with fewer
+constexpr int TF_THREADS = TF_EPI + 64;                // + warp 16 TMA, warp 17 MMA
 constexpr uint32_t TF_COL_D = 256;                     // TMEM column of the conv accumulators
 
-__device__ __forceinline__ void tf_epi_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void tf_epi_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+
+#ifdef M2T_TIMING
+__device__ long long g_tail_dbg[64];   // CTA 0, first 8 tiles: 6 clock64 stamps per tile (m2t_debug_attn_timing record 4)
+#define M2T_TT(slot) do { if (blockIdx.x == 0 && tid == 0 && it < 8) g_tail_dbg[(slot) + 8 * it] = clock64(); } while (0)
+#else
+#define M2T_TT(slot) do { } while (0)
+#endif
 
 __global__ void __launch_bounds__(TF_THREADS, 1)
 tail_fused_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW,
@@ -64,10 +72,10 @@ tail_fused_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     const int per_img = tiles_x * tiles_y;
     const int ntiles = Bc * per_img;
 
-    if (warp == 5) tmem_alloc(tmem_slot, 512);
-    if (tid == 128) {
+    if (warp == 17) tmem_alloc(tmem_slot, 512);
+    if (tid == TF_EPI) {
         mbar_init(wfull, 1); mbar_init(afull, 1); mbar_init(aempty, 1);
-        for (int a = 0; a < 2; ++a) { mbar_init(&accfull[a], 1); mbar_init(&accempty[a], 8); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&accfull[a], 1); mbar_init(&accempty[a], TF_EPI / 32); }
         mbar_init(ufull, 1); mbar_init(dfull, 1);
         mbar_fence_init();
         tma_prefetch_desc(&mapA);
@@ -78,7 +86,7 @@ tail_fused_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 4) {
+    if (warp == 16) {
         // ---- TMA producer ---------------------------------------------------------------------------------
         if (elect_one_sync()) {
             mbar_expect_tx(wfull, 256 * 128);
@@ -96,7 +104,7 @@ tail_fused_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
             }
             __syncwarp();
         }
-    } else if (warp == 5) {
+    } else if (warp == 17) {
         // ---- MMA issuer -----------------------------------------------------------------------------------
         constexpr uint32_t idesc1 = umma_idesc_f16(128, 128);
         constexpr uint32_t idesc2 = umma_idesc_f16(128, TF_NC);
@@ -137,15 +145,18 @@ tail_fused_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         }
     } else {
         // ---- epilogue warps -------------------------------------------------------------------------------
-        const int quad = warp & 3, wg = warp >= 6 ? 1 : 0;
-        const int et = wg * 128 + quad * 32 + lane;                  // 0..255
+        // warpgroup wg serves sub-pixel column wg/2 and channels (wg%2)*32.. of every accumulator unit
+        const int quad = warp & 3, wg = warp >> 2;
+        const int et = tid;                                          // 0..511
         const uint32_t lanef = (uint32_t)(quad * 32) << 16;
         {   // conv weights [9][16][64] (rows 0..2 of each tap real) -> [32][64] rows tap*3+c, 128-B swizzled
-            const int row = et >> 3, ch = et & 7;
-            uint4 v = make_uint4(0u, 0u, 0u, 0u);
-            if (row < 27) v = *reinterpret_cast<const uint4*>(wc + ((row / 3) * 16 + (row % 3)) * NF + ch * 8);
-            *reinterpret_cast<uint4*>(sm + TF_OFF_WC + row * 128 + ((ch ^ (row & 7)) << 4)) = v;
-            sbias[et] = bias[et];
+            if (et < 256) {
+                const int row = et >> 3, ch = et & 7;
+                uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                if (row < 27) v = *reinterpret_cast<const uint4*>(wc + ((row / 3) * 16 + (row % 3)) * NF + ch * 8);
+                *reinterpret_cast<uint4*>(sm + TF_OFF_WC + row * 128 + ((ch ^ (row & 7)) << 4)) = v;
+                sbias[et] = bias[et];
+            }
         }
         fence_proxy_async();
         tf_epi_sync();
@@ -157,6 +168,7 @@ tail_fused_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             const int bl = tile / per_img, r = tile - bl * per_img;
             const int y0 = (r / tiles_x) * TF_TH, x0 = (r % tiles_x) * TF_TW;
+            M2T_TT(0);
             // ---- epilogue 1: GEMM-1 accumulators -> GELU -> U tile ------------------------------------------
             for (int u = 0; u < 4; ++u, ++un) {
                 const uint32_t acc = un & 1, aph = (un >> 1) & 1;
@@ -164,7 +176,7 @@ tail_fused_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
                 const int ty = p / TF_AW, tx = p - ty * TF_AW;
                 const int gy = y0 - 1 + ty, gx = x0 - 1 + tx;
                 const bool valid = p < TF_APX && gy >= 0 && gy < h && gx >= 0 && gx < w;
-                const int uu = u & 1, vv = wg;                       // sub-pixel (row, col)
+                const int uu = u & 1, vv = wg >> 1, c0 = (wg & 1) * 32; // sub-pixel (row, col), first channel
                 const int Y = 2 * gy + uu, X = 2 * gx + vv;
                 int dyr = Y == 1 ? -2 : (Y == H2 - 2 ? 2 : 0);        // reflected copy: -1 <- 1, H2 <- H2-2
                 int dxr = X == 1 ? -2 : (X == W2 - 2 ? 2 : 0);
@@ -174,8 +186,7 @@ tail_fused_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
                 const float* bs = sbias + (uu * 2 + vv) * NF;
                 mbar_wait(&accfull[acc], aph);
                 tc_fence_after();
-#pragma unroll
-                for (int c0 = 0; c0 < NF; c0 += 32) {
+                {
                     uint32_t rr[32];
                     tmem_ld32(tmem_base + acc * 128 + vv * NF + c0 + lanef, rr);
                     tmem_ld_wait();
@@ -208,15 +219,18 @@ tail_fused_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&accempty[acc]);
             }
+            M2T_TT(1);
             fence_proxy_async();           // U tile written by the generic proxy, read by the tensor core
             tf_epi_sync();
             if (et == 0) mbar_arrive(ufull);
+            M2T_TT(2);
             // ---- epilogue 2: conv accumulators -> planes -> 9-tap gather -------------------------------------
             mbar_wait(dfull, it & 1);
             tc_fence_after();
+            M2T_TT(3);
 #pragma unroll 1
-            for (int jj = 0; jj < 4; ++jj) {
-                const int m = wg + 2 * jj;
+            for (int jj = 0; jj < 2; ++jj) {
+                const int m = wg + 4 * jj;
                 uint32_t rr[32];
                 tmem_ld32(tmem_base + TF_COL_D + m * TF_NC + lanef, rr);
                 tmem_ld_wait();
@@ -226,9 +240,9 @@ tail_fused_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
             }
             tc_fence_before();
             tf_epi_sync();
+            M2T_TT(4);
 #pragma unroll 1
-            for (int j = 0; j < 3; ++j) {
-                const int o = et + 256 * j;                          // 32 x 24 output pixels of the tile
+            for (int o = et; o < 4 * TF_TH * TF_TW; o += TF_EPI) {    // 32 x 24 output pixels of the tile
                 const int oyl = o / (2 * TF_TW), oxl = o - oyl * (2 * TF_TW);
                 const int Yo = 2 * y0 + oyl, Xo = 2 * x0 + oxl;
                 if (Yo < hout && Xo < wout) {
@@ -248,13 +262,23 @@ tail_fused_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
                 }
             }
             tf_epi_sync();                 // planes consumed: the next tile may overwrite the U tile
+            M2T_TT(5);
         }
     }
     pdl_trigger();
     tc_fence_before();
     __syncthreads();
-    if (warp == 5) tmem_dealloc(tmem_base, 512);
+    if (warp == 17) tmem_dealloc(tmem_base, 512);
 }
+
+#ifdef M2T_TIMING
+int read_tail_timing(long long* host64) {
+    M2T_CUDA(cudaMemcpyFromSymbol(host64, g_tail_dbg, sizeof(long long) * 64));
+    return M2T_OK;
+}
+#else
+int read_tail_timing(long long* host64) { memset(host64, 0, sizeof(long long) * 64); return M2T_OK; }
+#endif
 
 // A: fp16 [Bc][h][w][64]; W1: fp16 [256][64] sub-pixel-major; bias fp32 [256]; Wc: fp16 [9][16][64];
 // y: fp32 NCHW, images b0.. cropped to hout x wout (hout <= 2h, wout <= 2w)
