@@ -15,7 +15,8 @@
 // window partition / reverse (ref :310, :332) are TMA box coordinates and the store address.
 // Operands stream in 64-channel blocks through two rings (Q+K blocks, V blocks).  C = 16 / 64 CTAs need <= 256
 // TMEM columns and <= 110 KB of shared memory, so two CTAs share an SM and hide each other's latencies.
-// Warp roles (192 threads): warps 0-3 softmax + epilogue (thread = query row), warp 4 TMA, warp 5 MMA issue.
+// Warp roles (192 threads): warps 0-3 softmax + epilogue (thread = query row), warp 4 TMA, warp 5 MMA issue;
+// C = 256 fused adds warps 6-9, which share the epilogue of the rows of warps 0-3 (the epilogue is half of that kernel's chain).
 //
 // FUSE = true additionally folds the CFTM branch glue (ref :139-161) into the epilogue, see AttnFuse.
 #include "common.cuh"
@@ -50,7 +51,12 @@ struct AtCfg {
     static constexpr uint32_t OFF_T = OFF_P + 2 * 16384;      // P: per window two 64-key blocks of [64 rows][128 B]
     static constexpr uint32_t OFF_REL = OFF_T + ST * T_STAGE;
     static constexpr uint32_t OFF_BAR = OFF_REL + (NBLK * REL_BLOCK + 1023) / 1024 * 1024;
-    static constexpr uint32_t SMEM = 1024 + OFF_BAR + 256;
+    // C = 256 fused: a second epilogue warpgroup (warps 6-9) takes half of the sub-pixels of every 64-channel block;
+    // the per-row 1/sum travels through smem (double-buffered by pair parity)
+    static constexpr bool SPLIT = FUSE && C == 256;
+    static constexpr int THREADS = SPLIT ? 320 : 192;
+    static constexpr uint32_t OFF_INV = OFF_BAR + 256;
+    static constexpr uint32_t SMEM = 1024 + OFF_BAR + 256 + (SPLIT ? 1024 : 0);
     static constexpr uint32_t TX_QK = 2 * 64 * ROWB + 2 * 100 * ROWB;
     static constexpr uint32_t TX_V = 2 * 100 * ROWB;
     static constexpr uint32_t TX_T = 2 * 64 * ROWB;
@@ -85,7 +91,7 @@ __device__ long long g_attn_dbg[4 * 64];   // one 64-entry record per branch (fu
 #endif
 
 template <int C, bool FUSE>
-__global__ void __launch_bounds__(192, AtCfg<C, FUSE>::MIN_CTAS)
+__global__ void __launch_bounds__(AtCfg<C, FUSE>::THREADS, AtCfg<C, FUSE>::MIN_CTAS)
 attn_umma_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapKV,
                  const __grid_constant__ CUtensorMap mapR, const __grid_constant__ CUtensorMap mapT,
                  __half* __restrict__ O, int h, int w, int nwin, const AttnFuse fz) {
@@ -117,11 +123,11 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
 #endif
 
     // zero P (the 12 padding key columns stay zero for ever) and the 12 padding rows of every V stage
-    for (uint32_t i = tid * 16; i < 2 * 16384; i += 192 * 16) *reinterpret_cast<uint4*>(sm + CF::OFF_P + i) = make_uint4(0, 0, 0, 0);
+    for (uint32_t i = tid * 16; i < 2 * 16384; i += CF::THREADS * 16) *reinterpret_cast<uint4*>(sm + CF::OFF_P + i) = make_uint4(0, 0, 0, 0);
     for (int s = 0; s < SV; ++s)
         for (int win = 0; win < 2; ++win) {
             uint8_t* pad = sm + CF::OFF_V + s * CF::V_STAGE + win * CF::WIN_B + 100 * ROWB;
-            for (uint32_t i = tid * 16; i < (WR - 100) * ROWB; i += 192 * 16) *reinterpret_cast<uint4*>(pad + i) = make_uint4(0, 0, 0, 0);
+            for (uint32_t i = tid * 16; i < (WR - 100) * ROWB; i += CF::THREADS * 16) *reinterpret_cast<uint4*>(pad + i) = make_uint4(0, 0, 0, 0);
         }
     fence_proxy_async();
     if (warp == 5) tmem_alloc(tmem_slot, CF::TM_COLS);
@@ -129,13 +135,13 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
         for (int s = 0; s < 2; ++s) {
             mbar_init(&q_full[s], 1); mbar_init(&q_empty[s], 1);
             mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1);
-            mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], 4);
+            mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], CF::SPLIT ? 8 : 4);
         }
         mbar_init(rfull, 1);
         mbar_init(s_full, 1);
         mbar_init(p_ready, 4);
         mbar_init(o_full, 1);
-        mbar_init(o_empty, 4);
+        mbar_init(o_empty, CF::SPLIT ? 8 : 4);
         mbar_fence_init();
         tma_prefetch_desc(&mapQ);
         tma_prefetch_desc(&mapKV);
@@ -268,14 +274,22 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
             }
         }
     } else {
-        // thread (warp, lane) owns TMEM lane 32*warp + lane: window (lane >> 4), query row 16*warp + (lane & 15)
-        const int win = lane >> 4, qi = warp * 16 + (lane & 15);
-        const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
+        // thread (warp, lane) owns TMEM lane 32*quad + lane: window (lane >> 4), query row 16*quad + (lane & 15).
+        // Warps 0-3 do the softmax and (their share of) the epilogue; helper warps 6-9 (SPLIT only) share the rows of
+        // the primary warp with the same quadrant and only run the epilogue.
+        const int quad = warp & 3;
+        const bool helper = CF::SPLIT && warp >= 6;
+        const int win = lane >> 4, qi = quad * 16 + (lane & 15);
+        const uint32_t lane_sel = (uint32_t)(quad * 32) << 16;
+        float* sinv = reinterpret_cast<float*>(sm + CF::OFF_INV);
+        (void)sinv;
         uint8_t* prow = sm + CF::OFF_P + win * 16384 + qi * 128;
         uint32_t it = 0, gt = 0;
         (void)gt;
         pdl_wait();
         for (int p = blockIdx.x; p < npairs; p += gridDim.x, ++it) {
+            float inv;
+            if (!helper) {
             M2T_T(0);
             mbar_wait(s_full, it & 1);
             tc_fence_after();
@@ -320,12 +334,17 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
                 }
                 *reinterpret_cast<uint4*>(prow + (q >> 3) * 8192 + (((q & 7) ^ (qi & 7)) << 4)) = u;
             }
-            const float inv = 1.f / sum;
+            inv = 1.f / sum;
+            if constexpr (CF::SPLIT) sinv[(it & 1) * 128 + quad * 32 + lane] = inv;
             M2T_T(2);
             fence_proxy_async();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(p_ready);
+            } else {
+                mbar_wait(p_ready, it & 1);        // the primaries have published 1/sum of this pair
+                inv = sinv[(it & 1) * 128 + quad * 32 + lane];
+            }
 
             const int wi = 2 * p + win;
             const bool valid = wi < nwin;
@@ -355,15 +374,16 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
                 if constexpr (!CF::TSTAGE) {
                     const __half* trow = fz.T + (((long)wc.b * h + ly) * w + lx) * C;
 #pragma unroll
-                    for (int j = 0; j < 2 * SPB; ++j) tkr[j] = *reinterpret_cast<const uint4*>(trow + j * 8);
+                    for (int j = 0; j < SPB; ++j) ldg256(trow + j * 16, tkr[2 * j], tkr[2 * j + 1]);
                 }
-                uint4 hcur[2 * SPB], hnxt[2 * SPB];             // n_{k+1}/2 segments of the current / next block
+                constexpr int JN = CF::SPLIT ? SPB / 2 : SPB;    // sub-pixels of each block this thread handles
+                const int j0 = helper ? SPB / 2 : 0;
+                uint4 hcur[2 * JN], hnxt[2 * JN];               // n_{k+1}/2 segments of the current / next block
                 auto load_h = [&](int nb, uint4* dst) {
 #pragma unroll
-                    for (int j = 0; j < SPB; ++j) {
-                        const __half* hp = tnext_ptr(nb * SPB + j);
-                        dst[2 * j] = *reinterpret_cast<const uint4*>(hp);
-                        dst[2 * j + 1] = *reinterpret_cast<const uint4*>(hp + 8);
+                    for (int j = 0; j < JN; ++j) {
+                        const __half* hp = tnext_ptr(nb * SPB + j0 + j);
+                        ldg256(hp, dst[2 * j], dst[2 * j + 1]);
                     }
                 };
                 if (has_next) load_h(0, hcur);
@@ -380,7 +400,8 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
                         tst = sm + CF::OFF_T + (gt & 1) * CF::T_STAGE + win * 64 * ROWB + qi * 128;
                     }
 #pragma unroll
-                    for (int j = 0; j < SPB; ++j) {
+                    for (int jj = 0; jj < JN; ++jj) {
+                        const int j = j0 + jj;
                         const int s = nb * SPB + j;
                         uint32_t r[16];
                         tmem_ld16(tmem_base + lane_sel + TM_O + s * NB, r);
@@ -408,20 +429,18 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
 #pragma unroll
                             for (int e = 0; e < 8; ++e) yh[e] = __floats2half2_rn(yv[2 * e], yv[2 * e + 1]);
                             __half* yp = fz.Y + pix * NF + NB * br;
-                            *reinterpret_cast<uint4*>(yp) = yo[0];
-                            *reinterpret_cast<uint4*>(yp + 8) = yo[1];
+                            stg256(yp, yo[0], yo[1]);
                             if (has_next) {
                                 uint4 to[2];
                                 __half2* tnh = reinterpret_cast<__half2*>(to);
-                                const __half2* hh = reinterpret_cast<const __half2*>(&hcur[2 * j]);
+                                const __half2* hh = reinterpret_cast<const __half2*>(&hcur[2 * jj]);
 #pragma unroll
                                 for (int e = 0; e < 8; ++e) {
                                     const float2 hf = __half22float2(hh[e]);
                                     tnh[e] = __floats2half2_rn(fmaf(0.5f, yv[2 * e], hf.x), fmaf(0.5f, yv[2 * e + 1], hf.y));
                                 }
                                 __half* tp = tnext_ptr(s);
-                                *reinterpret_cast<uint4*>(tp) = to[0];
-                                *reinterpret_cast<uint4*>(tp + 8) = to[1];
+                                stg256(tp, to[0], to[1]);
                             }
                         }
                     }
@@ -432,7 +451,7 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
                     }
                     if (has_next && nb + 1 < NBLK) {
 #pragma unroll
-                        for (int j = 0; j < 2 * SPB; ++j) hcur[j] = hnxt[j];
+                        for (int j = 0; j < 2 * JN; ++j) hcur[j] = hnxt[j];
                     }
                 }
             } else {
@@ -506,7 +525,7 @@ static int launch_attn_umma_cf(const __half* QKV, const __half* relx, __half* O,
     const int cap = device_sm_count() * CF::MIN_CTAS;
     const int grid = npairs < cap ? npairs : cap;
     M2T_ENSURE_SMEM((attn_umma_kernel<C, FUSE>), CF::SMEM);
-    M2T_CUDA(launch_pdl(attn_umma_kernel<C, FUSE>, dim3(grid), dim3(192), CF::SMEM, s, mapQ, mapKV, mapR, mapT, O, h, w, nwin, fz));
+    M2T_CUDA(launch_pdl(attn_umma_kernel<C, FUSE>, dim3(grid), dim3(CF::THREADS), CF::SMEM, s, mapQ, mapKV, mapR, mapT, O, h, w, nwin, fz));
     return M2T_OK;
 }
 

@@ -216,8 +216,13 @@ branch_prep_all_kernel(const float* __restrict__ X, const double* __restrict__ s
     const float sc = branch == 0 ? 1.f : 0.5f;
     const float4* xp = reinterpret_cast<const float4*>(X + pix * NF + NB * branch);
     float4 xv[4];
+    {   // 64 contiguous bytes per thread as two 256-bit loads
+        uint4 a[4];
+        ldg256(xp, a[0], a[1]);
+        ldg256(xp + 2, a[2], a[3]);
 #pragma unroll
-    for (int v = 0; v < 4; ++v) xv[v] = xp[v];
+        for (int v = 0; v < 4; ++v) xv[v] = make_float4(__uint_as_float(a[v].x), __uint_as_float(a[v].y), __uint_as_float(a[v].z), __uint_as_float(a[v].w));
+    }
     uint4 o[2];
     __half2* oh = reinterpret_cast<__half2*>(o);
 #pragma unroll
@@ -236,8 +241,7 @@ branch_prep_all_kernel(const float* __restrict__ X, const double* __restrict__ s
         const long lp = ((long)b * (Hp >> 2) + (y >> 2)) * (Wp >> 2) + (x >> 2);
         dst = (branch == 2 ? H3 : H4) + lp * 256 + ((y & 3) * 4 + (x & 3)) * NB;
     }
-    *reinterpret_cast<uint4*>(dst) = o[0];
-    *reinterpret_cast<uint4*>(dst + 8) = o[1];
+    stg256(dst, o[0], o[1]);
     // multi-wave grid: let the next kernel's CTAs in only when this CTA is done, or they would take the SMs that
     // this grid's later waves still need
     pdl_trigger();

@@ -138,16 +138,16 @@ qkv_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 tmem_ld_wait();
                 if (row < M) {
 #pragma unroll
-                    for (int v = 0; v < OCH / 8; ++v) {
-                        uint4 u;
-                        uint32_t* pu = reinterpret_cast<uint32_t*>(&u);
+                    for (int v = 0; v < OCH / 16; ++v) {       // 32 B per store: one sector transaction, not two
+                        uint4 u[2];
+                        uint32_t* pu = reinterpret_cast<uint32_t*>(u);
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const __half2 h = __floats2half2_rn(__uint_as_float(r[v * 8 + 2 * e]),
-                                                                __uint_as_float(r[v * 8 + 2 * e + 1]));
+                        for (int e = 0; e < 8; ++e) {
+                            const __half2 h = __floats2half2_rn(__uint_as_float(r[v * 16 + 2 * e]),
+                                                                __uint_as_float(r[v * 16 + 2 * e + 1]));
                             pu[e] = *reinterpret_cast<const uint32_t*>(&h);
                         }
-                        *reinterpret_cast<uint4*>(orow + c0 + v * 8) = u;
+                        stg256(orow + c0 + v * 16, u[0], u[1]);
                     }
                 }
             }

@@ -140,16 +140,16 @@ tail_up_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                         tmem_ld32(tmem_base + acc * 256 + sp * NF + c0 + ((uint32_t)(quad * 32) << 16), r);
                         tmem_ld_wait();
 #pragma unroll
-                        for (int v = 0; v < 4; ++v) {
-                            uint4 q;
-                            uint32_t* pq = reinterpret_cast<uint32_t*>(&q);
+                        for (int v = 0; v < 2; ++v) {            // 32 B per store: one sector transaction, not two
+                            uint4 q[2];
+                            uint32_t* pq = reinterpret_cast<uint32_t*>(q);
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const int c = c0 + v * 8 + 2 * e;
-                                pq[e] = gelu_pair_h2(f2_pack(__uint_as_float(r[v * 8 + 2 * e]), __uint_as_float(r[v * 8 + 2 * e + 1])),
+                            for (int e = 0; e < 8; ++e) {
+                                const int c = c0 + v * 16 + 2 * e;
+                                pq[e] = gelu_pair_h2(f2_pack(__uint_as_float(r[v * 16 + 2 * e]), __uint_as_float(r[v * 16 + 2 * e + 1])),
                                                      *reinterpret_cast<const uint64_t*>(bs + c));
                             }
-                            *reinterpret_cast<uint4*>(op + c0 + v * 8) = q;
+                            stg256(op + c0 + v * 16, q[0], q[1]);
                         }
                     }
                 }
