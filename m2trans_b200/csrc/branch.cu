@@ -198,7 +198,9 @@ branch_prep_all_kernel(const float* __restrict__ X, const double* __restrict__ s
     __shared__ float smu[NF], srs[NF];
     pdl_wait();
     const int t = threadIdx.x;
-    const long pix = (long)blockIdx.x * 64 + (t >> 2);
+    // The producer (head or the previous ff conv) wrote X front to back just before this kernel: walk it back to
+    // front so the most recently written part is read while it is still in L2.
+    const long pix = (long)(gridDim.x - 1 - blockIdx.x) * 64 + (t >> 2);
     const int npix = Hp * Wp;
     const int b = (int)(pix / npix);
     const int r = (int)(pix - (long)b * npix);

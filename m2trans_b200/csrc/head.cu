@@ -1,10 +1,12 @@
 // Head stage: frame reflect-pad (ref M2Trans_network.py:78-86) + 3->64 3x3 reflect conv + bias
 // (ref :34,:63), written as the fp32 NHWC residual stream, plus the InstanceNorm partial sums of
 // the first CFTM (ref :127,:135).  K = 27 is too thin for the tensor cores: this stage is
-// HBM-bound (12 B in, 256 B out per pixel) and runs on the CUDA cores.
-// One CTA = 32 consecutive pixels of one padded row: the 3 x 3 x 34 input patch is staged in shared memory
-// once (both reflections resolved there), 4 threads per pixel each produce 16 channels and store 4 float4
-// (64 B contiguous per pixel and instruction).
+// HBM-bound on paper (12 B in, 256 B out per pixel) and runs on the CUDA cores.
+// One CTA = a 32 x 8 pixel tile; its 3 x 10 x 34 input patch is staged in shared memory with both reflections
+// resolved.  A thread owns FOUR output channels and keeps their 27 x 4 weights in registers; a half-warp covers
+// the 64 channels of one pixel, so the patch reads are shared-memory broadcasts (27 per pixel) and the arithmetic
+// is 54 packed FFMA2 per pixel: FMA-bound, not LSU-bound like the first version that re-read the weights
+// from shared memory for every pixel.  Each half-warp stores the 256 contiguous bytes of its pixel.
 #include "common.cuh"
 
 namespace m2t {
@@ -14,108 +16,92 @@ __device__ __forceinline__ int reflect1(int i, int n) { return i < 0 ? -i : (i >
 // frame padding: bottom/right only (ref :85)
 __device__ __forceinline__ int frame_src(int i, int n) { return i < n ? i : 2 * (n - 1) - i; }
 
-constexpr int HEAD_PX = 32;  // pixels per CTA (4 threads per pixel); Wp is a multiple of 32
+constexpr int HEAD_TW = 32, HEAD_TH = 8;          // tile; Hp and Wp are multiples of 32
+constexpr int HEAD_THREADS = 32 * HEAD_TH;        // warp w computes row w of the tile
 
-constexpr int HEAD_CHUNKS = 8;    // chunks of HEAD_PX pixels per CTA: 256 pixels, always inside one image
+__device__ __forceinline__ uint64_t hd_pack(float a, float b) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t hd_fma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
 
-__global__ void __launch_bounds__(HEAD_PX * 4)
+__global__ void __launch_bounds__(HEAD_THREADS)
 head_conv_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                  float* __restrict__ res, double* __restrict__ stats, int B, int H, int W, int Hp, int Wp) {
-    __shared__ float sw[27 * NF];
-    __shared__ float sb[NF];
-    __shared__ float sx[2][3][3][HEAD_PX + 2];
-    __shared__ float red[HEAD_PX * 4 / 32][2][NF];
-    const int t = threadIdx.x;
-    for (int i = t; i < 27 * NF; i += HEAD_PX * 4) sw[i] = w[i];
-    if (t < NF) sb[t] = bias[t];
-    pdl_wait();          // weights above are constants; everything below touches activations / statistics
+    __shared__ float sx[3][HEAD_TH + 2][HEAD_TW + 2];
+    __shared__ float red[HEAD_TH][2][NF];
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const int cq = lane & 15, half = lane >> 4;
+    // weights of this thread's 4 channels, as packed pairs: constants, loaded before the dependency wait
+    uint64_t w01[27], w23[27];
+#pragma unroll
+    for (int k = 0; k < 27; ++k) {
+        const float4 wv = __ldg(reinterpret_cast<const float4*>(w + k * NF + 4 * cq));
+        w01[k] = hd_pack(wv.x, wv.y);
+        w23[k] = hd_pack(wv.z, wv.w);
+    }
+    const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + 4 * cq));
+    pdl_wait();
 
-    const int npix = Hp * Wp;
-    const long cta_px0 = (long)blockIdx.x * HEAD_PX * HEAD_CHUNKS;
-    const int b = (int)(cta_px0 / npix);
+    const int tiles_x = Wp / HEAD_TW, tiles_y = Hp / HEAD_TH;
+    const int b = blockIdx.x / (tiles_x * tiles_y), r = blockIdx.x - b * tiles_x * tiles_y;
+    const int y0 = (r / tiles_x) * HEAD_TH, x0 = (r % tiles_x) * HEAD_TW;
     const float* xb = x + (long)b * 3 * H * W;
-    const int q = t & 3, p = t >> 2;
-    // per-thread InstanceNorm partial sums of its 16 channels over all chunks: one set of atomics per CTA
-    float ssum[4][4], ssq[4][4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-#pragma unroll
-        for (int e = 0; e < 4; ++e) { ssum[j][e] = 0.f; ssq[j][e] = 0.f; }
-
-    auto stage = [&](int chunk, int buf) {
-        const int rem = (int)(cta_px0 + (long)chunk * HEAD_PX - (long)b * npix);
-        const int y = rem / Wp, x0 = rem - y * Wp;
-        for (int i = t; i < 9 * (HEAD_PX + 2); i += HEAD_PX * 4) {
-            const int c = i / (3 * (HEAD_PX + 2)), r = i - c * 3 * (HEAD_PX + 2);
-            const int ky = r / (HEAD_PX + 2), col = r - ky * (HEAD_PX + 2);
-            const int sy = frame_src(reflect1(y + ky - 1, Hp), H);
-            const int sxx = frame_src(reflect1(x0 + col - 1, Wp), W);
-            sx[buf][c][ky][col] = __ldg(xb + ((long)c * H + sy) * W + sxx);
-        }
-    };
-    stage(0, 0);
+    for (int i = t; i < 3 * (HEAD_TH + 2) * (HEAD_TW + 2); i += HEAD_THREADS) {
+        const int c = i / ((HEAD_TH + 2) * (HEAD_TW + 2)), rr = i - c * (HEAD_TH + 2) * (HEAD_TW + 2);
+        const int py = rr / (HEAD_TW + 2), px = rr - py * (HEAD_TW + 2);
+        const int sy = frame_src(reflect1(y0 + py - 1, Hp), H);
+        const int sxx = frame_src(reflect1(x0 + px - 1, Wp), W);
+        sx[c][py][px] = __ldg(xb + ((long)c * H + sy) * W + sxx);
+    }
     __syncthreads();
-    for (int chunk = 0; chunk < HEAD_CHUNKS; ++chunk) {
-        const int buf = chunk & 1;
-        if (chunk + 1 < HEAD_CHUNKS) stage(chunk + 1, buf ^ 1);
-        float acc[4][4];
+
+    float s[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+    float* orow = res + (((long)b * Hp + y0 + warp) * Wp + x0) * NF + 4 * cq;
+#pragma unroll 2
+    for (int i = 0; i < HEAD_TW / 2; ++i) {
+        const int px = 2 * i + half;
+        uint64_t a01 = hd_pack(bv.x, bv.y), a23 = hd_pack(bv.z, bv.w);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float4 bv = *reinterpret_cast<const float4*>(&sb[4 * (q + 4 * j)]);
-            acc[j][0] = bv.x; acc[j][1] = bv.y; acc[j][2] = bv.z; acc[j][3] = bv.w;
-        }
+        for (int c = 0; c < 3; ++c)
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-#pragma unroll
-            for (int ky = 0; ky < 3; ++ky) {
+            for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
                 for (int kx = 0; kx < 3; ++kx) {
-                    const float v = sx[buf][c][ky][p + kx];
-                    const float* wr = &sw[(c * 9 + ky * 3 + kx) * NF];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float4 wv = *reinterpret_cast<const float4*>(&wr[4 * (q + 4 * j)]);
-                        acc[j][0] = fmaf(v, wv.x, acc[j][0]);
-                        acc[j][1] = fmaf(v, wv.y, acc[j][1]);
-                        acc[j][2] = fmaf(v, wv.z, acc[j][2]);
-                        acc[j][3] = fmaf(v, wv.w, acc[j][3]);
-                    }
+                    const float v = sx[c][warp + ky][px + kx];
+                    const uint64_t vv = hd_pack(v, v);
+                    a01 = hd_fma2(vv, w01[c * 9 + ky * 3 + kx], a01);
+                    a23 = hd_fma2(vv, w23[c * 9 + ky * 3 + kx], a23);
                 }
-            }
-        }
-        float* o = res + (cta_px0 + (long)chunk * HEAD_PX + p) * NF;
+        float o[4];
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(o[0]), "=f"(o[1]) : "l"(a01));
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(o[2]), "=f"(o[3]) : "l"(a23));
+        *reinterpret_cast<float4*>(orow + (long)px * NF) = make_float4(o[0], o[1], o[2], o[3]);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            *reinterpret_cast<float4*>(o + 4 * (q + 4 * j)) = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) { ssum[j][e] += acc[j][e]; ssq[j][e] = fmaf(acc[j][e], acc[j][e], ssq[j][e]); }
-        }
-        __syncthreads();          // next chunk's patch is staged; this chunk's patch may be overwritten
+        for (int e = 0; e < 4; ++e) { s[e] += o[e]; s2[e] = fmaf(o[e], o[e], s2[e]); }
     }
 
-    // lanes with equal (lane & 3) hold the same 16 channels
+    // lanes l and l ^ 16 hold the same channels; one slot per (warp, channel), fixed summation order below
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int e = 0; e < 4; ++e) {
+        s[e] += __shfl_xor_sync(0xffffffffu, s[e], 16);
+        s2[e] += __shfl_xor_sync(0xffffffffu, s2[e], 16);
+    }
+    if (half == 0) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            float s = ssum[j][e], s2 = ssq[j][e];
-#pragma unroll
-            for (int m = 4; m < 32; m <<= 1) {
-                s += __shfl_xor_sync(0xffffffffu, s, m);
-                s2 += __shfl_xor_sync(0xffffffffu, s2, m);
-            }
-            if ((t & 31) < 4) {       // one slot per (warp, channel): fixed summation order below
-                red[t >> 5][0][4 * (q + 4 * j) + e] = s;
-                red[t >> 5][1][4 * (q + 4 * j) + e] = s2;
-            }
-        }
+        for (int e = 0; e < 4; ++e) { red[warp][0][4 * cq + e] = s[e]; red[warp][1][4 * cq + e] = s2[e]; }
     }
     __syncthreads();
     if (t < 2 * NF) {
         const int c = t >> 1, k = t & 1;
         double tot = 0.0;
 #pragma unroll
-        for (int wv = 0; wv < HEAD_PX * 4 / 32; ++wv) tot += (double)red[wv][k][c];
+        for (int wv = 0; wv < HEAD_TH; ++wv) tot += (double)red[wv][k][c];
         atomicAdd(&stats[((long)b * NF + c) * 2 + k], tot);
     }
     pdl_trigger();       // multi-wave grid: admit the next kernel only as this one drains
@@ -123,9 +109,9 @@ head_conv_kernel(const float* __restrict__ x, const float* __restrict__ w, const
 
 int launch_head(const float* x, const float* w, const float* b, float* res, double* stats, const Geom& g,
                 cudaStream_t s) {
-    const long total = (long)g.B * g.Hp * g.Wp;            // multiple of 1024: Hp and Wp are multiples of 32
-    M2T_CUDA(launch_pdl(head_conv_kernel, dim3((unsigned)(total / (HEAD_PX * HEAD_CHUNKS))), dim3(HEAD_PX * 4), 0, s, x, w, b,
-                        res, stats, g.B, g.H, g.W, g.Hp, g.Wp));
+    const int tiles = g.B * (g.Hp / HEAD_TH) * (g.Wp / HEAD_TW);
+    M2T_CUDA(launch_pdl(head_conv_kernel, dim3((unsigned)tiles), dim3(HEAD_THREADS), 0, s, x, w, b, res, stats, g.B, g.H,
+                        g.W, g.Hp, g.Wp));
     return M2T_OK;
 }
 
