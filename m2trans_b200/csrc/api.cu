@@ -44,6 +44,14 @@ bool pdl_enabled() {
     }
     return cached == 1;
 }
+bool pdl_in_graph() {
+    static int cached = -1;
+    if (cached < 0) {
+        const char* e = getenv("M2T_GRAPH_PDL");   // development switch: "0" drops the PDL attribute during stream capture
+        cached = (e && e[0] == '0') ? 0 : 1;
+    }
+    return cached == 1;
+}
 
 int check_device() {
     int dev = 0, major = 0, minor = 0;

@@ -61,6 +61,7 @@ int check_device();   // M2T_OK on an sm_100 device, M2T_E_DEVICE otherwise (api
 // on the previous kernel) and then block in pdl_wait() until the previous grid has completed and flushed.
 // Rule: no thread reads activations or writes ANY global memory before pdl_wait().
 bool pdl_enabled();
+bool pdl_in_graph();
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
                               Args&&... args) {
@@ -71,10 +72,12 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
     cfg.numAttrs = pdl_enabled() ? 1 : 0;
-    // Measured on B200 (cfg2): eager + PDL 2.35 ms < eager 2.43 ms, but graph 2.22 ms < graph + PDL 2.31 ms: inside a
-    // CUDA graph the plain kernel-to-kernel edge is already ~1 us, and early-launched CTAs only add contention.
+    // Measured on B200 (cfg2, final kernels): graph 1.745 ms, graph + PDL 1.718 ms, eager + PDL 1.725 ms (device
+    // time with the host running ahead).  An earlier measurement had PDL hurting inside graphs; that was caused by
+    // multi-wave kernels triggering at their START (dependents stole SM slots), fixed by triggering at the end.
+    // M2T_GRAPH_PDL=0 drops the attribute during capture for A/B runs.
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-    if (cfg.numAttrs && cudaStreamIsCapturing(s, &cap) == cudaSuccess && cap != cudaStreamCaptureStatusNone) cfg.numAttrs = 0;
+    if (cfg.numAttrs && !pdl_in_graph() && cudaStreamIsCapturing(s, &cap) == cudaSuccess && cap != cudaStreamCaptureStatusNone) cfg.numAttrs = 0;
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 #ifdef __CUDACC__

@@ -16,7 +16,7 @@ __device__ __forceinline__ int reflect1(int i, int n) { return i < 0 ? -i : (i >
 // frame padding: bottom/right only (ref :85)
 __device__ __forceinline__ int frame_src(int i, int n) { return i < n ? i : 2 * (n - 1) - i; }
 
-constexpr int HEAD_TW = 32, HEAD_TH = 8;          // tile; Hp and Wp are multiples of 32
+constexpr int HEAD_TW = 32, HEAD_TH = 4;          // tile; Hp and Wp are multiples of 32
 constexpr int HEAD_THREADS = 32 * HEAD_TH;        // warp w computes row w of the tile
 
 __device__ __forceinline__ uint64_t hd_pack(float a, float b) {
