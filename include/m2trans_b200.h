@@ -171,7 +171,9 @@ int m2t_transblock_forward(const float* d_x, float* d_y, const float* const* d_p
 int m2t_probe_umma(const void* d_a_image, uint32_t a_bytes, const void* d_b_image, uint32_t b_bytes,
                    uint64_t a_desc, uint64_t b_desc, uint32_t a_step, uint32_t b_step, int k_steps,
                    uint32_t idesc, int n_cols, float* d_out, void* stream);
-/* m2t_debug_attn_timing: host64 holds 5 x 64 values.  Record 4: CTA 0 of the last fused-tail launch, per tile i < 8 at
+/* m2t_debug_attn_timing: host64 holds 6 x 64 values.  Record 5: CTA 0 of the last tcgen05 ff-conv launch, per tile i < 8:
+ * epilogue [8i+0..4] tile start, residual loads issued, accumulator ready, staged, stored; MMA warp [8i+5..7] before
+ * / after the accumulator-free wait and after the halo-tile wait.  Record 4: CTA 0 of the last fused-tail launch, per tile i < 8 at
  * [8i+0..5]: tile start, GELU epilogue done, U tile published, conv accumulators ready, planes written, gather done.
  * Records 0..3: clock64 stamps of CTA 0 of the last tcgen05 attention launch of each branch (per record:
  * [6] kernel entry, [7] prologue done, then per pair i < 6 at [8i+0..5]: before S wait, S ready,

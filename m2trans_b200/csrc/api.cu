@@ -429,7 +429,8 @@ int m2t_stage_tail(uint32_t variant, int scale, int n_blocks, const void* d_pack
 int m2t_debug_attn_timing(long long* host64) {
     if (!host64) { set_error("null pointer"); return M2T_E_ARG; }
     M2T_TRY(read_attn_timing(host64));
-    return read_tail_timing(host64 + 256);
+    M2T_TRY(read_tail_timing(host64 + 256));
+    return read_conv_timing(host64 + 320);
 }
 
 }  // extern "C"

@@ -179,6 +179,7 @@ int launch_attn_umma(int C, const __half* QKV, const __half* relx, __half* O, in
 
 int read_attn_timing(long long* host64);   // development aid, zeros unless built with -DM2T_TIMING (256 values)
 int read_tail_timing(long long* host64);   // the same for the fused tail kernel (64 values)
+int read_conv_timing(long long* host64);   // the same for the tcgen05 ff conv (64 values)
 
 // conv_simt.cu : X_out = conv3x3_zero(Y) + bias + X_in, plus InstanceNorm partial sums
 // res/xr (optional): also write xr = fp16(Xout + res), the tail's first GEMM operand (ref :70)

@@ -76,11 +76,11 @@ ffconv_simt_kernel(const __half* __restrict__ Y, const __half* __restrict__ Wp, 
 #pragma unroll
         for (int o = 0; o < NF; ++o) Os[t * EPI_LD + o] = acc[o];
         __syncthreads();
-        float4 xi[16];
+        uint4 xi[16], rv[16];
         EpiStats st;
         st.clear();
-        epilogue_load_residual<CT_W>(t, Xin, b, y0, x0, Hp, Wpx, xi);
-        epilogue_apply<CT_W>(Os, t, xi, bias, Xout, st, b, y0, x0, Hp, Wpx, res, xr);
+        epilogue_load_residual<CT_W>(t, Xin, b, y0, x0, Hp, Wpx, xi, xr != nullptr ? res : nullptr, rv);
+        epilogue_apply<CT_W>(Os, t, xi, bias, Xout, st, b, y0, x0, Hp, Wpx, rv, xr);
         epilogue_flush_stats<0>(red, t, st, stats, b);
     }
 }

@@ -10,11 +10,16 @@
 // 36 MMAs (M=128, N=64, K=16) accumulate one tile in TMEM; two accumulators let the epilogue of tile i
 // overlap the MMAs of tile i+1.  The 9 x 64 x 64 weights stay resident in shared memory (72 KB).
 //
-// Warp roles (192 threads): warps 0-3 epilogue (TMEM -> smem staging -> coalesced +bias +residual store and
-// InstanceNorm partial sums), warp 4 TMA producer, warp 5 MMA issuer.
-// The stage is memory-bound (reads 128 B Y + 256 B X, writes 256 B X per pixel); the tensor pipe is ~half idle.
+// The fp32 residual stream moves by TMA in BOTH directions.  The first version loaded the residual rows with LDG and
+// stored the result with STG from the epilogue threads: with one epilogue warp per SM sub-partition the per-SM
+// load/store queue, not HBM, set the pace (measured: 7 K cycles per tile, the tensor pipe idle 70 % of the time, DRAM at
+// half its bandwidth).  Now the 128 x 64 fp32 tile of Xin lands in shared memory as two 128-byte-swizzled half tiles
+// (3-stage ring), thread = pixel = TMEM lane adds accumulator + bias IN PLACE (conflict-free 16-byte accesses thanks
+// to the swizzle), and a dedicated warp sends the tile back with a TMA store.  The InstanceNorm partial sums are a
+// second pass over the finished tile in shared memory with thread = channel.
+//
+// Warp roles (224 threads): warps 0-3 epilogue, warp 4 TMA loads, warp 5 MMA issuer, warp 6 TMA stores.
 #include "common.cuh"
-#include "epilogue.cuh"
 #include "tma.cuh"
 #include "umma.cuh"
 
@@ -24,34 +29,44 @@ constexpr int CU_TH = 16, CU_TW = 8;                                  // output 
 constexpr int CU_HW = CU_TW + 2;                                      // halo tile width (10)
 constexpr uint32_t CU_TILE_BYTES = (CU_TH + 2) * CU_HW * 128;         // 23040
 constexpr uint32_t CU_STAGE = 23 * 1024;                              // 1024-aligned stage pitch
-constexpr int CU_STAGES = 3;
+constexpr int CU_STAGES = 2;                                          // Y halo tiles (the MMAs run ahead of the epilogue)
+constexpr int CU_XSTAGES = 3;                                         // fp32 residual tiles
+constexpr uint32_t CU_XHALF = 128 * 128;                              // 128 pixels x 32 channels x 4 B
+constexpr uint32_t CU_XSTAGE = 2 * CU_XHALF;
 constexpr uint32_t CU_W_BYTES = 9 * NF * 128;                         // 73728
 constexpr uint32_t CU_OFF_A = CU_W_BYTES;
-constexpr uint32_t CU_OFF_O = CU_OFF_A + CU_STAGES * CU_STAGE;
-constexpr uint32_t CU_O_BYTES = 128 * EPI_LD * 4;                      // one fp32 staging tile per epilogue warpgroup
-constexpr uint32_t CU_OFF_RED = CU_OFF_O + 2 * CU_O_BYTES;            // 2 x float [4][2][64]
-constexpr uint32_t CU_OFF_BAR = CU_OFF_RED + 2 * 4 * 2 * NF * 4;
+constexpr uint32_t CU_OFF_X = CU_OFF_A + CU_STAGES * CU_STAGE;
+constexpr uint32_t CU_OFF_BIAS = CU_OFF_X + CU_XSTAGES * CU_XSTAGE;
+constexpr uint32_t CU_OFF_BAR = CU_OFF_BIAS + NF * 4;
 constexpr uint32_t CU_SMEM = 1024 + CU_OFF_BAR + 256;
-#ifndef M2T_CONV_WGS
-#define M2T_CONV_WGS 1
+constexpr int CU_THREADS = 224;
+
+#ifdef M2T_TIMING
+__device__ long long g_conv_dbg[64];   // CTA 0: epilogue thread 0 stamps [8i+0..4], MMA warp stamps [8i+5..7], tiles i < 8
+#define M2T_CT(slot) do { if (xr == nullptr && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 5) && it < 8) g_conv_dbg[(slot) + 8 * it] = clock64(); } while (0)
+#else
+#define M2T_CT(slot) do { } while (0)
 #endif
-constexpr int CU_WGS = M2T_CONV_WGS;   // epilogue warpgroups (A/B switch for tuning)
-constexpr int CU_THREADS = CU_WGS == 2 ? 320 : 192;   // warps 0-3: epilogue (even tiles), 4: TMA, 5: MMA, 6-9: epilogue of odd tiles
 
 __global__ void __launch_bounds__(CU_THREADS, 1)
 ffconv_umma_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ CUtensorMap mapW,
-                   const float* __restrict__ bias, const float* Xin, float* Xout, double* __restrict__ stats, int B,
-                   int Hp, int Wp, const float* __restrict__ res, __half* __restrict__ xr) {
+                   const __grid_constant__ CUtensorMap mapXin, const __grid_constant__ CUtensorMap mapXout,
+                   const float* __restrict__ bias, double* __restrict__ stats, int B, int Hp, int Wp,
+                   const float* __restrict__ res, __half* __restrict__ xr) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
+    float* sbias = reinterpret_cast<float*>(sm + CU_OFF_BIAS);
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + CU_OFF_BAR);
-    uint64_t* full = bars;                       // [STAGES]
-    uint64_t* empty = bars + CU_STAGES;          // [STAGES]
-    uint64_t* wfull = bars + 2 * CU_STAGES;
-    uint64_t* tfull = bars + 2 * CU_STAGES + 1;  // [2]
-    uint64_t* tempty = bars + 2 * CU_STAGES + 3; // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * CU_STAGES + 5);
+    uint64_t* full = bars;                        // [2]  Y halo tile landed
+    uint64_t* empty = bars + 2;                   // [2]  ... consumed by the MMAs
+    uint64_t* wfull = bars + 4;
+    uint64_t* tfull = bars + 5;                   // [2]  accumulator complete
+    uint64_t* tempty = bars + 7;                  // [2]  ... drained
+    uint64_t* xfull = bars + 9;                   // [3]  residual tile landed
+    uint64_t* xout = bars + 12;                   // [3]  result tile complete in smem (store may start)
+    uint64_t* xempty = bars + 15;                 // [3]  tile buffer free (store has read it, stats pass done)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int tiles_x = Wp / CU_TW, tiles_y = Hp / CU_TH;
@@ -62,14 +77,20 @@ ffconv_umma_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_consta
     const int tile_lo = (int)((long)blockIdx.x * ntiles / gridDim.x);
     const int tile_hi = (int)((long)(blockIdx.x + 1) * ntiles / gridDim.x);
 
+    if (tid < NF) sbias[tid] = bias[tid];
     if (warp == 5) tmem_alloc(tmem_slot, 128);
     if (tid == 128) {
-        for (int s = 0; s < CU_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&full[s], 1); mbar_init(&empty[s], 1);
+            mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4);
+        }
         mbar_init(wfull, 1);
-        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+        for (int s = 0; s < CU_XSTAGES; ++s) { mbar_init(&xfull[s], 1); mbar_init(&xout[s], 1); mbar_init(&xempty[s], 5); }
         mbar_fence_init();
         tma_prefetch_desc(&mapY);
         tma_prefetch_desc(&mapW);
+        tma_prefetch_desc(&mapXin);
+        tma_prefetch_desc(&mapXout);
     }
     tc_fence_before();
     __syncthreads();
@@ -88,7 +109,16 @@ ffconv_umma_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_consta
         for (int tile = tile_lo; tile < tile_hi; ++tile, ++it) {
             const int b = tile / per_img, r = tile - b * per_img;
             const int y0 = (r / tiles_x) * CU_TH, x0 = (r % tiles_x) * CU_TW;
-            const uint32_t s = it % CU_STAGES, ph = (it / CU_STAGES) & 1;
+            const uint32_t s = it & 1, ph = (it >> 1) & 1;
+            const uint32_t xs = it % CU_XSTAGES, xph = (it / CU_XSTAGES) & 1;
+            mbar_wait(&xempty[xs], xph ^ 1);
+            if (elect_one_sync()) {
+                uint8_t* xt = sm + CU_OFF_X + xs * CU_XSTAGE;
+                mbar_expect_tx(&xfull[xs], CU_XSTAGE);
+                tma_load_4d(xt, &mapXin, &xfull[xs], 0, x0, y0, b);
+                tma_load_4d(xt + CU_XHALF, &mapXin, &xfull[xs], 32, x0, y0, b);
+            }
+            __syncwarp();
             mbar_wait(&empty[s], ph ^ 1);
             if (elect_one_sync()) {
                 mbar_expect_tx(&full[s], CU_TILE_BYTES);
@@ -104,10 +134,13 @@ ffconv_umma_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_consta
         mbar_wait(wfull, 0);
         uint32_t it = 0;
         for (int tile = tile_lo; tile < tile_hi; ++tile, ++it) {
-            const uint32_t s = it % CU_STAGES, ph = (it / CU_STAGES) & 1;
+            const uint32_t s = it & 1, ph = (it >> 1) & 1;
             const uint32_t acc = it & 1, aph = (it >> 1) & 1;
+            M2T_CT(5);
             mbar_wait(&tempty[acc], aph ^ 1);
+            M2T_CT(6);
             mbar_wait(&full[s], ph);
+            M2T_CT(7);
             tc_fence_after();
             if (elect_one_sync()) {
                 const uint64_t da0 = umma_desc_at(tmpl_a, base + CU_OFF_A + s * CU_STAGE);
@@ -126,57 +159,135 @@ ffconv_umma_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_consta
             }
             __syncwarp();
         }
-    } else {
-        // Two epilogue warpgroups: wg 0 (warps 0-3) drains accumulator 0 = even tiles, wg 1 (warps 6-9) accumulator 1
-        // = odd tiles, each with its own staging tile and named barrier.  The residual rows of a tile are requested
-        // before its accumulator is complete, so up to 64 KB of loads per SM overlap the MMAs and the other group.
-        const int wg = warp >= 6 ? 1 : 0, quad = warp & 3;
-        const int t = quad * 32 + lane;                         // 0..127 inside the warpgroup = TMEM lane = tile pixel
-        float* Os = reinterpret_cast<float*>(sm + CU_OFF_O + wg * CU_O_BYTES);
-        float (*red)[2][NF] = reinterpret_cast<float (*)[2][NF]>(sm + CU_OFF_RED + wg * 4 * 2 * NF * 4);
+    } else if (warp == 6) {
+        // TMA store warp: sends each finished tile back and releases its buffer once the store has read it
         pdl_wait();
-        EpiStats st;
-        st.clear();
+        uint32_t it = 0;
+        for (int tile = tile_lo; tile < tile_hi; ++tile, ++it) {
+            const int b = tile / per_img, r = tile - b * per_img;
+            const int y0 = (r / tiles_x) * CU_TH, x0 = (r % tiles_x) * CU_TW;
+            const uint32_t xs = it % CU_XSTAGES, xph = (it / CU_XSTAGES) & 1;
+            mbar_wait(&xout[xs], xph);
+            if (elect_one_sync()) {
+                const uint8_t* xt = sm + CU_OFF_X + xs * CU_XSTAGE;
+                tma_store_4d(&mapXout, xt, 0, x0, y0, b);
+                tma_store_4d(&mapXout, xt + CU_XHALF, 32, x0, y0, b);
+                tma_store_commit();
+                tma_store_wait_read();
+                mbar_arrive(&xempty[xs]);
+            }
+            __syncwarp();
+        }
+        tma_store_wait_all();                      // a no-op for lanes that issued nothing
+    } else {
+        // Epilogue: thread t = TMEM lane = tile pixel t (row t of both half tiles)
+        const int t = warp * 32 + lane;
+        const uint32_t lanef = (uint32_t)(warp * 32) << 16;
+        const int sc = t & 63, shalf = t >> 6;                  // statistics pass: channel, half of the pixels
+        const uint32_t sc_off = (uint32_t)(sc >> 5) * CU_XHALF + (uint32_t)(sc & 3) * 4;
+        const uint32_t sc_chunk = (uint32_t)(sc & 31) >> 2;
+        pdl_wait();
+        float ssum = 0.f, ssq = 0.f;
         int cur_b = -1;
         uint32_t it = 0;
         for (int tile = tile_lo; tile < tile_hi; ++tile, ++it) {
-            if (CU_WGS == 2 && (int)(it & 1) != wg) continue;
             const int b = tile / per_img, r = tile - b * per_img;
             const int y0 = (r / tiles_x) * CU_TH, x0 = (r % tiles_x) * CU_TW;
             const uint32_t acc = it & 1, aph = (it >> 1) & 1;
-            float4 xi[16];
-            epilogue_load_residual<CU_TW>(t, Xin, b, y0, x0, Hp, Wp, xi);
-            if (b != cur_b) {                                  // image changed: publish the finished image's sums
-                if (cur_b >= 0) { if (wg == 0) epilogue_flush_stats<1>(red, t, st, stats, cur_b); else epilogue_flush_stats<2>(red, t, st, stats, cur_b); }
+            const uint32_t xs = it % CU_XSTAGES, xph = (it / CU_XSTAGES) & 1;
+            uint8_t* xt = sm + CU_OFF_X + xs * CU_XSTAGE;
+            const long pix = ((long)b * Hp + (y0 + (t >> 3))) * Wp + (x0 + (t & 7));
+            M2T_CT(0);
+            uint4 rv[16];                                       // last CFTM: this pixel's row of the head output
+            if (xr != nullptr) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) ldg256(res + pix * NF + 8 * j, rv[2 * j], rv[2 * j + 1]);
+            }
+            if (b != cur_b) {                                   // image changed: publish the finished image's sums
+                if (cur_b >= 0) {
+                    atomicAdd(&stats[((long)cur_b * NF + sc) * 2], (double)ssum);
+                    atomicAdd(&stats[((long)cur_b * NF + sc) * 2 + 1], (double)ssq);
+                    ssum = 0.f; ssq = 0.f;
+                }
                 cur_b = b;
             }
+            M2T_CT(1);
             mbar_wait(&tfull[acc], aph);
+            mbar_wait(&xfull[xs], xph);
             tc_fence_after();
+            M2T_CT(2);
 #pragma unroll
-            for (int c0 = 0; c0 < NF; c0 += 32) {
+            for (int hh = 0; hh < 2; ++hh) {
                 uint32_t rr[32];
-                tmem_ld32(tmem_base + acc * NF + c0 + ((uint32_t)(quad * 32) << 16), rr);
+                tmem_ld32(tmem_base + acc * NF + hh * 32 + lanef, rr);
                 tmem_ld_wait();
+                uint8_t* row = xt + hh * CU_XHALF + t * 128;
+                uint32_t hx[16];                               // fp16(res + x) of these 32 channels (last CFTM)
 #pragma unroll
-                for (int i = 0; i < 32; ++i) Os[t * EPI_LD + c0 + i] = __uint_as_float(rr[i]);
+                for (int j = 0; j < 8; ++j) {
+                    float4* cell = reinterpret_cast<float4*>(row + ((j ^ (t & 7)) << 4));
+                    const float4 xv = *cell;
+                    const float4 bv = *reinterpret_cast<const float4*>(sbias + hh * 32 + 4 * j);
+                    float4 v;
+                    v.x = __uint_as_float(rr[4 * j]) + bv.x + xv.x;
+                    v.y = __uint_as_float(rr[4 * j + 1]) + bv.y + xv.y;
+                    v.z = __uint_as_float(rr[4 * j + 2]) + bv.z + xv.z;
+                    v.w = __uint_as_float(rr[4 * j + 3]) + bv.w + xv.w;
+                    *cell = v;
+                    if (xr != nullptr) {
+                        const uint4 rq = rv[hh * 8 + j];
+                        const __half2 h0 = __floats2half2_rn(v.x + __uint_as_float(rq.x), v.y + __uint_as_float(rq.y));
+                        const __half2 h1 = __floats2half2_rn(v.z + __uint_as_float(rq.z), v.w + __uint_as_float(rq.w));
+                        hx[2 * j] = *reinterpret_cast<const uint32_t*>(&h0);
+                        hx[2 * j + 1] = *reinterpret_cast<const uint32_t*>(&h1);
+                    }
+                }
+                if (xr != nullptr) {   // fp16(res + x), the tail's first GEMM operand (ref :70): 64 B per half
+                    __half* xp = xr + pix * NF + hh * 32;
+                    stg256(xp, make_uint4(hx[0], hx[1], hx[2], hx[3]), make_uint4(hx[4], hx[5], hx[6], hx[7]));
+                    stg256(xp + 16, make_uint4(hx[8], hx[9], hx[10], hx[11]), make_uint4(hx[12], hx[13], hx[14], hx[15]));
+                }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);          // accumulator drained: MMA may reuse it
-            if (wg == 0) epi_sync<1>(); else epi_sync<2>();    // all 128 staged rows visible
-            epilogue_apply<CU_TW>(Os, t, xi, bias, Xout, st, b, y0, x0, Hp, Wp, res, xr);
-            if (wg == 0) epi_sync<1>(); else epi_sync<2>();    // Os free for the next tile
+            fence_proxy_async();                               // the tile is read next by the TMA store
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (t == 0) mbar_arrive(&xout[xs]);
+            M2T_CT(3);
+            // statistics of the finished tile: thread = (channel, half of the pixels), conflict-free row reads
+#pragma unroll 8
+            for (int p = shalf * 64; p < shalf * 64 + 64; ++p) {
+                const float v = *reinterpret_cast<const float*>(xt + sc_off + p * 128 + ((sc_chunk ^ (uint32_t)(p & 7)) << 4));
+                ssum += v;
+                ssq = fmaf(v, v, ssq);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&xempty[xs]);
+            M2T_CT(4);
         }
-        if (cur_b >= 0) { if (wg == 0) epilogue_flush_stats<1>(red, t, st, stats, cur_b); else epilogue_flush_stats<2>(red, t, st, stats, cur_b); }
+        if (cur_b >= 0) {
+            atomicAdd(&stats[((long)cur_b * NF + sc) * 2], (double)ssum);
+            atomicAdd(&stats[((long)cur_b * NF + sc) * 2 + 1], (double)ssq);
+        }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 5) tmem_dealloc(tmem_base, 128);
 }
 
+#ifdef M2T_TIMING
+int read_conv_timing(long long* host64) {
+    M2T_CUDA(cudaMemcpyFromSymbol(host64, g_conv_dbg, sizeof(long long) * 64));
+    return M2T_OK;
+}
+#else
+int read_conv_timing(long long* host64) { memset(host64, 0, sizeof(long long) * 64); return M2T_OK; }
+#endif
+
 int launch_ffconv_umma(const __half* Y, const __half* Wpk, const float* bias, const float* Xin, float* Xout,
                        double* stats, const Geom& g, cudaStream_t s, const float* res, __half* xr) {
-    CUtensorMap mapY, mapW;
+    CUtensorMap mapY, mapW, mapXin, mapXout;
     {
         const uint64_t dims[4] = {NF, (uint64_t)g.Wp, (uint64_t)g.Hp, (uint64_t)g.B};
         const uint64_t str[4] = {2, NF * 2, (uint64_t)g.Wp * NF * 2, (uint64_t)g.Hp * g.Wp * NF * 2};
@@ -188,11 +299,18 @@ int launch_ffconv_umma(const __half* Y, const __half* Wpk, const float* bias, co
         const uint32_t box[2] = {NF, NF};
         M2T_TRY(make_tensor_map(&mapW, Wpk, 2, 2, dims, str, box, 3));
     }
+    {   // fp32 residual stream: 32-channel (128-byte) boxes of 16 x 8 pixels
+        const uint64_t dims[4] = {NF, (uint64_t)g.Wp, (uint64_t)g.Hp, (uint64_t)g.B};
+        const uint64_t str[4] = {4, NF * 4, (uint64_t)g.Wp * NF * 4, (uint64_t)g.Hp * g.Wp * NF * 4};
+        const uint32_t box[4] = {32, CU_TW, CU_TH, 1};
+        M2T_TRY(make_tensor_map(&mapXin, Xin, 4, 4, dims, str, box, 3));
+        M2T_TRY(make_tensor_map(&mapXout, Xout, 4, 4, dims, str, box, 3));
+    }
     M2T_ENSURE_SMEM(ffconv_umma_kernel, CU_SMEM);
     const int ntiles = g.B * (g.Hp / CU_TH) * (g.Wp / CU_TW);
     const int grid = ntiles < device_sm_count() ? ntiles : device_sm_count();
-    M2T_CUDA(launch_pdl(ffconv_umma_kernel, dim3(grid), dim3(CU_THREADS), CU_SMEM, s, mapY, mapW, bias, Xin, Xout, stats, g.B, g.Hp,
-                        g.Wp, res, xr));
+    M2T_CUDA(launch_pdl(ffconv_umma_kernel, dim3(grid), dim3(CU_THREADS), CU_SMEM, s, mapY, mapW, mapXin, mapXout, bias, stats,
+                        g.B, g.Hp, g.Wp, res, xr));
     return M2T_OK;
 }
 
