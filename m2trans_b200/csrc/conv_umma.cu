@@ -111,18 +111,20 @@ ffconv_umma_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_consta
             const int y0 = (r / tiles_x) * CU_TH, x0 = (r % tiles_x) * CU_TW;
             const uint32_t s = it & 1, ph = (it >> 1) & 1;
             const uint32_t xs = it % CU_XSTAGES, xph = (it / CU_XSTAGES) & 1;
+            // Y first: its stage frees early (the MMAs run ahead), the residual stage only when the epilogue of
+            // tile it-3 is done, and that wait must not hold back the tile the MMAs need next
+            mbar_wait(&empty[s], ph ^ 1);
+            if (elect_one_sync()) {
+                mbar_expect_tx(&full[s], CU_TILE_BYTES);
+                tma_load_4d(sm + CU_OFF_A + s * CU_STAGE, &mapY, &full[s], 0, x0 - 1, y0 - 1, b);
+            }
+            __syncwarp();
             mbar_wait(&xempty[xs], xph ^ 1);
             if (elect_one_sync()) {
                 uint8_t* xt = sm + CU_OFF_X + xs * CU_XSTAGE;
                 mbar_expect_tx(&xfull[xs], CU_XSTAGE);
                 tma_load_4d(xt, &mapXin, &xfull[xs], 0, x0, y0, b);
                 tma_load_4d(xt + CU_XHALF, &mapXin, &xfull[xs], 32, x0, y0, b);
-            }
-            __syncwarp();
-            mbar_wait(&empty[s], ph ^ 1);
-            if (elect_one_sync()) {
-                mbar_expect_tx(&full[s], CU_TILE_BYTES);
-                tma_load_4d(sm + CU_OFF_A + s * CU_STAGE, &mapY, &full[s], 0, x0 - 1, y0 - 1, b);
             }
             __syncwarp();
         }
