@@ -11,8 +11,9 @@ Printed JSON line (rank 0):
   value      whole-job output MP/s with inputs resident in HBM (CUDA events, max over ranks)
   e2e        same metric through the public nn.Module call with HOST buffers: pinned H2D of the LR
              batch + forward + D2H of the SR batch inside the timed region
-  roofline   the dominant kernel (CFTM 3x3 feed-forward conv) timed alone with CUDA events, against
-             MEASURED_PEAKS.json; roofline_forward = whole forward vs. the sustained tensor peak
+  roofline   the dominant kernel (CFTM 3x3 feed-forward conv, HBM-bound: 640 algorithmic B/px) timed with CUDA
+             events over 10 back-to-back launches, against MEASURED_PEAKS.json; roofline_tensor = the same
+             kernel against the tensor peak; roofline_forward = whole forward vs. the sustained tensor peak
   cpu_baseline  the CPU oracle (a torch fp32 port of the reference forward) on the host cores
 Multi-GPU: images are independent, so every rank runs the same per-GPU batch (weak scaling) with no
 collective on the data path; torch.distributed (NCCL) is used only for the barrier and the max-reduce
@@ -41,6 +42,8 @@ WORKLOADS = {
 }
 FLOP_PER_PX = {2: 1299328, 3: 1357568, 4: 1471872}     # algorithmic FLOPs per padded LR px
 FFCONV_FLOP_PER_PX = 2 * 64 * 64 * 9                    # 73 728
+FFCONV_BYTES_PER_PX = 128 + 256 + 256                   # fp16 Y in, fp32 X in, fp32 X out
+FFCONV_DRAM_BYTES_CFG2 = 114.6e6                        # ncu: 101.5 MB read + 13.1 MB written per launch at cfg2
 
 
 def peaks():
@@ -53,34 +56,65 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons during the timed region (B200_PROFILING.md recipe).  Polls NVML every 2 ms (the
+    timed region of the default run lasts ~40 ms; one nvidia-smi call takes longer than that) and falls back to
+    nvidia-smi when the NVML bindings are missing."""
+
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index: int):
         super().__init__(daemon=True)
-        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+        self.index, self.sm, self.mx, self.reasons, self._stop_evt = index, [], [], set(), threading.Event()
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
 
-    def run(self):
+    def _poll_nvml(self):
+        n = self.nvml
+        self.sm.append(int(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+        self.mx.append(int(n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)))
+        try:
+            r = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+        except Exception:
+            r = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+        bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+        self.reasons.update(k for k, v in bits.items() if r & v)
+
+    def _poll_smi(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                             capture_output=True, text=True, timeout=5).stdout.strip()
+        r = [c.strip() for c in out.split(",")]
+        if len(r) >= 6 and r[0].isdigit():
+            self.sm.append(int(r[0]))
+            self.mx.append(int(r[1]))
+            self.reasons.update(self.NAMES[i] for i in range(4) if r[2 + i].lower().startswith("active"))
+
+    def run(self):
         while not self._stop_evt.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                if self.nvml is not None:
+                    self._poll_nvml()
+                else:
+                    self._poll_smi()
             except Exception:
                 pass
-            self._stop_evt.wait(0.2)
+            self._stop_evt.wait(0.002 if self.nvml is not None else 0.2)
 
     def stop(self):
         self._stop_evt.set()
         self.join(timeout=6)
-        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
-        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(self.rows)}
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                "reasons": sorted(self.reasons), "samples": len(sm), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def model_args(scale):
@@ -232,25 +266,30 @@ def run_ours(args):
     hp, wp = (H + 31) // 32 * 32, (W + 31) // 32 * 32
     P = B * hp * wp
     pk = peaks()
-    Y = torch.randn(B, hp, wp, 64, device=dev).half()
-    Xin = torch.randn(B, hp, wp, 64, device=dev)
-    Xout = torch.empty_like(Xin)
+    sets = []
+    for _ in range(2):
+        sets.append((torch.randn(B, hp, wp, 64, device=dev).half(), torch.randn(B, hp, wp, 64, device=dev)))
     ffw = torch.randn(9, 64, 64, device=dev).half() * 0.05
     ffb = torch.randn(64, device=dev)
     stats = torch.zeros(B, 64, 2, dtype=torch.float64, device=dev)
     st = torch.cuda.current_stream(dev).cuda_stream
-    kms = []
-    for i in range(3 + 10):
-        flush.zero_()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        _lib.check(lib.m2t_stage_ffconv(0, Y.data_ptr(), ffw.data_ptr(), ffb.data_ptr(), Xin.data_ptr(), Xout.data_ptr(),
+
+    def ffconv(i):      # in place on the fp32 stream, as inside the forward (Xin == Xout from the second CFTM on)
+        Yk, Xk = sets[i % 2]
+        _lib.check(lib.m2t_stage_ffconv(0, Yk.data_ptr(), ffw.data_ptr(), ffb.data_ptr(), Xk.data_ptr(), Xk.data_ptr(),
                                         stats.data_ptr(), B, hp, wp, st), "m2t_stage_ffconv")
-        b.record()
-        torch.cuda.synchronize()
-        if i >= 3:
-            kms.append(a.elapsed_time(b))
-    k_ms = sum(kms) / len(kms)
+    for i in range(4):
+        ffconv(i)
+    torch.cuda.synchronize()
+    n_k = 10
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda._sleep(20_000_000)            # let the host queue all launches first
+    a.record()
+    for i in range(n_k):
+        ffconv(i)
+    b.record()
+    torch.cuda.synchronize()
+    k_ms = a.elapsed_time(b) / n_k
     k_tflops = FFCONV_FLOP_PER_PX * P / (k_ms * 1e-3) / 1e12
     fwd_tflops = FLOP_PER_PX[scale] * P / (ms * 1e-3) / 1e12
 
@@ -273,9 +312,17 @@ def run_ours(args):
                     "d2h_bytes_per_step": B * 3 * H * scale * W * scale * 4, "ms_per_step": e2e_ms},
             "gpu_launches": launches,
             "step_ms": {"min": step_sorted[0], "median": step_sorted[len(step_sorted) // 2], "max": step_sorted[-1]},
-            "roofline": {"kernel": "ffconv (CFTM 3x3 feed-forward conv + residual + norm stats)", "bound": "tensor",
-                         "achieved": k_tflops, "peak": pk["tflops_burst"], "unit": "TFLOP/s", "frac": k_tflops / pk["tflops_burst"],
-                         "traffic": None, "peak_source": pk["source"], "ms_per_launch": k_ms},
+            "roofline": {"kernel": "ffconv_umma (CFTM 3x3 feed-forward conv + residual + norm stats)", "bound": "hbm",
+                         "achieved": FFCONV_BYTES_PER_PX * P / (k_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                         "frac": FFCONV_BYTES_PER_PX * P / (k_ms * 1e-3) / 1e9 / pk["hbm_gbs"],
+                         "traffic": FFCONV_DRAM_BYTES_CFG2 if args.workload == "cfg2" else None,
+                         "traffic_note": "dram read+write of one launch, ncu --set full, profiles/r01_ncu_final_summary.txt; the "
+                                         "64 MiB of output mostly stays in L2 until the next kernel evicts it",
+                         "algorithmic_bytes_per_launch": FFCONV_BYTES_PER_PX * P,
+                         "peak_source": pk["source"], "ms_per_launch": k_ms,
+                         "timing": "10 launches back to back between one CUDA-event pair, two rotating buffer sets (336 MB > L2)"},
+            "roofline_tensor": {"kernel": "ffconv_umma", "bound": "tensor", "achieved": k_tflops, "peak": pk["tflops_burst"],
+                                "unit": "TFLOP/s", "frac": k_tflops / pk["tflops_burst"]},
             "roofline_forward": {"bound": "tensor", "achieved": fwd_tflops, "peak": pk["tflops_sustained"], "unit": "TFLOP/s",
                                  "frac": fwd_tflops / pk["tflops_sustained"], "peak_source": pk["source"]},
             "wall_s_timed_region": t_wall,

@@ -171,6 +171,12 @@ int m2t_transblock_forward(const float* d_x, float* d_y, const float* const* d_p
 int m2t_probe_umma(const void* d_a_image, uint32_t a_bytes, const void* d_b_image, uint32_t b_bytes,
                    uint64_t a_desc, uint64_t b_desc, uint32_t a_step, uint32_t b_step, int k_steps,
                    uint32_t idesc, int n_cols, float* d_out, void* stream);
+/* m2t_debug_profile_forward: runs m2t_forward once eagerly with a CUDA event after every launch (programmatic
+ * dependent launch off, so launches do not overlap), synchronises the stream and writes a per-kernel table
+ * (time, share, launches, mangled name) into `text` (HOST buffer of `cap` bytes).  Development aid: unlike ncu it
+ * sees the kernels with the caches as the previous kernel left them. */
+int m2t_debug_profile_forward(const m2t_plan* plan, const void* d_packed, const float* d_x, float* d_y,
+                              void* d_workspace, void* stream, char* text, size_t cap);
 /* m2t_debug_attn_timing: host64 holds 6 x 64 values.  Record 5: CTA 0 of the last tcgen05 ff-conv launch, per tile i < 8:
  * epilogue [8i+0..4] tile start, residual loads issued, accumulator ready, staged, stored; MMA warp [8i+5..7] before
  * / after the accumulator-free wait and after the halo-tile wait.  Record 4: CTA 0 of the last fused-tail launch, per tile i < 8 at

@@ -352,6 +352,26 @@ class M2Trans(nn.Module):
             plan["graph"].replay()
             return plan["ys"].clone()
 
+    @torch.no_grad()
+    def profile_forward(self, x) -> str:
+        """Development aid: one eager forward with a CUDA event after every launch; returns a per-kernel table
+        (m2t_debug_profile_forward).  Unlike ncu it times the kernels with the caches as their predecessor left them."""
+        _require_cuda_f32(x, "M2Trans.profile_forward")
+        lib = _lib.load()
+        x = x.contiguous()
+        b, _, h, w = x.shape
+        device = x.device
+        with torch.cuda.device(device), self._m2t.lock:
+            st = self._device_state(device)
+            packed = self._packed_weights(st, device)
+            plan = self._plan(st, b, h, w, device)
+            y = torch.empty((b, 3, h * self.scale, w * self.scale), dtype=torch.float32, device=device)
+            buf = C.create_string_buffer(1 << 14)
+            _lib.check(lib.m2t_debug_profile_forward(plan["handle"], _aligned_ptr(packed), x.data_ptr(), y.data_ptr(),
+                                                     _aligned_ptr(plan["ws"]), _stream_ptr(device), buf, len(buf)),
+                       "m2t_debug_profile_forward")
+        return buf.value.decode()
+
     def engine_tensor(self, x_shape, name: str) -> torch.Tensor:
         """Test hook: view of an internal NHWC tensor ('res', 'x' fp32; 'y' fp16) of the plan that
         served the last forward of shape `x_shape` on the current device."""

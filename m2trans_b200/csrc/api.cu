@@ -6,6 +6,8 @@
 
 #include <new>
 
+#include <vector>
+
 #include "common.cuh"
 
 namespace m2t {
@@ -51,6 +53,18 @@ bool pdl_in_graph() {
         cached = (e && e[0] == '0') ? 0 : 1;
     }
     return cached == 1;
+}
+
+// ---- per-launch profiling of one eager forward (development aid) ------------------------------------------
+struct ProfRec { std::vector<cudaEvent_t> ev; std::vector<const void*> fn; };
+static thread_local ProfRec* g_prof = nullptr;
+bool prof_active() { return g_prof != nullptr; }
+void prof_mark(cudaStream_t s, const void* kernel) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, s);
+    g_prof->ev.push_back(e);
+    g_prof->fn.push_back(kernel);
 }
 
 int check_device() {
@@ -345,6 +359,41 @@ int m2t_forward(const m2t_plan* plan, const void* d_packed, const float* d_x, fl
         M2T_TRY(run_tail(var, plan->cfg.scale, L, W, XR + b0 * img_stride, d_y, nb, b0, g, plan->cfg.rgb_range,
                          ws + plan->o_t1, s));
     }
+    return M2T_OK;
+}
+
+int m2t_debug_profile_forward(const m2t_plan* plan, const void* d_packed, const float* d_x, float* d_y,
+                              void* d_workspace, void* stream, char* text, size_t cap) {
+    if (!text || cap < 64) { set_error("profile_forward: text buffer too small"); return M2T_E_ARG; }
+    ProfRec rec;
+    cudaStream_t s = (cudaStream_t)stream;
+    g_prof = &rec;
+    prof_mark(s, nullptr);                                   // start marker
+    const int rc = m2t_forward(plan, d_packed, d_x, d_y, d_workspace, stream);
+    g_prof = nullptr;
+    if (rc != M2T_OK) return rc;
+    M2T_CUDA(cudaStreamSynchronize(s));
+    struct Agg { const void* fn; int n; float ms; };
+    std::vector<Agg> agg;
+    float total = 0.f;
+    for (size_t i = 1; i < rec.ev.size(); ++i) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, rec.ev[i - 1], rec.ev[i]);
+        total += ms;
+        bool found = false;
+        for (auto& a : agg) if (a.fn == rec.fn[i]) { a.n++; a.ms += ms; found = true; break; }
+        if (!found) agg.push_back({rec.fn[i], 1, ms});
+    }
+    for (cudaEvent_t e : rec.ev) cudaEventDestroy(e);
+    size_t off = 0;
+    for (const auto& a : agg) {
+        const char* name = "?";
+        cudaFuncGetName(&name, a.fn);
+        const int w = snprintf(text + off, cap - off, "%9.1f us %5.1f%%  x%-3d %.60s\n", a.ms * 1e3f, 100.f * a.ms / total, a.n, name);
+        if (w < 0 || (size_t)w >= cap - off) break;
+        off += (size_t)w;
+    }
+    snprintf(text + off, cap - off, "total %.1f us (eager, one event per launch, no PDL overlap, warm L2)\n", total * 1e3f);
     return M2T_OK;
 }
 

@@ -190,7 +190,9 @@ branch_post_kernel(int branch, const __half* __restrict__ O, const float* __rest
 // the same 32-byte segments, so it never touches the fp32 stream.
 // One thread per (pixel, 16-channel branch group): 64-byte loads, 32-byte stores.  The InstanceNorm statistics
 // (mean, rstd; biased variance, ref :127) are finalised here from the fp64 sums the producer accumulated, so no
-// separate finalise pass is needed on this path.  A CTA covers 64 consecutive pixels of one image.
+// separate finalise pass is needed on this path.  Persistent CTAs, each with a contiguous range of 64-pixel chunks:
+// the fp64 finalise (divide + square root on 64 threads, ~1.5 K cycles) runs once per CTA and image instead of once
+// per 64 pixels, where it cost as much as the data movement.
 __global__ void __launch_bounds__(256)
 branch_prep_all_kernel(const float* __restrict__ X, const double* __restrict__ stats, __half* __restrict__ T1,
                        __half* __restrict__ H2, __half* __restrict__ H3, __half* __restrict__ H4, int B, int Hp,
@@ -198,62 +200,66 @@ branch_prep_all_kernel(const float* __restrict__ X, const double* __restrict__ s
     __shared__ float smu[NF], srs[NF];
     pdl_wait();
     const int t = threadIdx.x;
-    // The producer (head or the previous ff conv) wrote X front to back just before this kernel: walk it back to
-    // front so the most recently written part is read while it is still in L2.
-    const long pix = (long)(gridDim.x - 1 - blockIdx.x) * 64 + (t >> 2);
     const int npix = Hp * Wp;
-    const int b = (int)(pix / npix);
-    const int r = (int)(pix - (long)b * npix);
-    const int y = r / Wp, x = r - y * Wp;
-    if (t < NF) {
-        const double inv = 1.0 / (double)npix;
-        const double m = stats[((long)b * NF + t) * 2] * inv;
-        double var = stats[((long)b * NF + t) * 2 + 1] * inv - m * m;
-        if (var < 0.0) var = 0.0;
-        smu[t] = (float)m;
-        srs[t] = (float)(1.0 / sqrt(var + (double)IN_EPS));
-    }
-    __syncthreads();
+    const int nchunks = (int)((long)B * npix / 64);
+    const int k_lo = (int)((long)blockIdx.x * nchunks / gridDim.x), k_hi = (int)((long)(blockIdx.x + 1) * nchunks / gridDim.x);
     const int branch = t & 3;
     const float sc = branch == 0 ? 1.f : 0.5f;
-    const float4* xp = reinterpret_cast<const float4*>(X + pix * NF + NB * branch);
-    float4 xv[4];
-    {   // 64 contiguous bytes per thread as two 256-bit loads
-        uint4 a[4];
+    int cur_b = -1;
+    for (int k = k_lo; k < k_hi; ++k) {
+        // The producer (head or the previous ff conv) wrote X front to back just before this kernel: walk it back to
+        // front so the most recently written part is read while it is still in L2.
+        const long pix = (long)(nchunks - 1 - k) * 64 + (t >> 2);
+        const int b = (int)(pix / npix);
+        const int r = (int)(pix - (long)b * npix);
+        const int y = r / Wp, x = r - y * Wp;
+        const float4* xp = reinterpret_cast<const float4*>(X + pix * NF + NB * branch);
+        uint4 a[4];                        // 64 contiguous bytes per thread as two 256-bit loads
         ldg256(xp, a[0], a[1]);
         ldg256(xp + 2, a[2], a[3]);
+        if (b != cur_b) {                  // uniform over the CTA: a chunk never straddles two images
+            __syncthreads();
+            if (t < NF) {
+                const double inv = 1.0 / (double)npix;
+                const double m = stats[((long)b * NF + t) * 2] * inv;
+                double var = stats[((long)b * NF + t) * 2 + 1] * inv - m * m;
+                if (var < 0.0) var = 0.0;
+                smu[t] = (float)m;
+                srs[t] = (float)(1.0 / sqrt(var + (double)IN_EPS));
+            }
+            __syncthreads();
+            cur_b = b;
+        }
+        uint4 o[2];
+        __half2* oh = reinterpret_cast<__half2*>(o);
 #pragma unroll
-        for (int v = 0; v < 4; ++v) xv[v] = make_float4(__uint_as_float(a[v].x), __uint_as_float(a[v].y), __uint_as_float(a[v].z), __uint_as_float(a[v].w));
+        for (int v = 0; v < 4; ++v) {
+            const int c = NB * branch + 4 * v;
+            const float x0 = __uint_as_float(a[v].x), x1 = __uint_as_float(a[v].y), x2 = __uint_as_float(a[v].z), x3 = __uint_as_float(a[v].w);
+            oh[2 * v] = __floats2half2_rn((x0 - smu[c]) * srs[c] * sc, (x1 - smu[c + 1]) * srs[c + 1] * sc);
+            oh[2 * v + 1] = __floats2half2_rn((x2 - smu[c + 2]) * srs[c + 2] * sc, (x3 - smu[c + 3]) * srs[c + 3] * sc);
+        }
+        __half* dst;
+        if (branch == 0) {
+            dst = T1 + pix * NB;
+        } else if (branch == 1) {
+            const long lp = ((long)b * (Hp >> 1) + (y >> 1)) * (Wp >> 1) + (x >> 1);
+            dst = H2 + lp * 64 + ((y & 1) * 2 + (x & 1)) * NB;
+        } else {
+            const long lp = ((long)b * (Hp >> 2) + (y >> 2)) * (Wp >> 2) + (x >> 2);
+            dst = (branch == 2 ? H3 : H4) + lp * 256 + ((y & 3) * 4 + (x & 3)) * NB;
+        }
+        stg256(dst, o[0], o[1]);
     }
-    uint4 o[2];
-    __half2* oh = reinterpret_cast<__half2*>(o);
-#pragma unroll
-    for (int v = 0; v < 4; ++v) {
-        const int c = NB * branch + 4 * v;
-        oh[2 * v] = __floats2half2_rn((xv[v].x - smu[c]) * srs[c] * sc, (xv[v].y - smu[c + 1]) * srs[c + 1] * sc);
-        oh[2 * v + 1] = __floats2half2_rn((xv[v].z - smu[c + 2]) * srs[c + 2] * sc, (xv[v].w - smu[c + 3]) * srs[c + 3] * sc);
-    }
-    __half* dst;
-    if (branch == 0) {
-        dst = T1 + pix * NB;
-    } else if (branch == 1) {
-        const long lp = ((long)b * (Hp >> 1) + (y >> 1)) * (Wp >> 1) + (x >> 1);
-        dst = H2 + lp * 64 + ((y & 1) * 2 + (x & 1)) * NB;
-    } else {
-        const long lp = ((long)b * (Hp >> 2) + (y >> 2)) * (Wp >> 2) + (x >> 2);
-        dst = (branch == 2 ? H3 : H4) + lp * 256 + ((y & 3) * 4 + (x & 3)) * NB;
-    }
-    stg256(dst, o[0], o[1]);
-    // multi-wave grid: let the next kernel's CTAs in only when this CTA is done, or they would take the SMs that
-    // this grid's later waves still need
     pdl_trigger();
 }
 
 int launch_branch_prep_all(const float* X, const double* stats, __half* T1, __half* H2, __half* H3, __half* H4,
                            const Geom& g, cudaStream_t s) {
-    const long npx = (long)g.B * g.Hp * g.Wp;
-    M2T_CUDA(launch_pdl(branch_prep_all_kernel, dim3((unsigned)(npx / 64)), dim3(256), 0, s, X, stats, T1, H2, H3, H4, g.B,
-                        g.Hp, g.Wp));
+    const long nchunks = (long)g.B * g.Hp * g.Wp / 64;
+    const long slots = 8L * device_sm_count();          // 256 threads, 32 registers: 8 CTAs per SM
+    const unsigned grid = (unsigned)(nchunks < slots ? nchunks : slots);
+    M2T_CUDA(launch_pdl(branch_prep_all_kernel, dim3(grid), dim3(256), 0, s, X, stats, T1, H2, H3, H4, g.B, g.Hp, g.Wp));
     return M2T_OK;
 }
 

@@ -62,6 +62,8 @@ int check_device();   // M2T_OK on an sm_100 device, M2T_E_DEVICE otherwise (api
 // Rule: no thread reads activations or writes ANY global memory before pdl_wait().
 bool pdl_enabled();
 bool pdl_in_graph();
+bool prof_active();                                   // m2t_debug_profile_forward is running on this thread
+void prof_mark(cudaStream_t s, const void* kernel);   // records an event after a launch
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
                               Args&&... args) {
@@ -71,14 +73,16 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
-    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cfg.numAttrs = (pdl_enabled() && !prof_active()) ? 1 : 0;
     // Measured on B200 (cfg2, final kernels): graph 1.745 ms, graph + PDL 1.718 ms, eager + PDL 1.725 ms (device
     // time with the host running ahead).  An earlier measurement had PDL hurting inside graphs; that was caused by
     // multi-wave kernels triggering at their START (dependents stole SM slots), fixed by triggering at the end.
     // M2T_GRAPH_PDL=0 drops the attribute during capture for A/B runs.
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     if (cfg.numAttrs && !pdl_in_graph() && cudaStreamIsCapturing(s, &cap) == cudaSuccess && cap != cudaStreamCaptureStatusNone) cfg.numAttrs = 0;
-    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+    if (prof_active()) prof_mark(s, reinterpret_cast<const void*>(kernel));
+    return e;
 }
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
