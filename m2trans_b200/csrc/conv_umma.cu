@@ -189,7 +189,9 @@ ffconv_umma_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_consta
         const uint32_t sc_off = (uint32_t)(sc >> 5) * CU_XHALF + (uint32_t)(sc & 3) * 4;
         const uint32_t sc_chunk = (uint32_t)(sc & 31) >> 2;
         pdl_wait();
-        float ssum = 0.f, ssq = 0.f;
+        // per-tile partial sums in fp32 (fixed order), accumulated across tiles in fp64: the statistics then do not depend
+        // on which tiles a CTA happens to own, i.e. on the batch size (frames stay bit-independent of their batch)
+        double dsum = 0.0, dsq = 0.0;
         int cur_b = -1;
         uint32_t it = 0;
         for (int tile = tile_lo; tile < tile_hi; ++tile, ++it) {
@@ -207,9 +209,9 @@ ffconv_umma_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_consta
             }
             if (b != cur_b) {                                   // image changed: publish the finished image's sums
                 if (cur_b >= 0) {
-                    atomicAdd(&stats[((long)cur_b * NF + sc) * 2], (double)ssum);
-                    atomicAdd(&stats[((long)cur_b * NF + sc) * 2 + 1], (double)ssq);
-                    ssum = 0.f; ssq = 0.f;
+                    atomicAdd(&stats[((long)cur_b * NF + sc) * 2], dsum);
+                    atomicAdd(&stats[((long)cur_b * NF + sc) * 2 + 1], dsq);
+                    dsum = 0.0; dsq = 0.0;
                 }
                 cur_b = b;
             }
@@ -258,19 +260,22 @@ ffconv_umma_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_consta
             if (t == 0) mbar_arrive(&xout[xs]);
             M2T_CT(3);
             // statistics of the finished tile: thread = (channel, half of the pixels), conflict-free row reads
+            float ssum = 0.f, ssq = 0.f;
 #pragma unroll 8
             for (int p = shalf * 64; p < shalf * 64 + 64; ++p) {
                 const float v = *reinterpret_cast<const float*>(xt + sc_off + p * 128 + ((sc_chunk ^ (uint32_t)(p & 7)) << 4));
                 ssum += v;
                 ssq = fmaf(v, v, ssq);
             }
+            dsum += (double)ssum;
+            dsq += (double)ssq;
             __syncwarp();
             if (lane == 0) mbar_arrive(&xempty[xs]);
             M2T_CT(4);
         }
         if (cur_b >= 0) {
-            atomicAdd(&stats[((long)cur_b * NF + sc) * 2], (double)ssum);
-            atomicAdd(&stats[((long)cur_b * NF + sc) * 2 + 1], (double)ssq);
+            atomicAdd(&stats[((long)cur_b * NF + sc) * 2], dsum);
+            atomicAdd(&stats[((long)cur_b * NF + sc) * 2 + 1], dsq);
         }
     }
     tc_fence_before();

@@ -107,12 +107,13 @@ def test_batch_consistency_and_determinism():
     x = synthetic_input(3, 40, 56, seed=5).cuda()
     y = model(x)
     y2 = model(x)
-    # The InstanceNorm sums are fp64 atomics: their order changes the statistics in the last ulp, which can
-    # flip the fp16 rounding of a few intermediate values; the visible effect stays ~1e-4 on the [0,1] output.
-    assert (y - y2).abs().max().item() <= 3e-4
+    # The InstanceNorm sums are per-tile fp32 partials (fixed order) accumulated in fp64: neither the atomics' order nor
+    # the batch composition changes the fp32 statistics, so repeated runs and batch-of-one runs agree bit for bit
+    # (an fp64 sum landing within 1e-16 of an fp32 rounding boundary would be the exception).
+    assert (y - y2).abs().max().item() <= 1e-6
     for i in range(3):
         yi = model(x[i:i + 1])
-        assert (yi[0] - y[i]).abs().max().item() <= 3e-4
+        assert (yi[0] - y[i]).abs().max().item() <= 1e-6
 
 
 def test_full_size_cfg2_properties():
@@ -194,3 +195,27 @@ def test_fused_tail_equals_two_kernel_tail(scale, shape):
     d = float((y_f - y_u).abs().max())
     print(f"x{scale} {shape}: fused vs unfused tail max-abs {d:.2e}")
     assert d <= 2e-6
+
+
+@pytest.mark.parametrize("name,scale,shape,probe", [("cfg3", 3, (32, 3, 200, 266), 31), ("cfg4", 4, (64, 3, 270, 480), 63)])
+def test_full_size_cfg3_cfg4_properties(name, scale, shape, probe):
+    """BASELINE configs[2], [3] at their full sizes (ragged frames: 200x266 -> 224x288, 270x480 -> 288x480).
+    Size-independent properties: exact output shape (the crop), range, finiteness; frames are independent, so the
+    last frame of the batch equals the same frame run alone; and that frame against the CPU oracle."""
+    from oracle import m2trans_oracle as O
+    from m2trans_b200.synthetic import synthetic_input, synthetic_state_dict
+    b, _, h, w = shape
+    model = _model(scale, 0)
+    x = synthetic_input(b, h, w, seed=33)
+    y = model(x.cuda())
+    assert tuple(y.shape) == (b, 3, h * scale, w * scale) and y.dtype == torch.float32
+    assert torch.isfinite(y).all() and float(y.min()) >= 0.0 and float(y.max()) <= 1.0
+    y_one = model(x[probe:probe + 1].cuda())
+    d = float((y_one[0] - y[probe]).abs().max())
+    ref = O.forward(synthetic_state_dict(scale, 0), x[probe:probe + 1])
+    p, m = _metrics(y[probe:probe + 1].cpu(), ref)
+    print(f"{name} frame {probe}: alone-vs-batch max-abs {d:.2e}; vs oracle PSNR {p:.1f} dB, max-abs {m:.2e}")
+    assert d <= 1e-6
+    assert p >= PSNR_MIN and m <= MAXABS_MAX
+    del y, y_one
+    torch.cuda.empty_cache()
