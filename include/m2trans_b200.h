@@ -111,6 +111,17 @@ size_t m2t_workspace_offset(const m2t_plan* plan, const char* name);
  *   d_workspace         m2t_workspace_bytes(plan) bytes, 256-byte aligned          */
 int m2t_forward(const m2t_plan* plan, const void* d_packed, const float* d_x, float* d_y,
                 void* d_workspace, void* stream);
+/* The same forward in up to three parts (bit mask): M2T_PHASE_HEAD reads d_x (frame pad + head conv), M2T_PHASE_BODY
+ * runs the CFTM blocks on the workspace only, M2T_PHASE_TAIL writes d_y.  The parts of one forward must run in this
+ * order on one stream with the same workspace.  Lets a host capture the pointer-independent BODY in a CUDA graph and
+ * launch HEAD / TAIL directly on the caller's tensors (no staging copies).  d_x / d_y may be NULL when their phase is
+ * not selected. */
+#define M2T_PHASE_HEAD 1u
+#define M2T_PHASE_BODY 2u
+#define M2T_PHASE_TAIL 4u
+#define M2T_PHASE_ALL  7u
+int m2t_forward_phases(const m2t_plan* plan, const void* d_packed, const float* d_x, float* d_y,
+                       void* d_workspace, void* stream, uint32_t phases);
 
 /* ---- per-stage entry points (unit tests, ncu) ------------------------------------------
  * The same kernels m2t_forward launches, on the engine's native NHWC tensors.

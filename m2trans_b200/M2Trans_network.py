@@ -336,21 +336,25 @@ class M2Trans(nn.Module):
                 y = torch.empty(out_shape, dtype=torch.float32, device=device)
                 launch(x, y)
                 return y
-            # CUDA-graph replay of the same launch sequence (m2t_forward never synchronises or allocates): the
-            # graph is captured once per (plan, packed weights) on static buffers; one forward is then a single
-            # graph launch plus the copies in and out of those buffers.
+            # CUDA-graph replay (m2t_forward never synchronises or allocates).  Only the CFTM blocks are captured: they
+            # touch nothing but the plan's workspace and the packed weights, so the graph is independent of the caller's
+            # tensors.  The head conv (1 launch, reads x) and the tail (2-3 launches per image chunk, writes y) are
+            # launched directly on the caller's tensors around the replay: no staging copy in, no 50 MB clone out.
+            def phases(mask, xin, yout):
+                _lib.check(lib.m2t_forward_phases(plan["handle"], _aligned_ptr(packed), xin, yout,
+                                                  _aligned_ptr(plan["ws"]), _stream_ptr(device), mask), "m2t_forward_phases")
+
+            y = torch.empty(out_shape, dtype=torch.float32, device=device)
             if plan.get("graph_key") != packed.data_ptr():
-                xs = torch.empty_like(x)
-                ys = torch.empty(out_shape, dtype=torch.float32, device=device)
-                xs.copy_(x)
-                launch(xs, ys)                               # eager warm-up: one-time attribute / driver lookups
+                launch(x, y)                                 # eager warm-up: one-time attribute / driver lookups
                 graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(graph):
-                    launch(xs, ys)
-                plan.update(graph=graph, graph_key=packed.data_ptr(), xs=xs, ys=ys)
-            plan["xs"].copy_(x)
+                    phases(_lib.PHASE_BODY, None, None)
+                plan.update(graph=graph, graph_key=packed.data_ptr())
+            phases(_lib.PHASE_HEAD, x.data_ptr(), None)
             plan["graph"].replay()
-            return plan["ys"].clone()
+            phases(_lib.PHASE_TAIL, None, y.data_ptr())
+            return y
 
     @torch.no_grad()
     def profile_forward(self, x) -> str:

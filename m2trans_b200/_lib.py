@@ -21,6 +21,7 @@ VAR_SIMT_TAIL = 1 << 2
 VAR_SIMT_ATTN = 1 << 3
 VAR_SIMT_ALL = 0xF
 VAR_UNFUSED_TAIL = 1 << 4
+PHASE_HEAD, PHASE_BODY, PHASE_TAIL, PHASE_ALL = 1, 2, 4, 7
 
 
 class M2TError(RuntimeError):
@@ -53,6 +54,7 @@ SIGNATURES = {
     "m2t_plan_num_launches": (_i, [_vp]),
     "m2t_workspace_offset": (_sz, [_vp, C.c_char_p]),
     "m2t_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "m2t_forward_phases": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _u32]),
     "m2t_stage_head": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "m2t_stage_stats_finalize": (_i, [_vp, _vp, _i, _i, _vp]),
     "m2t_stage_branch_prep": (_i, [_i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),

@@ -289,7 +289,14 @@ static int run_tail(uint32_t variant, int scale, const PackedLayout& L, const ui
 
 int m2t_forward(const m2t_plan* plan, const void* d_packed, const float* d_x, float* d_y, void* d_workspace,
                 void* stream) {
-    if (!plan || !d_packed || !d_x || !d_y || !d_workspace) { set_error("forward: null pointer"); return M2T_E_ARG; }
+    return m2t_forward_phases(plan, d_packed, d_x, d_y, d_workspace, stream, M2T_PHASE_ALL);
+}
+
+int m2t_forward_phases(const m2t_plan* plan, const void* d_packed, const float* d_x, float* d_y, void* d_workspace,
+                       void* stream, uint32_t phases) {
+    if (!plan || !d_packed || !d_workspace) { set_error("forward: null pointer"); return M2T_E_ARG; }
+    if (((phases & M2T_PHASE_HEAD) && !d_x) || ((phases & M2T_PHASE_TAIL) && !d_y)) { set_error("forward: null pointer"); return M2T_E_ARG; }
+    if (!(phases & M2T_PHASE_ALL)) { set_error("forward: no phase selected"); return M2T_E_ARG; }
     if (((uintptr_t)d_workspace & 255) || ((uintptr_t)d_packed & 255)) {
         set_error("forward: workspace / packed weights must be 256-byte aligned");
         return M2T_E_ARG;
@@ -313,14 +320,16 @@ int m2t_forward(const m2t_plan* plan, const void* d_packed, const float* d_x, fl
     const size_t stat_stride = (size_t)g.B * NF * 2;
     const int npix = g.Hp * g.Wp;
 
-    M2T_CUDA(cudaMemsetAsync(stats, 0, (size_t)(plan->cfg.n_blocks + 1) * stat_stride * sizeof(double), s));
-    M2T_TRY(launch_head(d_x, reinterpret_cast<const float*>(W + L.head_w), reinterpret_cast<const float*>(W + L.head_b),
-                        res, stats, g, s));
+    if (phases & M2T_PHASE_HEAD) {
+        M2T_CUDA(cudaMemsetAsync(stats, 0, (size_t)(plan->cfg.n_blocks + 1) * stat_stride * sizeof(double), s));
+        M2T_TRY(launch_head(d_x, reinterpret_cast<const float*>(W + L.head_w), reinterpret_cast<const float*>(W + L.head_b),
+                            res, stats, g, s));
+    }
     const float* Xin = res;
     // Default path: Haar-folded weights + branch glue fused into the attention epilogue (11 launches per CFTM).
     // The CUDA-core attention variant keeps the explicit prep / post kernels (18 launches per CFTM).
     const bool fused = !(var & M2T_VAR_SIMT_ATTN);
-    for (int i = 0; i < plan->cfg.n_blocks; ++i) {
+    for (int i = 0; (phases & M2T_PHASE_BODY) && i < plan->cfg.n_blocks; ++i) {
         if (!fused) M2T_TRY(launch_stats_finalize(stats + i * stat_stride, munorm, g.B, npix, s));
         if (fused) {
             // t_1 = n_1 and n_k/2 (k = 2..4) in their consumers' space-to-depth layouts, one pass over X (ref :135-137)
@@ -354,7 +363,7 @@ int m2t_forward(const m2t_plan* plan, const void* d_packed, const float* d_x, fl
         Xin = X;
     }
     const size_t img_stride = (size_t)npix * NF;
-    for (int b0 = 0; b0 < g.B; b0 += plan->tail_chunk) {
+    for (int b0 = 0; (phases & M2T_PHASE_TAIL) && b0 < g.B; b0 += plan->tail_chunk) {
         const int nb = g.B - b0 < plan->tail_chunk ? g.B - b0 : plan->tail_chunk;
         M2T_TRY(run_tail(var, plan->cfg.scale, L, W, XR + b0 * img_stride, d_y, nb, b0, g, plan->cfg.rgb_range,
                          ws + plan->o_t1, s));
