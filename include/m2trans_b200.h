@@ -50,6 +50,14 @@ extern "C" {
 #define M2T_VAR_SIMT_ATTN (1u << 3)  /* attention on CUDA cores instead of tcgen05     */
 #define M2T_VAR_SIMT_ALL  0xFu
 #define M2T_VAR_UNFUSED_TAIL (1u << 4) /* x2/x4: tail_up + border + tail_out instead of the fused last stage */
+/* Precise mode.  (1) The fp16 rounding residual of t_k travels beside t_k and is added back where
+ * y_k = attention + t_k is formed (two more 32-byte segments per pixel and branch).  (2) The ff conv uses
+ * split-precision weights: fp16 weight + fp16 residual * 2^11 in extra accumulator columns, 32 output channels per CTA.
+ * Together they remove the two largest error terms of the fp16 operand format (emulated at x3 on a speckle frame:
+ * max-abs 2.7e-3 -> 1.7e-3) for ~10 % of the forward time.  Default: on for x2 / x3, whose single-stage tail leaves
+ * less margin under the 2e-3 bar, off for x4.  These bits force it either way. */
+#define M2T_VAR_PRECISE_ON   (1u << 5)
+#define M2T_VAR_PRECISE_OFF  (1u << 6)
 
 typedef struct m2t_plan m2t_plan;
 

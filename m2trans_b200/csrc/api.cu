@@ -90,7 +90,7 @@ struct m2t_plan {
     PackedLayout L;
     int tail_chunk;            // images per tail pass
     // workspace byte offsets
-    size_t o_res, o_x, o_y, o_z, o_qkv, o_o, o_h3, o_h4, o_stats, o_munorm, o_xr, o_t1, ws_bytes;
+    size_t o_res, o_x, o_y, o_z, o_qkv, o_o, o_h3, o_h4, o_lo[4], o_stats, o_munorm, o_xr, o_t1, ws_bytes;
     int n_launches;
 };
 
@@ -149,6 +149,7 @@ size_t m2t_packed_offset(int scale, int n_blocks, const char* name) {
     }
     if (sscanf(name, "body.%d.%31s", &i, what) == 2 && i >= 0 && i < n_blocks) {
         if (!strcmp(what, "ffw")) return L.blk[i].ffw;
+        if (!strcmp(what, "ffw2")) return L.blk[i].ffw2;
         if (!strcmp(what, "ffb")) return L.blk[i].ffb;
     }
     return (size_t)-1;
@@ -198,6 +199,7 @@ int m2t_plan_create(const m2t_cfg* cfg, m2t_plan** out) {
     p->o_o = take(P * NB * 2);
     p->o_h3 = take(P * NB * 2);
     p->o_h4 = take(P * NB * 2);
+    for (int a = 0; a < 4; ++a) p->o_lo[a] = take(P * NB * 2);   // fp16 rounding residuals of t_1..t_4 (residual path)
     p->o_stats = take((size_t)(cfg->n_blocks + 1) * g.B * NF * 2 * sizeof(double));
     p->o_munorm = take((size_t)g.B * NF * sizeof(float2));
     // tail scratch: process images in chunks of at most ~2 GiB of intermediates
@@ -329,12 +331,17 @@ int m2t_forward_phases(const m2t_plan* plan, const void* d_packed, const float* 
     // Default path: Haar-folded weights + branch glue fused into the attention epilogue (11 launches per CFTM).
     // The CUDA-core attention variant keeps the explicit prep / post kernels (18 launches per CFTM).
     const bool fused = !(var & M2T_VAR_SIMT_ATTN);
+    // precise mode (M2T_VAR_PRECISE_*): t_k residuals on the residual path + split-precision ff-conv weights;
+    // default on for x2 / x3, off for x4
+    const bool precise = (var & M2T_VAR_PRECISE_ON) || (!(var & M2T_VAR_PRECISE_OFF) && plan->cfg.scale != 4);
     for (int i = 0; (phases & M2T_PHASE_BODY) && i < plan->cfg.n_blocks; ++i) {
         if (!fused) M2T_TRY(launch_stats_finalize(stats + i * stat_stride, munorm, g.B, npix, s));
         if (fused) {
             // t_1 = n_1 and n_k/2 (k = 2..4) in their consumers' space-to-depth layouts, one pass over X (ref :135-137)
             __half* Tb[4] = {Z, O, reinterpret_cast<__half*>(ws + plan->o_h3), reinterpret_cast<__half*>(ws + plan->o_h4)};
-            M2T_TRY(launch_branch_prep_all(Xin, stats + i * stat_stride, Tb[0], Tb[1], Tb[2], Tb[3], g, s));
+            __half* Lb[4];
+            for (int a = 0; a < 4; ++a) Lb[a] = precise ? reinterpret_cast<__half*>(ws + plan->o_lo[a]) : nullptr;
+            M2T_TRY(launch_branch_prep_all(Xin, stats + i * stat_stride, Tb[0], Lb[0], Tb[1], Tb[2], Tb[3], g, s));
             for (int a = 0; a < 4; ++a) {
                 const int lv = branch_level(a), C = branch_ch(a);
                 const int h = g.Hp >> lv, w = g.Wp >> lv;
@@ -342,6 +349,7 @@ int m2t_forward_phases(const m2t_plan* plan, const void* d_packed, const float* 
                 M2T_TRY(run_qkv(var, Tb[a], reinterpret_cast<const __half*>(W + A.wqkv_f), QKV, g.B * h * w, C, s));
                 AttnFuse fz;
                 fz.T = Tb[a]; fz.Y = Y; fz.Tnext = a < 3 ? Tb[a + 1] : nullptr;
+                fz.Tlo = Lb[a]; fz.Tnext_lo = a < 3 ? Lb[a + 1] : nullptr;
                 fz.branch = a; fz.Hp = g.Hp; fz.Wp = g.Wp;
                 M2T_TRY(launch_attn_umma(C, QKV, reinterpret_cast<const __half*>(W + A.relx), nullptr, g.B, h, w, s, &fz));
             }
@@ -357,6 +365,11 @@ int m2t_forward_phases(const m2t_plan* plan, const void* d_packed, const float* 
             M2T_TRY(launch_branch_post(lv, a, O, Xin, munorm, Y, g, s));
         }
         const bool last = i == plan->cfg.n_blocks - 1;      // the last block also emits fp16(res + x) for the tail
+        if (precise && !(var & M2T_VAR_SIMT_CONV))
+            M2T_TRY(launch_ffconv_umma_w2(Y, reinterpret_cast<const __half*>(W + L.blk[i].ffw2),
+                                          reinterpret_cast<const float*>(W + L.blk[i].ffb), Xin, X,
+                                          stats + (i + 1) * stat_stride, g, s, last ? res : nullptr, last ? XR : nullptr));
+        else
         M2T_TRY(run_ffconv(var, Y, reinterpret_cast<const __half*>(W + L.blk[i].ffw),
                            reinterpret_cast<const float*>(W + L.blk[i].ffb), Xin, X, stats + (i + 1) * stat_stride, g, s,
                            last ? res : nullptr, last ? XR : nullptr));

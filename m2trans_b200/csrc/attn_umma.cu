@@ -110,7 +110,9 @@ __device__ long long g_attn_dbg[4 * 64];   // one 64-entry record per branch (fu
 #define M2T_T(slot) do { } while (0)
 #endif
 
-template <int C, bool FUSE>
+// LO: the residual path uses t_k = T + Tlo (AttnFuse; precise mode).  A template parameter, not a run-time test: the
+// fast mode must not carry the extra registers and adds.
+template <int C, bool FUSE, bool LO>
 __global__ void __launch_bounds__(AtCfg<C, FUSE>::THREADS, AtCfg<C, FUSE>::MIN_CTAS)
 attn_umma_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapKV,
                  const __grid_constant__ CUtensorMap mapR, const __grid_constant__ CUtensorMap mapT,
@@ -403,14 +405,15 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
                 const int br = fz.branch;
                 const bool has_next = fz.Tnext != nullptr;
                 const int lvn = br == 0 ? 1 : 2, Sn = 1 << lvn, Cn = NB * Sn * Sn;
-                auto tnext_ptr = [&](int s) -> __half* {
+                auto tnext_off = [&](int s) -> long {
                     const int fy = ly * S + s / S, fx = lx * S + s % S;
                     const int sn = (fy & (Sn - 1)) * Sn + (fx & (Sn - 1));
-                    return fz.Tnext + ((((long)wc.b * (fz.Hp >> lvn)) + (fy >> lvn)) * (fz.Wp >> lvn) + (fx >> lvn)) * Cn + sn * NB;
+                    return ((((long)wc.b * (fz.Hp >> lvn)) + (fy >> lvn)) * (fz.Wp >> lvn) + (fx >> lvn)) * Cn + sn * NB;
                 };
+                const long trow_off = (((long)wc.b * h + ly) * w + lx) * C;
                 uint4 tkr[CF::TSTAGE ? 1 : 2 * SPB];            // register copy of the t_k row (C <= 64)
                 if constexpr (!CF::TSTAGE) {
-                    const __half* trow = fz.T + (((long)wc.b * h + ly) * w + lx) * C;
+                    const __half* trow = fz.T + trow_off;
 #pragma unroll
                     for (int j = 0; j < SPB; ++j) ldg256(trow + j * 16, tkr[2 * j], tkr[2 * j + 1]);
                 }
@@ -419,11 +422,19 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
                 uint4 hcur[2 * JN], hnxt[2 * JN];               // n_{k+1}/2 segments of the current / next block
                 auto load_h = [&](int nb, uint4* dst) {
 #pragma unroll
+                    for (int j = 0; j < JN; ++j) ldg256(fz.Tnext + tnext_off(nb * SPB + j0 + j), dst[2 * j], dst[2 * j + 1]);
+                };
+                // rounding residuals of t_k (AttnFuse::Tlo): the residual add below uses t_k = T + Tlo
+                uint4 lcur[2 * JN], lnxt[2 * JN];
+                constexpr bool has_lo = LO;
+                auto load_l = [&](int nb, uint4* dst) {
+#pragma unroll
                     for (int j = 0; j < JN; ++j) {
-                        const __half* hp = tnext_ptr(nb * SPB + j0 + j);
-                        ldg256(hp, dst[2 * j], dst[2 * j + 1]);
+                        if (has_lo) ldg256(fz.Tlo + trow_off + (nb * SPB + j0 + j) * NB, dst[2 * j], dst[2 * j + 1]);
+                        else { dst[2 * j] = make_uint4(0u, 0u, 0u, 0u); dst[2 * j + 1] = make_uint4(0u, 0u, 0u, 0u); }
                     }
                 };
+                load_l(0, lcur);
                 if (has_next) load_h(0, hcur);
                 M2T_T(3);
                 mbar_wait(o_full, it & 1);
@@ -431,7 +442,10 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
                 M2T_T(4);
 #pragma unroll 1
                 for (int nb = 0; nb < NBLK; ++nb) {
-                    if (has_next && nb + 1 < NBLK) load_h(nb + 1, hnxt);
+                    if (nb + 1 < NBLK) {
+                        load_l(nb + 1, lnxt);
+                        if (has_next) load_h(nb + 1, hnxt);
+                    }
                     const uint8_t* tst = nullptr;
                     if constexpr (CF::TSTAGE) {
                         mbar_wait(&t_full[gt & 1], (gt >> 1) & 1);
@@ -456,9 +470,14 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
                             const long pix = ((long)wc.b * fz.Hp + fy) * fz.Wp + fx;
                             float yv[NB];
                             const __half2* th = reinterpret_cast<const __half2*>(tk);
+                            const __half2* tl = reinterpret_cast<const __half2*>(&lcur[2 * jj]);
 #pragma unroll
                             for (int e = 0; e < 8; ++e) {
-                                const float2 tf = __half22float2(th[e]);
+                                float2 tf = __half22float2(th[e]);
+                                if constexpr (LO) {
+                                    const float2 lf = __half22float2(tl[e]);
+                                    tf.x += lf.x; tf.y += lf.y;
+                                }
                                 yv[2 * e] = fmaf(__uint_as_float(r[2 * e]), inv, tf.x);
                                 yv[2 * e + 1] = fmaf(__uint_as_float(r[2 * e + 1]), inv, tf.y);
                             }
@@ -469,16 +488,21 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
                             __half* yp = fz.Y + pix * NF + NB * br;
                             stg256(yp, yo[0], yo[1]);
                             if (has_next) {
-                                uint4 to[2];
+                                uint4 to[2], tol[2];
                                 __half2* tnh = reinterpret_cast<__half2*>(to);
+                                __half2* tnl = reinterpret_cast<__half2*>(tol);
                                 const __half2* hh = reinterpret_cast<const __half2*>(&hcur[2 * jj]);
 #pragma unroll
                                 for (int e = 0; e < 8; ++e) {
                                     const float2 hf = __half22float2(hh[e]);
-                                    tnh[e] = __floats2half2_rn(fmaf(0.5f, yv[2 * e], hf.x), fmaf(0.5f, yv[2 * e + 1], hf.y));
+                                    const float t0 = fmaf(0.5f, yv[2 * e], hf.x), t1 = fmaf(0.5f, yv[2 * e + 1], hf.y);
+                                    tnh[e] = __floats2half2_rn(t0, t1);
+                                    const float2 tr = __half22float2(tnh[e]);
+                                    tnl[e] = __floats2half2_rn(t0 - tr.x, t1 - tr.y);
                                 }
-                                __half* tp = tnext_ptr(s);
-                                stg256(tp, to[0], to[1]);
+                                const long toff = tnext_off(s);
+                                stg256(fz.Tnext + toff, to[0], to[1]);
+                                if (has_lo) stg256(fz.Tnext_lo + toff, tol[0], tol[1]);
                             }
                         }
                     }
@@ -487,9 +511,9 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
                         if (lane == 0) mbar_arrive(&t_empty[gt & 1]);
                         ++gt;
                     }
-                    if (has_next && nb + 1 < NBLK) {
+                    if (nb + 1 < NBLK) {
 #pragma unroll
-                        for (int j = 0; j < 2 * JN; ++j) hcur[j] = hnxt[j];
+                        for (int j = 0; j < 2 * JN; ++j) { lcur[j] = lnxt[j]; if (has_next) hcur[j] = hnxt[j]; }
                     }
                 }
             } else {
@@ -530,7 +554,7 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
     if (warp == 5) tmem_dealloc(tmem_base, CF::TM_COLS);
 }
 
-template <int C, bool FUSE>
+template <int C, bool FUSE, bool LO>
 static int launch_attn_umma_cf(const __half* QKV, const __half* relx, __half* O, int B, int h, int w, cudaStream_t s,
                                const AttnFuse& fz) {
     using CF = AtCfg<C, FUSE>;
@@ -562,16 +586,17 @@ static int launch_attn_umma_cf(const __half* QKV, const __half* relx, __half* O,
     const int npairs = (nwin + 1) / 2;
     const int cap = device_sm_count() * CF::MIN_CTAS;
     const int grid = npairs < cap ? npairs : cap;
-    M2T_ENSURE_SMEM((attn_umma_kernel<C, FUSE>), CF::SMEM);
-    M2T_CUDA(launch_pdl(attn_umma_kernel<C, FUSE>, dim3(grid), dim3(CF::THREADS), CF::SMEM, s, mapQ, mapKV, mapR, mapT, O, h, w, nwin, fz));
+    M2T_ENSURE_SMEM((attn_umma_kernel<C, FUSE, LO>), CF::SMEM);
+    M2T_CUDA(launch_pdl(attn_umma_kernel<C, FUSE, LO>, dim3(grid), dim3(CF::THREADS), CF::SMEM, s, mapQ, mapKV, mapR, mapT, O, h, w, nwin, fz));
     return M2T_OK;
 }
 
 template <int C>
 static int launch_attn_umma_c(const __half* QKV, const __half* relx, __half* O, int B, int h, int w, cudaStream_t s,
                               const AttnFuse* fuse) {
-    if (fuse != nullptr) return launch_attn_umma_cf<C, true>(QKV, relx, O, B, h, w, s, *fuse);
-    return launch_attn_umma_cf<C, false>(QKV, relx, O, B, h, w, s, AttnFuse{});
+    if (fuse != nullptr && fuse->Tlo != nullptr) return launch_attn_umma_cf<C, true, true>(QKV, relx, O, B, h, w, s, *fuse);
+    if (fuse != nullptr) return launch_attn_umma_cf<C, true, false>(QKV, relx, O, B, h, w, s, *fuse);
+    return launch_attn_umma_cf<C, false, false>(QKV, relx, O, B, h, w, s, AttnFuse{});
 }
 
 int launch_attn_umma(int C, const __half* QKV, const __half* relx, __half* O, int B, int h, int w, cudaStream_t s,

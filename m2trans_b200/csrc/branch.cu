@@ -195,8 +195,8 @@ branch_post_kernel(int branch, const __half* __restrict__ O, const float* __rest
 // per 64 pixels, where it cost as much as the data movement.
 __global__ void __launch_bounds__(256)
 branch_prep_all_kernel(const float* __restrict__ X, const double* __restrict__ stats, __half* __restrict__ T1,
-                       __half* __restrict__ H2, __half* __restrict__ H3, __half* __restrict__ H4, int B, int Hp,
-                       int Wp) {
+                       __half* __restrict__ T1lo, __half* __restrict__ H2, __half* __restrict__ H3,
+                       __half* __restrict__ H4, int B, int Hp, int Wp) {
     __shared__ float smu[NF], srs[NF];
     pdl_wait();
     const int t = threadIdx.x;
@@ -230,18 +230,24 @@ branch_prep_all_kernel(const float* __restrict__ X, const double* __restrict__ s
             __syncthreads();
             cur_b = b;
         }
-        uint4 o[2];
+        uint4 o[2], ol[2];                 // fp16 value and (branch 1 only) its rounding residual
         __half2* oh = reinterpret_cast<__half2*>(o);
+        __half2* olh = reinterpret_cast<__half2*>(ol);
 #pragma unroll
         for (int v = 0; v < 4; ++v) {
             const int c = NB * branch + 4 * v;
-            const float x0 = __uint_as_float(a[v].x), x1 = __uint_as_float(a[v].y), x2 = __uint_as_float(a[v].z), x3 = __uint_as_float(a[v].w);
-            oh[2 * v] = __floats2half2_rn((x0 - smu[c]) * srs[c] * sc, (x1 - smu[c + 1]) * srs[c + 1] * sc);
-            oh[2 * v + 1] = __floats2half2_rn((x2 - smu[c + 2]) * srs[c + 2] * sc, (x3 - smu[c + 3]) * srs[c + 3] * sc);
+            const float n0 = (__uint_as_float(a[v].x) - smu[c]) * srs[c] * sc, n1 = (__uint_as_float(a[v].y) - smu[c + 1]) * srs[c + 1] * sc;
+            const float n2 = (__uint_as_float(a[v].z) - smu[c + 2]) * srs[c + 2] * sc, n3 = (__uint_as_float(a[v].w) - smu[c + 3]) * srs[c + 3] * sc;
+            oh[2 * v] = __floats2half2_rn(n0, n1);
+            oh[2 * v + 1] = __floats2half2_rn(n2, n3);
+            const float2 h01 = __half22float2(oh[2 * v]), h23 = __half22float2(oh[2 * v + 1]);
+            olh[2 * v] = __floats2half2_rn(n0 - h01.x, n1 - h01.y);
+            olh[2 * v + 1] = __floats2half2_rn(n2 - h23.x, n3 - h23.y);
         }
         __half* dst;
         if (branch == 0) {
             dst = T1 + pix * NB;
+            if (T1lo != nullptr) stg256(T1lo + pix * NB, ol[0], ol[1]);
         } else if (branch == 1) {
             const long lp = ((long)b * (Hp >> 1) + (y >> 1)) * (Wp >> 1) + (x >> 1);
             dst = H2 + lp * 64 + ((y & 1) * 2 + (x & 1)) * NB;
@@ -254,12 +260,12 @@ branch_prep_all_kernel(const float* __restrict__ X, const double* __restrict__ s
     pdl_trigger();
 }
 
-int launch_branch_prep_all(const float* X, const double* stats, __half* T1, __half* H2, __half* H3, __half* H4,
-                           const Geom& g, cudaStream_t s) {
+int launch_branch_prep_all(const float* X, const double* stats, __half* T1, __half* T1lo, __half* H2, __half* H3,
+                           __half* H4, const Geom& g, cudaStream_t s) {
     const long nchunks = (long)g.B * g.Hp * g.Wp / 64;
     const long slots = 8L * device_sm_count();          // 256 threads, 32 registers: 8 CTAs per SM
     const unsigned grid = (unsigned)(nchunks < slots ? nchunks : slots);
-    M2T_CUDA(launch_pdl(branch_prep_all_kernel, dim3(grid), dim3(256), 0, s, X, stats, T1, H2, H3, H4, g.B, g.Hp, g.Wp));
+    M2T_CUDA(launch_pdl(branch_prep_all_kernel, dim3(grid), dim3(256), 0, s, X, stats, T1, T1lo, H2, H3, H4, g.B, g.Hp, g.Wp));
     return M2T_OK;
 }
 

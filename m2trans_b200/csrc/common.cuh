@@ -114,6 +114,7 @@ struct AttnW {
 struct BlockW {
     AttnW attn[4];
     size_t ffw;    // fp16 [9][64 out][64 in]
+    size_t ffw2;   // fp16 [2 halves][9][64 rows][64 in]: rows 0..31 hi, 32..63 residual * 2^11 (split-precision conv)
     size_t ffb;    // fp32 [64]
 };
 struct PackedLayout {
@@ -173,10 +174,14 @@ struct AttnFuse {
     const __half* T;        // this branch's input t_k, space-to-depth fp16 [B,h,w,C]
     __half* Y;              // cat[y1..y4] fp16 NHWC [B,Hp,Wp,64]
     __half* Tnext;          // next branch's space-to-depth tensor holding n_{k+1}/2, or nullptr after branch 4
+    // t_k = T + Tlo: the fp16 rounding residual travels beside t_k for the RESIDUAL path (y_k = attention + t_k); the
+    // qkv GEMM reads T alone.  Rounding t_k before that add was the largest single contributor to the output error.
+    const __half* Tlo;      // same layout as T
+    __half* Tnext_lo;       // same layout as Tnext, written here
     int branch;             // 0..3
     int Hp, Wp;
 };
-int launch_branch_prep_all(const float* X, const double* stats, __half* T1, __half* H2, __half* H3, __half* H4,
+int launch_branch_prep_all(const float* X, const double* stats, __half* T1, __half* T1lo, __half* H2, __half* H3, __half* H4,
                            const Geom& g, cudaStream_t s);
 int launch_attn_umma(int C, const __half* QKV, const __half* relx, __half* O, int B, int h, int w,
                      cudaStream_t s, const AttnFuse* fuse = nullptr);
@@ -195,6 +200,10 @@ int launch_ffconv_simt(const __half* Y, const __half* Wp, const float* bias, con
 int launch_ffconv_umma(const __half* Y, const __half* Wp, const float* bias, const float* Xin, float* Xout,
                        double* stats, const Geom& g, cudaStream_t s, const float* res = nullptr,
                        __half* xr = nullptr);
+// split-precision weights (BlockW::ffw2): every CTA computes 32 output channels with hi and residual weight rows
+int launch_ffconv_umma_w2(const __half* Y, const __half* Wp2, const float* bias, const float* Xin, float* Xout,
+                          double* stats, const Geom& g, cudaStream_t s, const float* res = nullptr,
+                          __half* xr = nullptr);
 
 // tail_simt.cu
 //   tail_up : A fp16 [B,h,w,64] -> out fp16 [B, r h + 2 pad, r w + 2 pad, 64] (interior only; pad = 0 or 1)

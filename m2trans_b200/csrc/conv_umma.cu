@@ -1,6 +1,6 @@
 // tcgen05 implicit-GEMM form of CFTM.feed_forward + residual (ref M2Trans_network.py:124-126, :164):
 //   Xout[p][o] = sum_{tap,c} Y[p + tap][c] * W[tap][o][c] + bias[o] + Xin[p][o]        (zero padding)
-// One output tile = 16 rows x 8 pixels (M = 128), N = 64 output channels, K = 9 taps x 64 channels.
+// One output tile = 16 rows x 8 pixels (M = 128), N = 64 accumulator columns, K = 9 taps x 64 channels.
 //
 // No im2col: TMA loads ONE 18 x 10 pixel halo tile of Y (fp16 NHWC, 128 B per pixel = one 128-byte swizzle
 // row; out-of-frame pixels arrive as zeros = the conv's zero padding).  The A operand of tap (dy,dx) is the
@@ -8,15 +8,22 @@
 // 8-row groups are 10 rows apart (SBO = 1280 B): the 128-byte swizzle phase follows the absolute
 // shared-memory address, so shifted descriptors read exactly what TMA wrote (tests/test_probes.py pins this).
 // 36 MMAs (M=128, N=64, K=16) accumulate one tile in TMEM; two accumulators let the epilogue of tile i
-// overlap the MMAs of tile i+1.  The 9 x 64 x 64 weights stay resident in shared memory (72 KB).
+// overlap the MMAs of tile i+1.  The 9 x 64 x 64 weight rows stay resident in shared memory (72 KB).
 //
 // The fp32 residual stream moves by TMA in BOTH directions.  The first version loaded the residual rows with LDG and
 // stored the result with STG from the epilogue threads: with one epilogue warp per SM sub-partition the per-SM
 // load/store queue, not HBM, set the pace (measured: 7 K cycles per tile, the tensor pipe idle 70 % of the time, DRAM at
-// half its bandwidth).  Now the 128 x 64 fp32 tile of Xin lands in shared memory as two 128-byte-swizzled half tiles
+// half its bandwidth).  Now the fp32 tile of Xin lands in shared memory as 128-byte-swizzled half tiles of 32 channels
 // (3-stage ring), thread = pixel = TMEM lane adds accumulator + bias IN PLACE (conflict-free 16-byte accesses thanks
 // to the swizzle), and a dedicated warp sends the tile back with a TMA store.  The InstanceNorm partial sums are a
 // second pass over the finished tile in shared memory with thread = channel.
+//
+// Two weight formats (template parameter W2):
+//   W2 = false  the 64 accumulator columns are the 64 output channels, fp16 weights [9][64][64]
+//   W2 = true   split-precision weights (BlockW::ffw2): a CTA owns 32 output channels; accumulator columns 0..31 use
+//               the fp16 weights, columns 32..63 their rounding residuals * 2^11, and the epilogue adds
+//               hi + residual * 2^-11.  fp16 weight rounding was the largest error term left after the residual-path
+//               fix (emulated: 4.9e-4 max / 9e-5 rms at x3); the tensor pipe had the room (29 % busy).
 //
 // Warp roles (224 threads): warps 0-3 epilogue, warp 4 TMA loads, warp 5 MMA issuer, warp 6 TMA stores.
 #include "common.cuh"
@@ -32,14 +39,20 @@ constexpr uint32_t CU_STAGE = 23 * 1024;                              // 1024-al
 constexpr int CU_STAGES = 2;                                          // Y halo tiles (the MMAs run ahead of the epilogue)
 constexpr int CU_XSTAGES = 3;                                         // fp32 residual tiles
 constexpr uint32_t CU_XHALF = 128 * 128;                              // 128 pixels x 32 channels x 4 B
-constexpr uint32_t CU_XSTAGE = 2 * CU_XHALF;
 constexpr uint32_t CU_W_BYTES = 9 * NF * 128;                         // 73728
 constexpr uint32_t CU_OFF_A = CU_W_BYTES;
 constexpr uint32_t CU_OFF_X = CU_OFF_A + CU_STAGES * CU_STAGE;
-constexpr uint32_t CU_OFF_BIAS = CU_OFF_X + CU_XSTAGES * CU_XSTAGE;
-constexpr uint32_t CU_OFF_BAR = CU_OFF_BIAS + NF * 4;
-constexpr uint32_t CU_SMEM = 1024 + CU_OFF_BAR + 256;
 constexpr int CU_THREADS = 224;
+
+template <bool W2>
+struct CuCfg {
+    static constexpr int NCH = W2 ? 32 : 64;                          // output channels per CTA
+    static constexpr int NHALF = NCH / 32;                            // 32-channel half tiles per residual tile
+    static constexpr uint32_t XSTAGE = NHALF * CU_XHALF;
+    static constexpr uint32_t OFF_BIAS = CU_OFF_X + CU_XSTAGES * XSTAGE;
+    static constexpr uint32_t OFF_BAR = OFF_BIAS + NF * 4;
+    static constexpr uint32_t SMEM = 1024 + OFF_BAR + 256;
+};
 
 #ifdef M2T_TIMING
 __device__ long long g_conv_dbg[64];   // CTA 0: epilogue thread 0 stamps [8i+0..4], MMA warp stamps [8i+5..7], tiles i < 8
@@ -48,16 +61,19 @@ __device__ long long g_conv_dbg[64];   // CTA 0: epilogue thread 0 stamps [8i+0.
 #define M2T_CT(slot) do { } while (0)
 #endif
 
+template <bool W2>
 __global__ void __launch_bounds__(CU_THREADS, 1)
 ffconv_umma_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ CUtensorMap mapW,
                    const __grid_constant__ CUtensorMap mapXin, const __grid_constant__ CUtensorMap mapXout,
                    const float* __restrict__ bias, double* __restrict__ stats, int B, int Hp, int Wp,
                    const float* __restrict__ res, __half* __restrict__ xr) {
+    using CF = CuCfg<W2>;
+    constexpr int NCH = CF::NCH, NHALF = CF::NHALF;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
-    float* sbias = reinterpret_cast<float*>(sm + CU_OFF_BIAS);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + CU_OFF_BAR);
+    float* sbias = reinterpret_cast<float*>(sm + CF::OFF_BIAS);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + CF::OFF_BAR);
     uint64_t* full = bars;                        // [2]  Y halo tile landed
     uint64_t* empty = bars + 2;                   // [2]  ... consumed by the MMAs
     uint64_t* wfull = bars + 4;
@@ -72,10 +88,15 @@ ffconv_umma_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_consta
     const int tiles_x = Wp / CU_TW, tiles_y = Hp / CU_TH;
     const int per_img = tiles_x * tiles_y;
     const int ntiles = B * per_img;
+    // W2: CTA c owns output channels (c & 1) * 32 .. and shares the tiles with the other CTAs of its parity
+    const int chalf = W2 ? (int)(blockIdx.x & 1) : 0;
+    const int c0 = chalf * 32;                                     // first output channel of this CTA
+    const int part = W2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int nparts = W2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     // contiguous tile range per CTA: neighbouring tiles share halo rows in L2 and mostly belong to one image,
     // so the InstanceNorm partial sums are flushed once or twice per CTA instead of once per tile
-    const int tile_lo = (int)((long)blockIdx.x * ntiles / gridDim.x);
-    const int tile_hi = (int)((long)(blockIdx.x + 1) * ntiles / gridDim.x);
+    const int tile_lo = (int)((long)part * ntiles / nparts);
+    const int tile_hi = (int)((long)(part + 1) * ntiles / nparts);
 
     if (tid < NF) sbias[tid] = bias[tid];
     if (warp == 5) tmem_alloc(tmem_slot, 128);
@@ -102,7 +123,7 @@ ffconv_umma_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_consta
         // TMA producer: the whole warp runs the loop, one elected lane issues
         if (elect_one_sync()) {
             mbar_expect_tx(wfull, CU_W_BYTES);   // weights are constants: loaded while the previous kernel drains
-            for (int tap = 0; tap < 9; ++tap) tma_load_2d(sm + tap * NF * 128, &mapW, wfull, 0, tap * NF);
+            for (int tap = 0; tap < 9; ++tap) tma_load_2d(sm + tap * NF * 128, &mapW, wfull, 0, (chalf * 9 + tap) * NF);
         }
         pdl_wait();
         uint32_t it = 0;
@@ -121,10 +142,9 @@ ffconv_umma_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_consta
             __syncwarp();
             mbar_wait(&xempty[xs], xph ^ 1);
             if (elect_one_sync()) {
-                uint8_t* xt = sm + CU_OFF_X + xs * CU_XSTAGE;
-                mbar_expect_tx(&xfull[xs], CU_XSTAGE);
-                tma_load_4d(xt, &mapXin, &xfull[xs], 0, x0, y0, b);
-                tma_load_4d(xt + CU_XHALF, &mapXin, &xfull[xs], 32, x0, y0, b);
+                uint8_t* xt = sm + CU_OFF_X + xs * CF::XSTAGE;
+                mbar_expect_tx(&xfull[xs], CF::XSTAGE);
+                for (int hh = 0; hh < NHALF; ++hh) tma_load_4d(xt + hh * CU_XHALF, &mapXin, &xfull[xs], c0 + 32 * hh, x0, y0, b);
             }
             __syncwarp();
         }
@@ -171,9 +191,8 @@ ffconv_umma_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_consta
             const uint32_t xs = it % CU_XSTAGES, xph = (it / CU_XSTAGES) & 1;
             mbar_wait(&xout[xs], xph);
             if (elect_one_sync()) {
-                const uint8_t* xt = sm + CU_OFF_X + xs * CU_XSTAGE;
-                tma_store_4d(&mapXout, xt, 0, x0, y0, b);
-                tma_store_4d(&mapXout, xt + CU_XHALF, 32, x0, y0, b);
+                const uint8_t* xt = sm + CU_OFF_X + xs * CF::XSTAGE;
+                for (int hh = 0; hh < NHALF; ++hh) tma_store_4d(&mapXout, xt + hh * CU_XHALF, c0 + 32 * hh, x0, y0, b);
                 tma_store_commit();
                 tma_store_wait_read();
                 mbar_arrive(&xempty[xs]);
@@ -182,10 +201,12 @@ ffconv_umma_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_consta
         }
         tma_store_wait_all();                      // a no-op for lanes that issued nothing
     } else {
-        // Epilogue: thread t = TMEM lane = tile pixel t (row t of both half tiles)
+        // Epilogue: thread t = TMEM lane = tile pixel t (row t of every half tile)
         const int t = warp * 32 + lane;
         const uint32_t lanef = (uint32_t)(warp * 32) << 16;
-        const int sc = t & 63, shalf = t >> 6;                  // statistics pass: channel, half of the pixels
+        // statistics pass: thread = (channel, part of the pixels)
+        constexpr int SPX = 128 * NCH / 128;                    // pixels per thread: 64 (NCH = 64) or 32
+        const int sc = t % NCH, spart = t / NCH;
         const uint32_t sc_off = (uint32_t)(sc >> 5) * CU_XHALF + (uint32_t)(sc & 3) * 4;
         const uint32_t sc_chunk = (uint32_t)(sc & 31) >> 2;
         pdl_wait();
@@ -199,18 +220,18 @@ ffconv_umma_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_consta
             const int y0 = (r / tiles_x) * CU_TH, x0 = (r % tiles_x) * CU_TW;
             const uint32_t acc = it & 1, aph = (it >> 1) & 1;
             const uint32_t xs = it % CU_XSTAGES, xph = (it / CU_XSTAGES) & 1;
-            uint8_t* xt = sm + CU_OFF_X + xs * CU_XSTAGE;
+            uint8_t* xt = sm + CU_OFF_X + xs * CF::XSTAGE;
             const long pix = ((long)b * Hp + (y0 + (t >> 3))) * Wp + (x0 + (t & 7));
             M2T_CT(0);
-            uint4 rv[16];                                       // last CFTM: this pixel's row of the head output
+            uint4 rv[NCH / 4];                                  // last CFTM: this pixel's row of the head output
             if (xr != nullptr) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) ldg256(res + pix * NF + 8 * j, rv[2 * j], rv[2 * j + 1]);
+                for (int j = 0; j < NCH / 8; ++j) ldg256(res + pix * NF + c0 + 8 * j, rv[2 * j], rv[2 * j + 1]);
             }
             if (b != cur_b) {                                   // image changed: publish the finished image's sums
                 if (cur_b >= 0) {
-                    atomicAdd(&stats[((long)cur_b * NF + sc) * 2], dsum);
-                    atomicAdd(&stats[((long)cur_b * NF + sc) * 2 + 1], dsq);
+                    atomicAdd(&stats[((long)cur_b * NF + c0 + sc) * 2], dsum);
+                    atomicAdd(&stats[((long)cur_b * NF + c0 + sc) * 2 + 1], dsq);
                     dsum = 0.0; dsq = 0.0;
                 }
                 cur_b = b;
@@ -221,17 +242,25 @@ ffconv_umma_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_consta
             tc_fence_after();
             M2T_CT(2);
 #pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
+            for (int hh = 0; hh < NHALF; ++hh) {
                 uint32_t rr[32];
                 tmem_ld32(tmem_base + acc * NF + hh * 32 + lanef, rr);
-                tmem_ld_wait();
+                if constexpr (W2) {                            // columns 32..63: the same channels through the residual rows
+                    uint32_t rl[32];
+                    tmem_ld32(tmem_base + acc * NF + 32 + lanef, rl);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) rr[i] = __float_as_uint(fmaf(__uint_as_float(rl[i]), 1.f / 2048.f, __uint_as_float(rr[i])));
+                } else {
+                    tmem_ld_wait();
+                }
                 uint8_t* row = xt + hh * CU_XHALF + t * 128;
                 uint32_t hx[16];                               // fp16(res + x) of these 32 channels (last CFTM)
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     float4* cell = reinterpret_cast<float4*>(row + ((j ^ (t & 7)) << 4));
                     const float4 xv = *cell;
-                    const float4 bv = *reinterpret_cast<const float4*>(sbias + hh * 32 + 4 * j);
+                    const float4 bv = *reinterpret_cast<const float4*>(sbias + c0 + hh * 32 + 4 * j);
                     float4 v;
                     v.x = __uint_as_float(rr[4 * j]) + bv.x + xv.x;
                     v.y = __uint_as_float(rr[4 * j + 1]) + bv.y + xv.y;
@@ -247,7 +276,7 @@ ffconv_umma_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_consta
                     }
                 }
                 if (xr != nullptr) {   // fp16(res + x), the tail's first GEMM operand (ref :70): 64 B per half
-                    __half* xp = xr + pix * NF + hh * 32;
+                    __half* xp = xr + pix * NF + c0 + hh * 32;
                     stg256(xp, make_uint4(hx[0], hx[1], hx[2], hx[3]), make_uint4(hx[4], hx[5], hx[6], hx[7]));
                     stg256(xp + 16, make_uint4(hx[8], hx[9], hx[10], hx[11]), make_uint4(hx[12], hx[13], hx[14], hx[15]));
                 }
@@ -259,10 +288,10 @@ ffconv_umma_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_consta
             asm volatile("bar.sync 1, 128;" ::: "memory");
             if (t == 0) mbar_arrive(&xout[xs]);
             M2T_CT(3);
-            // statistics of the finished tile: thread = (channel, half of the pixels), conflict-free row reads
+            // statistics of the finished tile: conflict-free row reads (a warp reads 32 channels of one pixel)
             float ssum = 0.f, ssq = 0.f;
 #pragma unroll 8
-            for (int p = shalf * 64; p < shalf * 64 + 64; ++p) {
+            for (int p = spart * SPX; p < spart * SPX + SPX; ++p) {
                 const float v = *reinterpret_cast<const float*>(xt + sc_off + p * 128 + ((sc_chunk ^ (uint32_t)(p & 7)) << 4));
                 ssum += v;
                 ssq = fmaf(v, v, ssq);
@@ -274,8 +303,8 @@ ffconv_umma_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_consta
             M2T_CT(4);
         }
         if (cur_b >= 0) {
-            atomicAdd(&stats[((long)cur_b * NF + sc) * 2], dsum);
-            atomicAdd(&stats[((long)cur_b * NF + sc) * 2 + 1], dsq);
+            atomicAdd(&stats[((long)cur_b * NF + c0 + sc) * 2], dsum);
+            atomicAdd(&stats[((long)cur_b * NF + c0 + sc) * 2 + 1], dsq);
         }
     }
     tc_fence_before();
@@ -292,8 +321,10 @@ int read_conv_timing(long long* host64) {
 int read_conv_timing(long long* host64) { memset(host64, 0, sizeof(long long) * 64); return M2T_OK; }
 #endif
 
-int launch_ffconv_umma(const __half* Y, const __half* Wpk, const float* bias, const float* Xin, float* Xout,
-                       double* stats, const Geom& g, cudaStream_t s, const float* res, __half* xr) {
+template <bool W2>
+static int launch_ffconv_umma_t(const __half* Y, const __half* Wpk, const float* bias, const float* Xin, float* Xout,
+                                double* stats, const Geom& g, cudaStream_t s, const float* res, __half* xr) {
+    using CF = CuCfg<W2>;
     CUtensorMap mapY, mapW, mapXin, mapXout;
     {
         const uint64_t dims[4] = {NF, (uint64_t)g.Wp, (uint64_t)g.Hp, (uint64_t)g.B};
@@ -301,8 +332,8 @@ int launch_ffconv_umma(const __half* Y, const __half* Wpk, const float* bias, co
         const uint32_t box[4] = {NF, CU_HW, CU_TH + 2, 1};
         M2T_TRY(make_tensor_map(&mapY, Y, 2, 4, dims, str, box, 3));
     }
-    {
-        const uint64_t dims[2] = {NF, 9 * NF}, str[2] = {2, NF * 2};
+    {   // weight rows: [9][64] (W2: [2][9][64]) x 64 input channels
+        const uint64_t dims[2] = {NF, (uint64_t)(W2 ? 2 : 1) * 9 * NF}, str[2] = {2, NF * 2};
         const uint32_t box[2] = {NF, NF};
         M2T_TRY(make_tensor_map(&mapW, Wpk, 2, 2, dims, str, box, 3));
     }
@@ -313,12 +344,28 @@ int launch_ffconv_umma(const __half* Y, const __half* Wpk, const float* bias, co
         M2T_TRY(make_tensor_map(&mapXin, Xin, 4, 4, dims, str, box, 3));
         M2T_TRY(make_tensor_map(&mapXout, Xout, 4, 4, dims, str, box, 3));
     }
-    M2T_ENSURE_SMEM(ffconv_umma_kernel, CU_SMEM);
+    M2T_ENSURE_SMEM(ffconv_umma_kernel<W2>, CF::SMEM);
     const int ntiles = g.B * (g.Hp / CU_TH) * (g.Wp / CU_TW);
-    const int grid = ntiles < device_sm_count() ? ntiles : device_sm_count();
-    M2T_CUDA(launch_pdl(ffconv_umma_kernel, dim3(grid), dim3(CU_THREADS), CU_SMEM, s, mapY, mapW, mapXin, mapXout, bias, stats,
-                        g.B, g.Hp, g.Wp, res, xr));
+    int grid = device_sm_count();
+    if (W2) {
+        grid &= ~1;                                           // CTA pairs: one per channel half
+        if (grid > 2 * ntiles) grid = 2 * ntiles;
+    } else if (grid > ntiles) {
+        grid = ntiles;
+    }
+    M2T_CUDA(launch_pdl(ffconv_umma_kernel<W2>, dim3(grid), dim3(CU_THREADS), CF::SMEM, s, mapY, mapW, mapXin, mapXout, bias,
+                        stats, g.B, g.Hp, g.Wp, res, xr));
     return M2T_OK;
+}
+
+int launch_ffconv_umma(const __half* Y, const __half* Wpk, const float* bias, const float* Xin, float* Xout,
+                       double* stats, const Geom& g, cudaStream_t s, const float* res, __half* xr) {
+    return launch_ffconv_umma_t<false>(Y, Wpk, bias, Xin, Xout, stats, g, s, res, xr);
+}
+
+int launch_ffconv_umma_w2(const __half* Y, const __half* Wpk2, const float* bias, const float* Xin, float* Xout,
+                          double* stats, const Geom& g, cudaStream_t s, const float* res, __half* xr) {
+    return launch_ffconv_umma_t<true>(Y, Wpk2, bias, Xin, Xout, stats, g, s, res, xr);
 }
 
 }  // namespace m2t

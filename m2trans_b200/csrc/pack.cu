@@ -23,6 +23,7 @@ int make_packed_layout(int scale, int n_blocks, PackedLayout* L) {
             L->blk[i].attn[a].relx = take((size_t)32 * C * 2);
         }
         L->blk[i].ffw = take((size_t)9 * NF * NF * 2);
+        L->blk[i].ffw2 = take((size_t)2 * 9 * NF * NF * 2);
         L->blk[i].ffb = take(NF * 4);
     }
     const int r0 = scale == 4 ? 2 : scale;
@@ -46,7 +47,9 @@ enum PackMode {
     PK_CONV3_W,        // src [O][64][3][3] -> dst [tap][Opad][64] fp16, rows >= O zero
     PK_RELX,           // src rel_h [10][C/2] (+ rel_w passed as src2) -> dst fp16 [32][C]
     PK_UP_W,           // tail 1x1 conv: src [64 r^2][64] -> dst fp16 row (uv*64 + c) <- src row (c*r^2 + uv)
-    PK_UP_B            // its bias with the same row permutation (fp32)
+    PK_UP_B,           // its bias with the same row permutation (fp32)
+    PK_CONV3_W2        // src [64][64][3][3] -> dst [half][tap][64 rows][64] fp16: rows 0..31 = hi of output channels
+                       // half*32.., rows 32..63 = their rounding residual * 2^11 (split-precision ff conv)
 };
 
 __global__ void pack_kernel(int mode, const float* __restrict__ src, const float* __restrict__ src2, void* dstv,
@@ -65,6 +68,13 @@ __global__ void pack_kernel(int mode, const float* __restrict__ src, const float
         case PK_CONV3_W: {  // i over dst [9][Opad=p1][64]; p0 = real O
             const int c = i % NF, o = (i / NF) % p1, tap = i / (NF * p1);
             reinterpret_cast<__half*>(dstv)[i] = o < p0 ? __float2half_rn(src[(o * NF + c) * 9 + tap]) : __half(0);
+        } break;
+        case PK_CONV3_W2: { // i over dst [2][9][64][64]
+            const int c = i % NF, row = (i / NF) % NF, tap = (i / (NF * NF)) % 9, hh = i / (NF * NF * 9);
+            const int o = hh * 32 + (row & 31);
+            const float wv = src[(o * NF + c) * 9 + tap];
+            const __half hi = __float2half_rn(wv);
+            reinterpret_cast<__half*>(dstv)[i] = row < 32 ? hi : __float2half_rn((wv - __half2float(hi)) * 2048.f);
         } break;
         case PK_RELX: {     // i over dst [32][C=p0]
             const int C = p0, hc = C / 2, c = i % C, row = i / C;
@@ -165,6 +175,7 @@ int pack_weights_impl(const PackedLayout& L, const float* const* P, int n_params
             M2T_TRY(run_pack(PK_RELX, relh, relw, packed + A.relx, 32 * C, C, 0, 1.f, s));
         }
         M2T_TRY(run_pack(PK_CONV3_W, P[base + 12], nullptr, packed + L.blk[i].ffw, 9 * NF * NF, NF, NF, 1.f, s));
+        M2T_TRY(run_pack(PK_CONV3_W2, P[base + 12], nullptr, packed + L.blk[i].ffw2, 2 * 9 * NF * NF, 0, 0, 1.f, s));
         M2T_TRY(run_pack(PK_COPY_F32, P[base + 13], nullptr, packed + L.blk[i].ffb, NF, 0, 0, 1.f, s));
     }
     const int tb = 6 + 14 * L.n_blocks;
