@@ -90,7 +90,7 @@ struct m2t_plan {
     PackedLayout L;
     int tail_chunk;            // images per tail pass
     // workspace byte offsets
-    size_t o_res, o_x, o_y, o_z, o_qkv, o_o, o_h3, o_h4, o_lo[4], o_stats, o_munorm, o_xr, o_t1, ws_bytes;
+    size_t o_res, o_x, o_y, o_ylo, o_z, o_qkv, o_o, o_h3, o_h4, o_lo[4], o_stats, o_munorm, o_xr, o_t1, ws_bytes;
     int n_launches;
 };
 
@@ -199,6 +199,7 @@ int m2t_plan_create(const m2t_cfg* cfg, m2t_plan** out) {
     p->o_o = take(P * NB * 2);
     p->o_h3 = take(P * NB * 2);
     p->o_h4 = take(P * NB * 2);
+    p->o_ylo = take(P * NF * 2);                                  // rounding residual of Y * 2^11 (precise mode)
     for (int a = 0; a < 4; ++a) p->o_lo[a] = take(P * NB * 2);   // fp16 rounding residuals of t_1..t_4 (residual path)
     p->o_stats = take((size_t)(cfg->n_blocks + 1) * g.B * NF * 2 * sizeof(double));
     p->o_munorm = take((size_t)g.B * NF * sizeof(float2));
@@ -350,6 +351,7 @@ int m2t_forward_phases(const m2t_plan* plan, const void* d_packed, const float* 
                 AttnFuse fz;
                 fz.T = Tb[a]; fz.Y = Y; fz.Tnext = a < 3 ? Tb[a + 1] : nullptr;
                 fz.Tlo = Lb[a]; fz.Tnext_lo = a < 3 ? Lb[a + 1] : nullptr;
+                fz.Ylo = precise ? reinterpret_cast<__half*>(ws + plan->o_ylo) : nullptr;
                 fz.branch = a; fz.Hp = g.Hp; fz.Wp = g.Wp;
                 M2T_TRY(launch_attn_umma(C, QKV, reinterpret_cast<const __half*>(W + A.relx), nullptr, g.B, h, w, s, &fz));
             }
@@ -366,7 +368,8 @@ int m2t_forward_phases(const m2t_plan* plan, const void* d_packed, const float* 
         }
         const bool last = i == plan->cfg.n_blocks - 1;      // the last block also emits fp16(res + x) for the tail
         if (precise && !(var & M2T_VAR_SIMT_CONV))
-            M2T_TRY(launch_ffconv_umma_w2(Y, reinterpret_cast<const __half*>(W + L.blk[i].ffw2),
+            M2T_TRY(launch_ffconv_umma_w2(Y, reinterpret_cast<const __half*>(ws + plan->o_ylo),
+                                          reinterpret_cast<const __half*>(W + L.blk[i].ffw2),
                                           reinterpret_cast<const float*>(W + L.blk[i].ffb), Xin, X,
                                           stats + (i + 1) * stat_stride, g, s, last ? res : nullptr, last ? XR : nullptr));
         else

@@ -487,6 +487,16 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
                             for (int e = 0; e < 8; ++e) yh[e] = __floats2half2_rn(yv[2 * e], yv[2 * e + 1]);
                             __half* yp = fz.Y + pix * NF + NB * br;
                             stg256(yp, yo[0], yo[1]);
+                            if constexpr (LO) {          // rounding residual of y_k * 2^11 for the split-precision ff conv
+                                uint4 yl[2];
+                                __half2* ylh = reinterpret_cast<__half2*>(yl);
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) {
+                                    const float2 yr = __half22float2(yh[e]);
+                                    ylh[e] = __floats2half2_rn((yv[2 * e] - yr.x) * 2048.f, (yv[2 * e + 1] - yr.y) * 2048.f);
+                                }
+                                stg256(fz.Ylo + pix * NF + NB * br, yl[0], yl[1]);
+                            }
                             if (has_next) {
                                 uint4 to[2], tol[2];
                                 __half2* tnh = reinterpret_cast<__half2*>(to);

@@ -178,6 +178,7 @@ struct AttnFuse {
     // qkv GEMM reads T alone.  Rounding t_k before that add was the largest single contributor to the output error.
     const __half* Tlo;      // same layout as T
     __half* Tnext_lo;       // same layout as Tnext, written here
+    __half* Ylo;            // (y_k - fp16(y_k)) * 2^11, same layout as Y: the split-precision ff conv's second A operand
     int branch;             // 0..3
     int Hp, Wp;
 };
@@ -201,8 +202,9 @@ int launch_ffconv_umma(const __half* Y, const __half* Wp, const float* bias, con
                        double* stats, const Geom& g, cudaStream_t s, const float* res = nullptr,
                        __half* xr = nullptr);
 // split-precision weights (BlockW::ffw2): every CTA computes 32 output channels with hi and residual weight rows
-int launch_ffconv_umma_w2(const __half* Y, const __half* Wp2, const float* bias, const float* Xin, float* Xout,
-                          double* stats, const Geom& g, cudaStream_t s, const float* res = nullptr,
+// and split-precision input: Ylo = fp16 rounding residual of Y * 2^11, same layout as Y
+int launch_ffconv_umma_w2(const __half* Y, const __half* Ylo, const __half* Wp2, const float* bias, const float* Xin,
+                          float* Xout, double* stats, const Geom& g, cudaStream_t s, const float* res = nullptr,
                           __half* xr = nullptr);
 
 // tail_simt.cu

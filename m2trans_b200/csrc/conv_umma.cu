@@ -22,8 +22,11 @@
 //   W2 = false  the 64 accumulator columns are the 64 output channels, fp16 weights [9][64][64]
 //   W2 = true   split-precision weights (BlockW::ffw2): a CTA owns 32 output channels; accumulator columns 0..31 use
 //               the fp16 weights, columns 32..63 their rounding residuals * 2^11, and the epilogue adds
-//               hi + residual * 2^-11.  fp16 weight rounding was the largest error term left after the residual-path
-//               fix (emulated: 4.9e-4 max / 9e-5 rms at x3); the tensor pipe had the room (29 % busy).
+//               hi + residual * 2^-11.  The A operand is split the same way: a second halo tile holds the rounding
+//               residual of Y * 2^11 (written by the attention epilogue) and 36 more MMAs (N = 32, residual tile x fp16
+//               weights) accumulate into columns 32..63.  fp16 rounding of the conv's weights and input were the two
+//               largest error terms left after the residual-path fix (emulated at x3: 9e-5 and 8e-5 rms of 1.6e-4);
+//               the tensor pipe had the room (29 % busy).
 //
 // Warp roles (224 threads): warps 0-3 epilogue, warp 4 TMA loads, warp 5 MMA issuer, warp 6 TMA stores.
 #include "common.cuh"
@@ -41,7 +44,6 @@ constexpr int CU_XSTAGES = 3;                                         // fp32 re
 constexpr uint32_t CU_XHALF = 128 * 128;                              // 128 pixels x 32 channels x 4 B
 constexpr uint32_t CU_W_BYTES = 9 * NF * 128;                         // 73728
 constexpr uint32_t CU_OFF_A = CU_W_BYTES;
-constexpr uint32_t CU_OFF_X = CU_OFF_A + CU_STAGES * CU_STAGE;
 constexpr int CU_THREADS = 224;
 
 template <bool W2>
@@ -49,7 +51,9 @@ struct CuCfg {
     static constexpr int NCH = W2 ? 32 : 64;                          // output channels per CTA
     static constexpr int NHALF = NCH / 32;                            // 32-channel half tiles per residual tile
     static constexpr uint32_t XSTAGE = NHALF * CU_XHALF;
-    static constexpr uint32_t OFF_BIAS = CU_OFF_X + CU_XSTAGES * XSTAGE;
+    static constexpr uint32_t ASTAGE = (W2 ? 2 : 1) * CU_STAGE;   // W2: the halo tile of Y and of its rounding residual
+    static constexpr uint32_t OFF_X = CU_OFF_A + CU_STAGES * ASTAGE;
+    static constexpr uint32_t OFF_BIAS = OFF_X + CU_XSTAGES * XSTAGE;
     static constexpr uint32_t OFF_BAR = OFF_BIAS + NF * 4;
     static constexpr uint32_t SMEM = 1024 + OFF_BAR + 256;
 };
@@ -63,8 +67,8 @@ __device__ long long g_conv_dbg[64];   // CTA 0: epilogue thread 0 stamps [8i+0.
 
 template <bool W2>
 __global__ void __launch_bounds__(CU_THREADS, 1)
-ffconv_umma_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ CUtensorMap mapW,
-                   const __grid_constant__ CUtensorMap mapXin, const __grid_constant__ CUtensorMap mapXout,
+ffconv_umma_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ CUtensorMap mapYlo,
+                   const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapXin, const __grid_constant__ CUtensorMap mapXout,
                    const float* __restrict__ bias, double* __restrict__ stats, int B, int Hp, int Wp,
                    const float* __restrict__ res, __half* __restrict__ xr) {
     using CF = CuCfg<W2>;
@@ -109,6 +113,7 @@ ffconv_umma_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_consta
         for (int s = 0; s < CU_XSTAGES; ++s) { mbar_init(&xfull[s], 1); mbar_init(&xout[s], 1); mbar_init(&xempty[s], 5); }
         mbar_fence_init();
         tma_prefetch_desc(&mapY);
+        if (W2) tma_prefetch_desc(&mapYlo);
         tma_prefetch_desc(&mapW);
         tma_prefetch_desc(&mapXin);
         tma_prefetch_desc(&mapXout);
@@ -136,13 +141,14 @@ ffconv_umma_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_consta
             // tile it-3 is done, and that wait must not hold back the tile the MMAs need next
             mbar_wait(&empty[s], ph ^ 1);
             if (elect_one_sync()) {
-                mbar_expect_tx(&full[s], CU_TILE_BYTES);
-                tma_load_4d(sm + CU_OFF_A + s * CU_STAGE, &mapY, &full[s], 0, x0 - 1, y0 - 1, b);
+                mbar_expect_tx(&full[s], (W2 ? 2 : 1) * CU_TILE_BYTES);
+                tma_load_4d(sm + CU_OFF_A + s * CF::ASTAGE, &mapY, &full[s], 0, x0 - 1, y0 - 1, b);
+                if (W2) tma_load_4d(sm + CU_OFF_A + s * CF::ASTAGE + CU_STAGE, &mapYlo, &full[s], 0, x0 - 1, y0 - 1, b);
             }
             __syncwarp();
             mbar_wait(&xempty[xs], xph ^ 1);
             if (elect_one_sync()) {
-                uint8_t* xt = sm + CU_OFF_X + xs * CF::XSTAGE;
+                uint8_t* xt = sm + CF::OFF_X + xs * CF::XSTAGE;
                 mbar_expect_tx(&xfull[xs], CF::XSTAGE);
                 for (int hh = 0; hh < NHALF; ++hh) tma_load_4d(xt + hh * CU_XHALF, &mapXin, &xfull[xs], c0 + 32 * hh, x0, y0, b);
             }
@@ -165,7 +171,7 @@ ffconv_umma_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_consta
             M2T_CT(7);
             tc_fence_after();
             if (elect_one_sync()) {
-                const uint64_t da0 = umma_desc_at(tmpl_a, base + CU_OFF_A + s * CU_STAGE);
+                const uint64_t da0 = umma_desc_at(tmpl_a, base + CU_OFF_A + s * CF::ASTAGE);
                 const uint64_t db0 = umma_desc_at(tmpl_b, base);
 #pragma unroll
                 for (int tap = 0; tap < 9; ++tap) {
@@ -174,6 +180,19 @@ ffconv_umma_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_consta
                         const uint64_t da = da0 + (uint64_t)((((tap / 3) * CU_HW + (tap % 3)) * 128 + k * 32) >> 4);
                         const uint64_t db = db0 + (uint64_t)((tap * NF * 128 + k * 32) >> 4);
                         umma_f16_ss(tmem_base + acc * NF, da, db, idesc, (tap | k) ? 1u : 0u);
+                    }
+                }
+                if constexpr (W2) {   // residual tile x fp16 weight rows (the first 32 of each tap) -> columns 32..63
+                    constexpr uint32_t idesc_lo = umma_idesc_f16(128, 32);
+                    const uint64_t dl0 = umma_desc_at(tmpl_a, base + CU_OFF_A + s * CF::ASTAGE + CU_STAGE);
+#pragma unroll
+                    for (int tap = 0; tap < 9; ++tap) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint64_t da = dl0 + (uint64_t)((((tap / 3) * CU_HW + (tap % 3)) * 128 + k * 32) >> 4);
+                            const uint64_t db = db0 + (uint64_t)((tap * NF * 128 + k * 32) >> 4);
+                            umma_f16_ss(tmem_base + acc * NF + 32, da, db, idesc_lo, 1u);
+                        }
                     }
                 }
                 umma_commit(&empty[s]);
@@ -191,7 +210,7 @@ ffconv_umma_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_consta
             const uint32_t xs = it % CU_XSTAGES, xph = (it / CU_XSTAGES) & 1;
             mbar_wait(&xout[xs], xph);
             if (elect_one_sync()) {
-                const uint8_t* xt = sm + CU_OFF_X + xs * CF::XSTAGE;
+                const uint8_t* xt = sm + CF::OFF_X + xs * CF::XSTAGE;
                 for (int hh = 0; hh < NHALF; ++hh) tma_store_4d(&mapXout, xt + hh * CU_XHALF, c0 + 32 * hh, x0, y0, b);
                 tma_store_commit();
                 tma_store_wait_read();
@@ -220,7 +239,7 @@ ffconv_umma_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_consta
             const int y0 = (r / tiles_x) * CU_TH, x0 = (r % tiles_x) * CU_TW;
             const uint32_t acc = it & 1, aph = (it >> 1) & 1;
             const uint32_t xs = it % CU_XSTAGES, xph = (it / CU_XSTAGES) & 1;
-            uint8_t* xt = sm + CU_OFF_X + xs * CF::XSTAGE;
+            uint8_t* xt = sm + CF::OFF_X + xs * CF::XSTAGE;
             const long pix = ((long)b * Hp + (y0 + (t >> 3))) * Wp + (x0 + (t & 7));
             M2T_CT(0);
             uint4 rv[NCH / 4];                                  // last CFTM: this pixel's row of the head output
@@ -322,15 +341,16 @@ int read_conv_timing(long long* host64) { memset(host64, 0, sizeof(long long) * 
 #endif
 
 template <bool W2>
-static int launch_ffconv_umma_t(const __half* Y, const __half* Wpk, const float* bias, const float* Xin, float* Xout,
-                                double* stats, const Geom& g, cudaStream_t s, const float* res, __half* xr) {
+static int launch_ffconv_umma_t(const __half* Y, const __half* Ylo, const __half* Wpk, const float* bias, const float* Xin,
+                                float* Xout, double* stats, const Geom& g, cudaStream_t s, const float* res, __half* xr) {
     using CF = CuCfg<W2>;
-    CUtensorMap mapY, mapW, mapXin, mapXout;
+    CUtensorMap mapY, mapYlo, mapW, mapXin, mapXout;
     {
         const uint64_t dims[4] = {NF, (uint64_t)g.Wp, (uint64_t)g.Hp, (uint64_t)g.B};
         const uint64_t str[4] = {2, NF * 2, (uint64_t)g.Wp * NF * 2, (uint64_t)g.Hp * g.Wp * NF * 2};
         const uint32_t box[4] = {NF, CU_HW, CU_TH + 2, 1};
         M2T_TRY(make_tensor_map(&mapY, Y, 2, 4, dims, str, box, 3));
+        M2T_TRY(make_tensor_map(&mapYlo, W2 ? Ylo : Y, 2, 4, dims, str, box, 3));
     }
     {   // weight rows: [9][64] (W2: [2][9][64]) x 64 input channels
         const uint64_t dims[2] = {NF, (uint64_t)(W2 ? 2 : 1) * 9 * NF}, str[2] = {2, NF * 2};
@@ -353,19 +373,19 @@ static int launch_ffconv_umma_t(const __half* Y, const __half* Wpk, const float*
     } else if (grid > ntiles) {
         grid = ntiles;
     }
-    M2T_CUDA(launch_pdl(ffconv_umma_kernel<W2>, dim3(grid), dim3(CU_THREADS), CF::SMEM, s, mapY, mapW, mapXin, mapXout, bias,
+    M2T_CUDA(launch_pdl(ffconv_umma_kernel<W2>, dim3(grid), dim3(CU_THREADS), CF::SMEM, s, mapY, mapYlo, mapW, mapXin, mapXout, bias,
                         stats, g.B, g.Hp, g.Wp, res, xr));
     return M2T_OK;
 }
 
 int launch_ffconv_umma(const __half* Y, const __half* Wpk, const float* bias, const float* Xin, float* Xout,
                        double* stats, const Geom& g, cudaStream_t s, const float* res, __half* xr) {
-    return launch_ffconv_umma_t<false>(Y, Wpk, bias, Xin, Xout, stats, g, s, res, xr);
+    return launch_ffconv_umma_t<false>(Y, nullptr, Wpk, bias, Xin, Xout, stats, g, s, res, xr);
 }
 
-int launch_ffconv_umma_w2(const __half* Y, const __half* Wpk2, const float* bias, const float* Xin, float* Xout,
-                          double* stats, const Geom& g, cudaStream_t s, const float* res, __half* xr) {
-    return launch_ffconv_umma_t<true>(Y, Wpk2, bias, Xin, Xout, stats, g, s, res, xr);
+int launch_ffconv_umma_w2(const __half* Y, const __half* Ylo, const __half* Wpk2, const float* bias, const float* Xin,
+                          float* Xout, double* stats, const Geom& g, cudaStream_t s, const float* res, __half* xr) {
+    return launch_ffconv_umma_t<true>(Y, Ylo, Wpk2, bias, Xin, Xout, stats, g, s, res, xr);
 }
 
 }  // namespace m2t

@@ -219,3 +219,41 @@ def test_full_size_cfg3_cfg4_properties(name, scale, shape, probe):
     assert p >= PSNR_MIN and m <= MAXABS_MAX
     del y, y_one
     torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("scale,h,w", [(3, 200, 266), (2, 128, 160)])
+def test_speckle_frames_meet_the_bar_at_full_size(scale, h, w):
+    """Smooth, heavy-tailed ("ultrasound-like") frames are the hard case for the fp16 operand format: with plain fp16
+    operands the x2 / x3 forward reaches 2.0-2.5e-3 on them (the single-stage tail attenuates less than x4's).  The
+    precise mode (default for x2 / x3: residual-path residuals of t_k, split-precision ff conv) brings them under
+    the bar; the fast mode stays selectable and is checked at its own, looser level."""
+    from m2trans_b200 import _lib
+    from oracle import m2trans_oracle as O
+    from m2trans_b200.synthetic import synthetic_input, synthetic_state_dict
+    worst, worst_fast = 0.0, 0.0
+    for seed in (0, 1):
+        x = synthetic_input(1, h, w, seed=100 + seed, kind="speckle")
+        ref = O.forward(synthetic_state_dict(scale, seed), x)
+        y = _model(scale, seed)(x.cuda()).cpu()
+        p, m = _metrics(y, ref)
+        yf = _model(scale, seed, variant=_lib.VAR_PRECISE_OFF)(x.cuda()).cpu()
+        pf, mf = _metrics(yf, ref)
+        print(f"x{scale} {h}x{w} speckle seed {seed}: precise PSNR {p:.1f} dB max-abs {m:.2e} | fast PSNR {pf:.1f} dB max-abs {mf:.2e}")
+        assert p >= PSNR_MIN and m <= MAXABS_MAX
+        assert pf >= PSNR_MIN and mf <= 3.5e-3
+        worst, worst_fast = max(worst, m), max(worst_fast, mf)
+    assert worst < worst_fast
+
+
+def test_precise_mode_on_x4():
+    """x4 defaults to the fast mode (it has 2x margin); the precise mode must work there too and be at least as close."""
+    from m2trans_b200 import _lib
+    from oracle import m2trans_oracle as O
+    from m2trans_b200.synthetic import synthetic_input, synthetic_state_dict
+    x = synthetic_input(2, 72, 104, seed=7, kind="speckle")
+    ref = O.forward(synthetic_state_dict(4, 1), x)
+    pf, mf = _metrics(_model(4, 1)(x.cuda()).cpu(), ref)
+    pp, mp = _metrics(_model(4, 1, variant=_lib.VAR_PRECISE_ON)(x.cuda()).cpu(), ref)
+    print(f"x4 speckle: fast PSNR {pf:.1f} dB max-abs {mf:.2e} | precise PSNR {pp:.1f} dB max-abs {mp:.2e}")
+    assert pf >= PSNR_MIN and mf <= MAXABS_MAX and pp >= PSNR_MIN and mp <= MAXABS_MAX
+    assert pp > pf
