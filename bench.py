@@ -306,7 +306,8 @@ def run_ours(args):
             "config": {"workload": f"{args.workload}: M2Trans x{scale}, {B}x3x{H}x{W} LR per GPU, synthetic model_x{scale} checkpoint seed 0",
                        "l2": "768 MB buffer rewritten between timed iterations; 3 rotating input batches",
                        "sharding": "images; no collective on the data path",
-                       "precision": "fp16 GEMM operands, fp32 accumulate (TMEM), fp32 residual stream / softmax / norm statistics"},
+                       "precision": "fp16 GEMM operands, fp32 accumulate (TMEM), fp32 residual stream / softmax / norm statistics; "
+                                    + ("fast mode (plain fp16 operands)" if scale == 4 else "precise mode (fp16 hi + residual pairs on the residual path and in the ff conv)")},
             "clocks": clocks,
             "e2e": {"value": world * out_mp / (e2e_ms * 1e-3), "unit": "MP/s", "h2d_bytes_per_step": B * 3 * H * W * 4,
                     "d2h_bytes_per_step": B * 3 * H * scale * W * scale * 4, "ms_per_step": e2e_ms},
