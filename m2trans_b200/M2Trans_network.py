@@ -269,16 +269,24 @@ class M2Trans(nn.Module):
         cached = self.__dict__.get("_m2t_slots")
         slots = cached[1] if cached is not None and cached[0] == id(self) else None
         if slots is None:
+            # A DataParallel replica (torch.nn.parallel.replicate) has an EMPTY _parameters dict: its broadcast copies
+            # are plain attributes, listed per module in _former_parameters in registration order.
+            replica = "_former_parameters" in self.__dict__
             slots, got = [], []
             for prefix, mod in self.named_modules():
-                own = [(mod._parameters, n) for n, v in mod._parameters.items() if v is not None]
+                if replica:
+                    src = mod.__dict__.get("_former_parameters", {})
+                    own = [(src, n) for n in src]
+                else:
+                    own = [(mod._parameters, n) for n, v in mod._parameters.items() if v is not None]
                 own += [(mod._buffers, n) for n, v in mod._buffers.items()
                         if v is not None and n not in mod._non_persistent_buffers_set]
                 slots += own
                 got += [(prefix + "." if prefix else "") + n for _, n in own]
-            want = list(self.state_dict(keep_vars=True))
-            if got != want:                               # never expected; fall back to the slow, always-correct walk
-                return [p for _, p in self.state_dict(keep_vars=True).items()]
+            if not replica:
+                want = list(self.state_dict(keep_vars=True))
+                if got != want:                           # never expected; fall back to the slow, always-correct walk
+                    return [p for _, p in self.state_dict(keep_vars=True).items()]
             self.__dict__["_m2t_slots"] = (id(self), slots)
         return [d[name] for d, name in slots]
 
@@ -291,8 +299,12 @@ class M2Trans(nn.Module):
 
     def _packed_weights(self, st: _DeviceState, device) -> torch.Tensor:
         params = self._param_list()
-        key = tuple((p.data_ptr(), p._version) for p in params)
-        if st.packed is not None and st.packed_key == key:
+        # Replicas get fresh broadcast copies on every DataParallel call; the caching allocator may hand out the same
+        # addresses again with _version 0 even after the source weights changed, so (data_ptr, _version) proves nothing
+        # there: a replica re-packs on every forward, into the same buffer so that the captured graph stays valid.
+        replica = "_former_parameters" in self.__dict__
+        key = None if replica else tuple((p.data_ptr(), p._version) for p in params)
+        if not replica and st.packed is not None and st.packed_key == key:
             return st.packed
         lib = _lib.load()
         for p in params:
@@ -306,7 +318,10 @@ class M2Trans(nn.Module):
         keep = [p.detach().contiguous() for p in params]
         ptrs = (C.c_void_p * n)(*[t.data_ptr() for t in keep])
         nbytes = lib.m2t_packed_weight_bytes(self.scale, self.n_blocks)
-        packed = torch.empty(nbytes + 256, dtype=torch.uint8, device=device)
+        if replica and st.packed is not None and st.packed.numel() == nbytes + 256:
+            packed = st.packed                                    # same buffer: graphs captured on it stay valid
+        else:
+            packed = torch.empty(nbytes + 256, dtype=torch.uint8, device=device)
         _lib.check(lib.m2t_pack_weights(self.scale, self.n_blocks, ptrs, n, _aligned_ptr(packed), _stream_ptr(device)),
                    "m2t_pack_weights")
         st.packed, st.packed_key = packed, key
@@ -350,7 +365,9 @@ class M2Trans(nn.Module):
                 _lib.check(lib.m2t_forward(plan["handle"], _aligned_ptr(packed), xin.data_ptr(), yout.data_ptr(),
                                            _aligned_ptr(plan["ws"]), _stream_ptr(device)), "m2t_forward")
 
-            if not self.cuda_graph or torch.cuda.is_current_stream_capturing():
+            # DataParallel replicas run concurrently in one thread per device; graph capture is a process-wide mode
+            # (another thread's allocation invalidates it), so replicas launch eagerly.
+            if not self.cuda_graph or torch.cuda.is_current_stream_capturing() or "_former_parameters" in self.__dict__:
                 y = torch.empty(out_shape, dtype=torch.float32, device=device)
                 launch(x, y)
                 return y

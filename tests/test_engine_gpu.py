@@ -257,3 +257,20 @@ def test_precise_mode_on_x4():
     print(f"x4 speckle: fast PSNR {pf:.1f} dB max-abs {mf:.2e} | precise PSNR {pp:.1f} dB max-abs {mp:.2e}")
     assert pf >= PSNR_MIN and mf <= MAXABS_MAX and pp >= PSNR_MIN and mp <= MAXABS_MAX
     assert pp > pf
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (nn.DataParallel replicas)")
+def test_multi_gpu_dataparallel_matches_single_gpu():
+    """ref test.py:68 wraps the model in nn.DataParallel over ALL visible GPUs: replicas are shallow copies whose
+    parameters live in _former_parameters and are re-broadcast on every call; forwards run in one thread per device."""
+    from m2trans_b200.M2Trans_network import M2Trans
+    from m2trans_b200.synthetic import reference_checkpoint, synthetic_input
+    x = synthetic_input(4, 40, 56, seed=3).cuda()
+    multi = torch.nn.DataParallel(M2Trans(_args(3))).cuda()
+    multi.load_state_dict(reference_checkpoint(3, 0)["model_state_dict"], strict=True)
+    y_multi, y_again = multi.eval()(x), multi(x)
+    y_single = _model(3, 0)(x)
+    assert len(multi.device_ids) >= 2 and y_multi.device == x.device
+    assert torch.equal(y_multi, y_single) and torch.equal(y_again, y_single)
+    multi.load_state_dict(reference_checkpoint(3, 1)["model_state_dict"], strict=True)      # replicas must see new weights
+    assert torch.equal(multi(x), _model(3, 1)(x))
