@@ -19,6 +19,7 @@ import torch.nn as nn
 
 from . import _lib
 from ._lib import M2TError
+from ._params import state_tensors
 
 __all__ = ["Mlp", "EffAttention", "TransBlock"]
 
@@ -88,7 +89,7 @@ class TransBlock(nn.Module):
             raise M2TError(f"TransBlock.forward: expected [B, N, {self.dim}], got {tuple(x.shape)}")
         b, n, _ = x.shape
         lib = _lib.load()
-        params = [p.detach() for p in self.state_dict().values()]
+        params = [p.detach() for p in state_tensors(self)]          # also right on DataParallel replicas
         for p in params:
             if p.device != x.device or p.dtype != torch.float32:
                 raise M2TError("TransBlock.forward: parameters must be float32 on the input's device")
