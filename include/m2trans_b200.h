@@ -56,6 +56,7 @@ extern "C" {
  * Together they remove the two largest error terms of the fp16 operand format (emulated at x3 on a speckle frame:
  * max-abs 2.7e-3 -> 1.7e-3) for ~10 % of the forward time.  Default: on for x2 / x3, whose single-stage tail leaves
  * less margin under the 2e-3 bar, off for x4.  These bits force it either way. */
+#define M2T_VAR_SPLIT_QKV16  (1u << 7) /* branch 1: separate qkv kernel + attention instead of the fused attn16_qkv kernel */
 #define M2T_VAR_PRECISE_ON   (1u << 5)
 #define M2T_VAR_PRECISE_OFF  (1u << 6)
 

@@ -22,6 +22,7 @@ VAR_SIMT_ATTN = 1 << 3
 VAR_SIMT_ALL = 0xF
 VAR_UNFUSED_TAIL = 1 << 4
 VAR_PRECISE_ON, VAR_PRECISE_OFF = 1 << 5, 1 << 6
+VAR_SPLIT_QKV16 = 1 << 7
 PHASE_HEAD, PHASE_BODY, PHASE_TAIL, PHASE_ALL = 1, 2, 4, 7
 
 

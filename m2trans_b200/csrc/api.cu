@@ -213,7 +213,8 @@ int m2t_plan_create(const m2t_cfg* cfg, m2t_plan** out) {
     p->o_t1 = take(m2t_tail_scratch_bytes(cfg->scale, chunk, g.Hp, g.Wp));
     p->ws_bytes = off;
     const int tail_passes = (g.B + chunk - 1) / chunk;
-    const int per_block = (cfg->variant & M2T_VAR_SIMT_ATTN) ? (1 + 4 * 4 + 1) : (1 + 4 * 2 + 1);
+    const bool qkv16_fused = !(cfg->variant & (M2T_VAR_SIMT_ATTN | M2T_VAR_SIMT_QKV | M2T_VAR_SPLIT_QKV16));
+    const int per_block = (cfg->variant & M2T_VAR_SIMT_ATTN) ? (1 + 4 * 4 + 1) : (1 + 4 * 2 + 1 - (qkv16_fused ? 1 : 0));
     // tail per image chunk: x3 and the unfused variants run up [, up], border, out; otherwise [up,] fused
     const bool tail_fused = cfg->scale != 3 && !(cfg->variant & (M2T_VAR_SIMT_TAIL | M2T_VAR_UNFUSED_TAIL));
     const int per_tail = tail_fused ? (cfg->scale == 4 ? 2 : 1) : (cfg->scale == 4 ? 4 : 3);
@@ -347,12 +348,18 @@ int m2t_forward_phases(const m2t_plan* plan, const void* d_packed, const float* 
                 const int lv = branch_level(a), C = branch_ch(a);
                 const int h = g.Hp >> lv, w = g.Wp >> lv;
                 const AttnW& A = L.blk[i].attn[a];
-                M2T_TRY(run_qkv(var, Tb[a], reinterpret_cast<const __half*>(W + A.wqkv_f), QKV, g.B * h * w, C, s));
                 AttnFuse fz;
                 fz.T = Tb[a]; fz.Y = Y; fz.Tnext = a < 3 ? Tb[a + 1] : nullptr;
                 fz.Tlo = Lb[a]; fz.Tnext_lo = a < 3 ? Lb[a + 1] : nullptr;
                 fz.Ylo = precise ? reinterpret_cast<__half*>(ws + plan->o_ylo) : nullptr;
                 fz.branch = a; fz.Hp = g.Hp; fz.Wp = g.Wp;
+                if (a == 0 && !(var & (M2T_VAR_SIMT_QKV | M2T_VAR_SPLIT_QKV16))) {
+                    // branch 1: qkv conv inside the attention kernel (attn16_qkv.cu)
+                    M2T_TRY(launch_attn16_qkv(Tb[a], reinterpret_cast<const __half*>(W + A.wqkv_f),
+                                              reinterpret_cast<const __half*>(W + A.relx), g.B, h, w, s, fz));
+                    continue;
+                }
+                M2T_TRY(run_qkv(var, Tb[a], reinterpret_cast<const __half*>(W + A.wqkv_f), QKV, g.B * h * w, C, s));
                 M2T_TRY(launch_attn_umma(C, QKV, reinterpret_cast<const __half*>(W + A.relx), nullptr, g.B, h, w, s, &fz));
             }
         } else

@@ -187,6 +187,10 @@ int launch_branch_prep_all(const float* X, const double* stats, __half* T1, __ha
 int launch_attn_umma(int C, const __half* QKV, const __half* relx, __half* O, int B, int h, int w,
                      cudaStream_t s, const AttnFuse* fuse = nullptr);
 
+// attn16_qkv.cu : branch 1 with the qkv conv inside the attention kernel (fused glue only)
+int launch_attn16_qkv(const __half* T, const __half* Wqkv, const __half* relx, int B, int h, int w, cudaStream_t s,
+                      const AttnFuse& fz);
+
 int read_attn_timing(long long* host64);   // development aid, zeros unless built with -DM2T_TIMING (256 values)
 int read_tail_timing(long long* host64);   // the same for the fused tail kernel (64 values)
 int read_conv_timing(long long* host64);   // the same for the tcgen05 ff conv (64 values)
