@@ -274,3 +274,13 @@ def test_multi_gpu_dataparallel_matches_single_gpu():
     assert torch.equal(y_multi, y_single) and torch.equal(y_again, y_single)
     multi.load_state_dict(reference_checkpoint(3, 1)["model_state_dict"], strict=True)      # replicas must see new weights
     assert torch.equal(multi(x), _model(3, 1)(x))
+
+
+@pytest.mark.parametrize("scale,shape", [(4, (2, 3, 40, 72)), (3, (1, 3, 33, 47))])
+def test_fused_branch1_equals_split_kernels(scale, shape):
+    """Branch 1 runs its qkv conv inside the attention kernel (attn16_qkv.cu); M2T_VAR_SPLIT_QKV16 selects the separate
+    qkv kernel + attention.  Same fp16 roundings of q, k, v, same MMAs: the outputs agree bit for bit."""
+    from m2trans_b200 import _lib
+    from m2trans_b200.synthetic import synthetic_input
+    x = synthetic_input(shape[0], shape[2], shape[3], seed=11).cuda()
+    assert torch.equal(_model(scale, 2)(x), _model(scale, 2, variant=_lib.VAR_SPLIT_QKV16)(x))
