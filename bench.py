@@ -259,19 +259,24 @@ def run_ours(args):
     # all K steps ahead (host enqueue costs ~0.1 ms per step, but a shared box can stall the Python thread for several
     # ms, which wall-clock timing of 10 steps turns into a 2x error).  The region still contains every H2D copy, every
     # forward through the public call and every D2H copy of the K steps.  The wall-clock figure is kept beside it.
-    e2e_start, e2e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0 = time.perf_counter()
-    torch.cuda._sleep(40_000_000)
-    e2e_start.record(s_main)
-    s_in.wait_event(e2e_start)
-    s_out.wait_event(e2e_start)
-    for i in range(args.steps):
-        e2e_step(i)
-    s_out.wait_stream(s_main)
-    e2e_end.record(s_out)
-    torch.cuda.synchronize()
-    e2e_wall_ms = 1e3 * (time.perf_counter() - t0) / args.steps        # includes the ~20 ms of parking
-    e2e_ms = e2e_start.elapsed_time(e2e_end) / args.steps
+    # The K-step region is measured three times and the median reported (all three are kept in the JSON line): the D2H
+    # copy of the SR batch shares the host's PCIe fabric with other tenants, and single regions were seen 2-6x slower.
+    e2e_runs, e2e_wall = [], []
+    for _rep in range(3):
+        e2e_start, e2e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        torch.cuda._sleep(40_000_000)
+        e2e_start.record(s_main)
+        s_in.wait_event(e2e_start)
+        s_out.wait_event(e2e_start)
+        for i in range(args.steps):
+            e2e_step(i)
+        s_out.wait_stream(s_main)
+        e2e_end.record(s_out)
+        torch.cuda.synchronize()
+        e2e_wall.append(1e3 * (time.perf_counter() - t0) / args.steps)    # includes the ~20 ms of parking
+        e2e_runs.append(e2e_start.elapsed_time(e2e_end) / args.steps)
+    e2e_ms = sorted(e2e_runs)[1]
     clocks = sampler.stop()
 
     # ---- dominant kernel alone: CFTM feed-forward 3x3 conv --------------------------
@@ -323,7 +328,8 @@ def run_ours(args):
             "clocks": clocks,
             "e2e": {"value": world * out_mp / (e2e_ms * 1e-3), "unit": "MP/s", "h2d_bytes_per_step": B * 3 * H * W * 4,
                     "d2h_bytes_per_step": B * 3 * H * scale * W * scale * 4, "ms_per_step": e2e_ms,
-                    "timing": "CUDA events over K pipelined steps (H2D + forward + D2H each), streams parked so the host queues ahead"},
+                    "timing": "CUDA events over K pipelined steps (H2D + forward + D2H each), streams parked so the host queues ahead; "
+                              "median of 3 such regions", "ms_per_step_all": e2e_runs},
             "gpu_launches": launches,
             "step_ms": {"min": step_sorted[0], "median": step_sorted[len(step_sorted) // 2], "max": step_sorted[-1]},
             "roofline": {"kernel": "ffconv_umma (CFTM 3x3 feed-forward conv + residual + norm stats)", "bound": "hbm",
