@@ -197,7 +197,9 @@ int m2t_probe_umma(const void* d_a_image, uint32_t a_bytes, const void* d_b_imag
  * sees the kernels with the caches as the previous kernel left them. */
 int m2t_debug_profile_forward(const m2t_plan* plan, const void* d_packed, const float* d_x, float* d_y,
                               void* d_workspace, void* stream, char* text, size_t cap);
-/* m2t_debug_attn_timing: host64 holds 6 x 64 values.  Record 5: CTA 0 of the last tcgen05 ff-conv launch, per tile i < 8:
+/* m2t_debug_attn_timing: host64 holds 7 x 64 values.  Record 6: CTA 0 of the last 256-channel qkv GEMM launch ([0] entry,
+ * [1] prologue done, [2] weight slab landed, then per tile t < 6 at [8+8t+0..4]: MMA warp before its waits, first A
+ * block landed, MMAs issued; epilogue: accumulator ready, tile stored).  Record 5: CTA 0 of the last tcgen05 ff-conv launch, per tile i < 8:
  * epilogue [8i+0..4] tile start, residual loads issued, accumulator ready, staged, stored; MMA warp [8i+5..7] before
  * / after the accumulator-free wait and after the halo-tile wait.  Record 4: CTA 0 of the last fused-tail launch, per tile i < 8 at
  * [8i+0..5]: tile start, GELU epilogue done, U tile published, conv accumulators ready, planes written, gather done.

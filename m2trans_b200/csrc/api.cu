@@ -511,7 +511,8 @@ int m2t_debug_attn_timing(long long* host64) {
     if (!host64) { set_error("null pointer"); return M2T_E_ARG; }
     M2T_TRY(read_attn_timing(host64));
     M2T_TRY(read_tail_timing(host64 + 256));
-    return read_conv_timing(host64 + 320);
+    M2T_TRY(read_conv_timing(host64 + 320));
+    return read_qkv_timing(host64 + 384);
 }
 
 }  // extern "C"

@@ -194,6 +194,7 @@ int launch_attn16_qkv(const __half* T, const __half* Wqkv, const __half* relx, i
 int read_attn_timing(long long* host64);   // development aid, zeros unless built with -DM2T_TIMING (256 values)
 int read_tail_timing(long long* host64);   // the same for the fused tail kernel (64 values)
 int read_conv_timing(long long* host64);   // the same for the tcgen05 ff conv (64 values)
+int read_qkv_timing(long long* host64);    // the same for the 256-channel qkv GEMM (64 values)
 
 // conv_simt.cu : X_out = conv3x3_zero(Y) + bias + X_in, plus InstanceNorm partial sums
 // res/xr (optional): also write xr = fp16(Xout + res), the tail's first GEMM operand (ref :70)

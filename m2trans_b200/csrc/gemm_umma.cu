@@ -31,15 +31,28 @@ struct QkvCfg {
     static constexpr uint32_t A_STAGE = 128 * ROWB;
     static constexpr uint32_t B_BLOCK = NT * ROWB;
     static constexpr uint32_t B_BYTES = (KB * B_BLOCK + 1023) / 1024 * 1024;
-    static constexpr uint32_t SMEM_MIN = 1024 + B_BYTES + STAGES * A_STAGE + 256;
+    // C >= 64: the epilogue stages the fp16 tile in two 128-row x 64-column (128-byte-swizzled) buffers and sends it out
+    // with TMA stores; per-thread row stores made the kernel epilogue-bound (4 K cycles per tile against 1.4 K of MMA)
+    static constexpr bool TSTORE = C >= 64;
+    static constexpr uint32_t OUT_BYTES = TSTORE ? 2 * 128 * 128 : 0;
+    static constexpr uint32_t OFF_OUT = B_BYTES + STAGES * A_STAGE;
+    static constexpr uint32_t SMEM_MIN = 1024 + B_BYTES + STAGES * A_STAGE + OUT_BYTES + 256;
     // every CTA allocates all 512 TMEM columns: never let two share an SM
     static constexpr uint32_t SMEM = SMEM_MIN < 120 * 1024 ? 120 * 1024 : SMEM_MIN;
 };
 
+#ifdef M2T_TIMING
+__device__ long long g_qkv_dbg[64];   // C = 256, CTA 0: [0] entry, [1] prologue done, [2] weight slab landed; per tile t < 6 at
+                                      // [8+8t..]: MMA warp before waits, first A block landed, MMAs issued; epilogue: acc ready, done
+#define M2T_QT(slot) do { if (C == 256 && blockIdx.x == 0 && lane == 0) g_qkv_dbg[(slot)] = clock64(); } while (0)
+#else
+#define M2T_QT(slot) do { } while (0)
+#endif
+
 template <int C>
 __global__ void __launch_bounds__(192, 1)
 qkv_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW,
-                __half* __restrict__ out, int M) {
+                const __grid_constant__ CUtensorMap mapO, __half* __restrict__ out, int M) {
     using CF = QkvCfg<C>;
     constexpr int NT = CF::NT, KB = CF::KB, STAGES = CF::STAGES, CB = CF::CB;
     extern __shared__ uint8_t smem_raw[];
@@ -47,7 +60,7 @@ qkv_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
     uint8_t* sB = sm;
     uint8_t* sA = sm + CF::B_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + CF::B_BYTES + STAGES * CF::A_STAGE);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + CF::B_BYTES + STAGES * CF::A_STAGE + CF::OUT_BYTES);
     uint64_t* full = bars;                 // [STAGES]
     uint64_t* empty = bars + STAGES;       // [STAGES]
     uint64_t* bfull = bars + 2 * STAGES;   // weights landed
@@ -59,6 +72,7 @@ qkv_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     const int chunk = blockIdx.x % CF::NCHUNK;
     const int first = blockIdx.x / CF::NCHUNK, stride = gridDim.x / CF::NCHUNK;
     const int num_mt = (M + 127) / 128;
+    if (warp == 0) M2T_QT(0);
 
     if (warp == 5) tmem_alloc(tmem_slot, 512);
     if (tid == 128) {
@@ -74,6 +88,7 @@ qkv_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     pdl_trigger();
+    if (warp == 0) M2T_QT(1);
 
     if (warp == 4) {
         // TMA producer: warp-uniform loop, one elected lane issues
@@ -99,14 +114,17 @@ qkv_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         constexpr uint32_t idesc = umma_idesc_f16(128, NT);
         constexpr uint64_t tmpl = umma_smem_desc(0, 16, CF::SBO, CF::LAYOUT);
         mbar_wait(bfull, 0);
+        M2T_QT(2);
         uint32_t it = 0, t = 0;
         for (int mt = first; mt < num_mt; mt += stride, ++t) {
             const uint32_t acc = t & 1, aph = (t >> 1) & 1;
+            if (t < 6) M2T_QT(8 + 8 * t);
             mbar_wait(&tempty[acc], aph ^ 1);
             tc_fence_after();
             for (int kb = 0; kb < KB; ++kb, ++it) {
                 const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
                 mbar_wait(&full[s], ph);
+                if (kb == 0 && t < 6) M2T_QT(8 + 8 * t + 1);
                 tc_fence_after();
                 if (elect_one_sync()) {
                     const uint64_t da0 = umma_desc_at(tmpl, base + CF::B_BYTES + s * CF::A_STAGE);
@@ -119,15 +137,51 @@ qkv_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 }
                 __syncwarp();
             }
+            if (t < 6) M2T_QT(8 + 8 * t + 2);
         }
     } else {
         pdl_wait();
-        uint32_t t = 0;
+        uint32_t t = 0, nblk = 0;
+        (void)nblk;
         for (int mt = first; mt < num_mt; mt += stride, ++t) {
             const uint32_t acc = t & 1, aph = (t >> 1) & 1;
             mbar_wait(&tfull[acc], aph);
             tc_fence_after();
+            if (warp == 0 && t < 6) M2T_QT(8 + 8 * t + 3);
             const int row = mt * 128 + warp * 32 + lane;
+            if constexpr (CF::TSTORE) {
+                // 64-column blocks through two staging buffers: TMEM -> fp16 -> swizzled smem row -> TMA store
+                const int trow = warp * 32 + lane;
+#pragma unroll 1
+                for (int blk = 0; blk < NT / 64; ++blk, ++nblk) {
+                    uint8_t* ob = sm + CF::OFF_OUT + (nblk & 1) * 16384;
+                    if (tid == 0) tma_store_wait_read1();          // the store that last used this buffer has read it
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        uint32_t r[32];
+                        tmem_ld32(tmem_base + acc * 256 + blk * 64 + hh * 32 + ((uint32_t)(warp * 32) << 16), r);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int v = 0; v < 4; ++v) {
+                            uint4 u;
+                            uint32_t* pu = reinterpret_cast<uint32_t*>(&u);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const __half2 h = __floats2half2_rn(__uint_as_float(r[v * 8 + 2 * e]), __uint_as_float(r[v * 8 + 2 * e + 1]));
+                                pu[e] = *reinterpret_cast<const uint32_t*>(&h);
+                            }
+                            *reinterpret_cast<uint4*>(ob + trow * 128 + (((hh * 4 + v) ^ (trow & 7)) << 4)) = u;
+                        }
+                    }
+                    fence_proxy_async();
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    if (tid == 0) {
+                        tma_store_2d(&mapO, ob, chunk * NT + blk * 64, mt * 128);     // rows past M are clipped
+                        tma_store_commit();
+                    }
+                }
+            } else {
             __half* orow = out + (long)row * (3 * C) + chunk * NT;
             constexpr int OCH = CF::OCH;
 #pragma unroll 1
@@ -151,15 +205,27 @@ qkv_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                     }
                 }
             }
+            }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);
+            if (warp == 0 && t < 6) M2T_QT(8 + 8 * t + 4);
         }
+        if (CF::TSTORE && tid == 0) tma_store_wait_all();
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 5) tmem_dealloc(tmem_base, 512);
 }
+
+#ifdef M2T_TIMING
+int read_qkv_timing(long long* host64) {
+    M2T_CUDA(cudaMemcpyFromSymbol(host64, g_qkv_dbg, sizeof(long long) * 64));
+    return M2T_OK;
+}
+#else
+int read_qkv_timing(long long* host64) { memset(host64, 0, sizeof(long long) * 64); return M2T_OK; }
+#endif
 
 template <int C>
 static int launch_qkv_umma_c(const __half* Z, const __half* Wqkv, __half* QKV, int M, cudaStream_t s) {
@@ -175,12 +241,18 @@ static int launch_qkv_umma_c(const __half* Z, const __half* Wqkv, __half* QKV, i
         const uint32_t box[2] = {(uint32_t)CF::CB, (uint32_t)CF::NT};
         M2T_TRY(make_tensor_map(&mapW, Wqkv, 2, 2, dims, str, box, CF::TMA_SWZ));
     }
+    CUtensorMap mapO = mapA;
+    if (CF::TSTORE) {
+        const uint64_t dims[2] = {(uint64_t)3 * C, (uint64_t)M}, str[2] = {2, (uint64_t)3 * C * 2};
+        const uint32_t box[2] = {64, 128};
+        M2T_TRY(make_tensor_map(&mapO, QKV, 2, 2, dims, str, box, 3));
+    }
     M2T_ENSURE_SMEM(qkv_umma_kernel<C>, CF::SMEM);
     const int num_mt = (M + 127) / 128;
     int per_chunk = device_sm_count() / CF::NCHUNK;
     if (per_chunk > num_mt) per_chunk = num_mt;
     if (per_chunk < 1) per_chunk = 1;
-    M2T_CUDA(launch_pdl(qkv_umma_kernel<C>, dim3(per_chunk * CF::NCHUNK), dim3(192), CF::SMEM, s, mapA, mapW, QKV, M));
+    M2T_CUDA(launch_pdl(qkv_umma_kernel<C>, dim3(per_chunk * CF::NCHUNK), dim3(192), CF::SMEM, s, mapA, mapW, mapO, QKV, M));
     return M2T_OK;
 }
 

@@ -17,7 +17,7 @@ lib.m2t_debug_attn_timing.argtypes = [C.POINTER(C.c_longlong)]
 
 def show(tag):
     torch.cuda.synchronize()
-    buf = (C.c_longlong * 384)()
+    buf = (C.c_longlong * 448)()
     _lib.check(lib.m2t_debug_attn_timing(buf), "timing")
     for br in range(4):
         t = list(buf)[64 * br: 64 * br + 64]

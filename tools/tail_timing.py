@@ -20,7 +20,7 @@ x = synthetic_input(16, 128, 128).cuda()
 for _ in range(3):
     m(x)
 torch.cuda.synchronize()
-buf = (C.c_longlong * 384)()
+buf = (C.c_longlong * 448)()
 _lib.check(lib.m2t_debug_attn_timing(buf), "timing")
 t = list(buf)[256:320]
 prev_end = None
