@@ -6,8 +6,10 @@
 //   tail_out_umma   : last 3x3 reflect conv 64 -> 3 (N padded to 16) as the same TMA-halo-tile implicit GEMM as the
 //                     ff conv, reading a tensor that carries a 1-pixel reflected border (so TMA never leaves it),
 //                     + clamp + crop, written straight into the caller's NCHW fp32 output.
-// GELU is the exact erf form of nn.GELU(); erf is evaluated with Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7,
-// far below the fp16 rounding of the stored activation) because the libm erff costs ~3x more issue slots.
+// GELU is the exact erf form of nn.GELU(), evaluated two at a time on the packed fp32x2 pipe (gelu.cuh).
+// A variant of tail_up that staged the output in shared memory and sent it out with TMA stores (one per 32-pixel segment
+// and output row) was measured SLOWER (cfg2 +20 us, cfg3 +3 %): the per-unit barrier and the wait for the store to read
+// the staging tile cost more than the per-thread 32-byte stores they replaced.
 #include "common.cuh"
 #include "gelu.cuh"
 #include "tma.cuh"
