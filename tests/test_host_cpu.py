@@ -126,3 +126,46 @@ def test_product_package_does_not_import_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.replace("no oracle", ""), os.path.join(dirpath, f)
+
+
+def _fake_replica(module):
+    """What torch.nn.parallel.replicate() does to every module of a replica, without needing CUDA: shallow __dict__
+    copy, EMPTY _parameters, the (here: same) tensors as plain attributes and in _former_parameters."""
+    import collections
+    mods = list(module.modules())
+    copies = [m._replicate_for_data_parallel() for m in mods]
+    index = {m: i for i, m in enumerate(mods)}
+    for m, r in zip(mods, copies):
+        r._former_parameters = collections.OrderedDict()
+        for key, child in m._modules.items():
+            if child is not None:
+                setattr(r, key, copies[index[child]])
+        for key, p in m._parameters.items():
+            if p is None:
+                r._parameters[key] = None
+            else:
+                t = p.detach()
+                setattr(r, key, t)
+                r._former_parameters[key] = t
+    return copies[0]
+
+
+def test_parameter_discovery_on_dataparallel_replicas():
+    """ref test.py:68 wraps the model in nn.DataParallel over all visible GPUs; a replica's state_dict() is empty, so
+    the engine must find the broadcast copies through _former_parameters, in state_dict order."""
+    import types
+    from m2trans_b200.M2Trans_network import M2Trans
+    from m2trans_b200._params import is_replica, state_tensors
+    from m2trans_b200.rlutrans import TransBlock
+    m = M2Trans(types.SimpleNamespace(scale=4, rgb_range=1.0, colors=3, n_feats=64, n_blocks=8))
+    want = [p for _, p in m.state_dict(keep_vars=True).items()]
+    assert all(a is b for a, b in zip(m._param_list(), want)) and len(want) == 123
+    rep = _fake_replica(m)
+    assert len(rep.state_dict()) == 0 and is_replica(rep) and not is_replica(m)
+    got = rep._param_list()
+    assert len(got) == 123 and all(a.data_ptr() == b.data_ptr() and a.shape == b.shape for a, b in zip(got, want))
+    assert m._param_list()[0] is want[0]                       # the original's cached slots are not the replica's
+    tb = TransBlock()
+    tw = [p for _, p in tb.state_dict(keep_vars=True).items()]
+    tr = state_tensors(_fake_replica(tb))
+    assert len(tr) == 12 and all(a.data_ptr() == b.data_ptr() for a, b in zip(tr, tw))
