@@ -67,7 +67,15 @@ __global__ void pack_kernel(int mode, const float* __restrict__ src, const float
         } break;
         case PK_CONV3_W: {  // i over dst [9][Opad=p1][64]; p0 = real O
             const int c = i % NF, o = (i / NF) % p1, tap = i / (NF * p1);
-            reinterpret_cast<__half*>(dstv)[i] = o < p0 ? __float2half_rn(src[(o * NF + c) * 9 + tap]) : __half(0);
+            // scale != 0 (the tail's final conv, p0 = 3 of 16 rows): rows p0..2*p0-1 carry the fp16 rounding residual of
+            // rows 0..p0-1 times `scale` (2^11); tail_out_umma adds them back, the other consumers read rows < p0 only
+            __half v = __half(0);
+            if (o < p0) v = __float2half_rn(src[(o * NF + c) * 9 + tap]);
+            else if (scale != 0.f && o < 2 * p0) {
+                const float wv = src[((o - p0) * NF + c) * 9 + tap];
+                v = __float2half_rn((wv - __half2float(__float2half_rn(wv))) * scale);
+            }
+            reinterpret_cast<__half*>(dstv)[i] = v;
         } break;
         case PK_CONV3_W2: { // i over dst [2][9][64][64]
             const int c = i % NF, row = (i / NF) % NF, tap = (i / (NF * NF)) % 9, hh = i / (NF * NF * 9);
@@ -174,7 +182,7 @@ int pack_weights_impl(const PackedLayout& L, const float* const* P, int n_params
             M2T_TRY(run_pack(PK_COPY_F32, relw, nullptr, packed + A.relf + (size_t)10 * hc * 4, 10 * hc, 0, 0, 1.f, s));
             M2T_TRY(run_pack(PK_RELX, relh, relw, packed + A.relx, 32 * C, C, 0, 1.f, s));
         }
-        M2T_TRY(run_pack(PK_CONV3_W, P[base + 12], nullptr, packed + L.blk[i].ffw, 9 * NF * NF, NF, NF, 1.f, s));
+        M2T_TRY(run_pack(PK_CONV3_W, P[base + 12], nullptr, packed + L.blk[i].ffw, 9 * NF * NF, NF, NF, 0.f, s));
         M2T_TRY(run_pack(PK_CONV3_W2, P[base + 12], nullptr, packed + L.blk[i].ffw2, 2 * 9 * NF * NF, 0, 0, 1.f, s));
         M2T_TRY(run_pack(PK_COPY_F32, P[base + 13], nullptr, packed + L.blk[i].ffb, NF, 0, 0, 1.f, s));
     }
@@ -185,9 +193,9 @@ int pack_weights_impl(const PackedLayout& L, const float* const* P, int n_params
     if (L.scale == 4) {
         M2T_TRY(run_pack(PK_UP_W, P[tb + 2], nullptr, packed + L.t3w, 256 * NF, 4, 0, 1.f, s));
         M2T_TRY(run_pack(PK_UP_B, P[tb + 3], nullptr, packed + L.t3b, 256, 4, 0, 1.f, s));
-        M2T_TRY(run_pack(PK_CONV3_W, P[tb + 4], nullptr, packed + L.tcw, 9 * 16 * NF, 3, 16, 1.f, s));
+        M2T_TRY(run_pack(PK_CONV3_W, P[tb + 4], nullptr, packed + L.tcw, 9 * 16 * NF, 3, 16, 2048.f, s));
     } else {
-        M2T_TRY(run_pack(PK_CONV3_W, P[tb + 2], nullptr, packed + L.tcw, 9 * 16 * NF, 3, 16, 1.f, s));
+        M2T_TRY(run_pack(PK_CONV3_W, P[tb + 2], nullptr, packed + L.tcw, 9 * 16 * NF, 3, 16, 2048.f, s));
     }
     return M2T_OK;
 }

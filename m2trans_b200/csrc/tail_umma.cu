@@ -312,7 +312,9 @@ tail_out_umma_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_cons
             if (oy < hout && ox < wout) {
                 float* yp = y + (long)(b0 + bl) * 3 * plane + (long)oy * wout + ox;
 #pragma unroll
-                for (int o = 0; o < 3; ++o) yp[o * plane] = fminf(fmaxf(__uint_as_float(rr[o]), 0.f), rgb_range);
+                for (int o = 0; o < 3; ++o)     // columns 3..5: the weights' fp16 rounding residual x 2^11 (pack.cu)
+                    yp[o * plane] = fminf(fmaxf(__uint_as_float(rr[o]) + __uint_as_float(rr[3 + o]) * (1.f / 2048.f),
+                                                0.f), rgb_range);
             }
         }
     }

@@ -185,8 +185,9 @@ def test_stage_ffconv_tensor_core_vs_cuda_core(B, Hp, Wp):
 @pytest.mark.parametrize("scale,shape", [(4, (2, 3, 40, 72)), (2, (1, 3, 96, 72)), (4, (1, 3, 128, 128)), (2, (3, 3, 33, 100))])
 def test_fused_tail_equals_two_kernel_tail(scale, shape):
     """x2/x4 default: the last PixelShuffle stage + 3x3 conv run as one kernel (tail_fused.cu); the unfused
-    variant keeps the 4x-resolution tensor in HBM.  Same operands and roundings, only the fp32 summation order of
-    the 9 taps differs."""
+    variant keeps the 4x-resolution tensor in HBM.  Same activations and roundings; the two-kernel conv also adds
+    the fp16 rounding residual of its weights (pack.cu, PK_CONV3_W), so the two differ by that term (~5e-5 rms) and
+    by the fp32 summation order of the 9 taps; an indexing or border bug would be 1e-2 or more."""
     from m2trans_b200 import _lib
     from m2trans_b200.synthetic import synthetic_input
     x = synthetic_input(shape[0], shape[2], shape[3], seed=5).cuda()
@@ -194,7 +195,7 @@ def test_fused_tail_equals_two_kernel_tail(scale, shape):
     y_u = _model(scale, 3, variant=_lib.VAR_UNFUSED_TAIL)(x)
     d = float((y_f - y_u).abs().max())
     print(f"x{scale} {shape}: fused vs unfused tail max-abs {d:.2e}")
-    assert d <= 2e-6
+    assert d <= 4e-4
 
 
 @pytest.mark.parametrize("name,scale,shape,probe", [("cfg3", 3, (32, 3, 200, 266), 31), ("cfg4", 4, (64, 3, 270, 480), 63)])
