@@ -182,6 +182,47 @@ size_t m2t_transblock_workspace_bytes(int B, int N, int dim);
 int m2t_transblock_forward(const float* d_x, float* d_y, const float* const* d_params, int n_params,
                            int B, int N, int dim, int num_heads, void* d_workspace, void* stream);
 
+/* ---- MedCLIP image-embedding pass ------------------------------------------
+ * Replaces the image side of SemanticLoss.__call__ (ref losses.py:53-54 bicubic resize to 224x224 with
+ * align_corners=True, :68-69 medmodel.encode_image, :71-72 L2 normalise, :76-77 dot with the normalised text
+ * feature).  encode_image is third-party (medclip's MedCLIPVisionModelViT = Swin-T
+ * 'microsoft/swin-tiny-patch4-window7-224' -> pooler_output [B,768] -> Linear(768,512,bias=False)); the
+ * architecture follows transformers/models/swin/modeling_swin.py.  bf16 tensor-core GEMMs, fp32 residual stream.
+ * Parameters: HOST array of m2t_clip_param_count() = 220 DEVICE fp32 tensors: SwinModel.state_dict() order without
+ * the relative_position_index buffers (patch projection weight/bias, embeddings norm; per block layernorm_before,
+ * relative_position_bias_table, query/key/value weight+bias, attention.output.dense, layernorm_after,
+ * intermediate.dense, output.dense; per stage downsample.reduction.weight, downsample.norm; final layernorm), then
+ * projection_head.weight [512][768].
+ * m2t_clip_encode_image: d_img fp32 [B][3][H][W] (values as the SR network returns them, no mean/std
+ * normalisation: the reference applies none); d_embed fp32 [B][512] L2-normalised; d_text fp32 [512] (any norm)
+ * and d_logits fp32 [B] are both given or both NULL; d_workspace m2t_clip_workspace_bytes(B) bytes, 1024-byte
+ * aligned. */
+int m2t_clip_param_count(void);
+size_t m2t_clip_packed_bytes(void);
+size_t m2t_clip_workspace_bytes(int B);
+int m2t_clip_pack_weights(const float* const* d_params, int n_params, void* d_packed, void* stream);
+int m2t_clip_encode_image(const void* d_packed, const float* d_img, int B, int H, int W, float* d_embed,
+                          const float* d_text, float* d_logits, void* d_workspace, void* stream);
+/* One Linear of the tower on its own (stage-level tests): out = epilogue(A W^T + bias), A bf16 [M][K], W bf16 [N][K]
+ * (nn.Linear layout), bias fp32 [N] or NULL.  epilogue 0: bf16 [M][N]; 1: GELU, bf16; 2: fp32 [M][N] += (the residual
+ * form); 3: fp32 [M][N] =.  K a multiple of 8, N a multiple of 32; neither needs to be a multiple of the 128 x 128 x 64
+ * tile. */
+int m2t_clip_stage_linear(int epilogue, const void* d_a, const void* d_w, const float* d_bias, void* d_out,
+                          int M, int N, int K, void* stream);
+/* The other kernels of the tower on their own (stage-level tests; the end-to-end embedding of a random-weight tower
+ * only resolves errors above ~1e-3, these resolve an indexing slip exactly).
+ * resize: d_img fp32 [B][3][H][W] -> d_rows bf16 [B*56*56][48], the 4x4 patch rows (column c*16 + ky*4 + kx) of the
+ *   bicubic, align_corners=True, 224x224 image (ref losses.py:53).
+ * layernorm: d_x fp32 tokens [B*h*w][C] -> bf16; merge = 0: LayerNorm(C) per token; merge = 1: the 2x2 patch-merging
+ *   gather, [B*h*w/4][4C], LayerNorm(4C) (modeling_swin.py:333-343).
+ * attention: d_qkv bf16 [B*h*w][3C] (q | k | v, head-major 32-wide slices) -> d_out bf16 [B*h*w][C]; d_bias fp32
+ *   [heads][49][49] (the gathered relative-position table); shift 0 or 3 (cyclic shift + region mask, :556-582, :615). */
+int m2t_clip_stage_resize(const float* d_img, void* d_rows, int B, int H, int W, void* stream);
+int m2t_clip_stage_layernorm(const float* d_x, void* d_out, const float* d_gamma, const float* d_beta, int B,
+                             int h, int w, int C, int merge, void* stream);
+int m2t_clip_stage_attention(const void* d_qkv, void* d_out, const float* d_bias, int B, int h, int w, int C,
+                             int heads, int shift, void* stream);
+
 /* ---- hardware probes (development aids; tests/test_probes.py) ---------------------------
  * m2t_probe_umma: copies two raw shared-memory images (A, B operands), issues k_steps
  * tcgen05.mma (kind::f16, cta_group::1, M=128) with the given 64-bit shared-memory

@@ -68,6 +68,15 @@ SIGNATURES = {
     "m2t_stage_tail": (_i, [_u32, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp]),
     "m2t_transblock_workspace_bytes": (_sz, [_i, _i, _i]),
     "m2t_transblock_forward": (_i, [_vp, _vp, C.POINTER(_vp), _i, _i, _i, _i, _i, _vp, _vp]),
+    "m2t_clip_param_count": (_i, []),
+    "m2t_clip_packed_bytes": (_sz, []),
+    "m2t_clip_workspace_bytes": (_sz, [_i]),
+    "m2t_clip_pack_weights": (_i, [C.POINTER(_vp), _i, _vp, _vp]),
+    "m2t_clip_encode_image": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "m2t_clip_stage_linear": (_i, [_i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "m2t_clip_stage_resize": (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    "m2t_clip_stage_layernorm": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "m2t_clip_stage_attention": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "m2t_probe_umma": (_i, [_vp, _u32, _vp, _u32, _u64, _u64, _u32, _u32, _i, _u32, _i, _vp, _vp]),
     "m2t_debug_attn_timing": (_i, [C.POINTER(C.c_longlong)]),
     "m2t_debug_profile_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_char_p, _sz]),

@@ -1,0 +1,16 @@
+// MedCLIP image tower (Swin-T + projection head): shared declarations.
+#pragma once
+#include "common.cuh"
+
+namespace m2t {
+
+// epilogues of launch_lin_umma (lin_umma.cu)
+enum { LIN_BF16 = 0, LIN_GELU_BF16 = 1, LIN_ADD_F32 = 2, LIN_F32 = 3 };
+int launch_lin_umma(int epi, const void* A, const void* W, const float* bias, void* out, int M, int N, int K,
+                    cudaStream_t s);
+
+constexpr int CL_IMG = 224, CL_PATCH = 4, CL_GRID = 56, CL_EMBED = 96, CL_WIN = 7, CL_WT = 49, CL_HD = 32;
+constexpr int CL_STAGES = 4, CL_FEAT = 768, CL_PROJ = 512, CL_NPARAMS = 220;
+constexpr float CL_LN_EPS = 1e-5f;
+
+}  // namespace m2t

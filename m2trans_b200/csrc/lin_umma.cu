@@ -1,0 +1,242 @@
+// tcgen05 bf16 GEMM for the Linear layers of the MedCLIP image tower (Swin-T):
+//   Y[m][n] = epilogue( sum_k A[m][k] * W[n][k] + bias[n] )      A bf16 [M][K], W bf16 [N][K] (nn.Linear layout)
+// Persistent, warp-specialised CTAs (192 threads), tiles of 128 rows x 128 columns, K in blocks of 64 (128-byte swizzle):
+//   warp 4   : TMA producer, ring of LG_STAGES {A block, W block} stages.  K, M and N need not be multiples of the tile:
+//              the tensor maps zero-fill out-of-range elements (K = 96 -> a 64 block and a 32 + 32 zero block; only the
+//              MMAs that touch real columns are issued), and the TMA stores clip rows >= M and columns >= N
+//   warp 5   : single-thread tcgen05.mma issue, M=128 x N=128 x K=16, fp32 accumulators in TMEM (two of 128 columns: the
+//              epilogue of tile i overlaps the MMAs of tile i+1)
+//   warps 0-3: epilogue -- tcgen05.ld, + bias, optional GELU, conversion, 128-byte swizzled staging rows, TMA store.  The
+//              residual form (X += Y) is a TMA reduce-add store of the fp32 tile: the read-modify-write happens in L2 and
+//              every element receives exactly one addend per GEMM, so the result does not depend on scheduling.
+#include <cuda_bf16.h>
+
+#include "clip.cuh"
+#include "tma.cuh"
+#include "umma.cuh"
+
+namespace m2t {
+
+constexpr int LG_BN = 128, LG_STAGES = 5;
+constexpr uint32_t LG_A = 128 * 128, LG_B = LG_BN * 128, LG_STAGE = LG_A + LG_B;
+constexpr uint32_t LG_OUT = 2 * 16384;
+constexpr uint32_t LG_OFF_OUT = LG_STAGES * LG_STAGE;
+constexpr uint32_t LG_SMEM = 1024 + LG_STAGES * LG_STAGE + LG_OUT + 256;
+
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+                 :: "l"(m), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1) : "memory");
+}
+
+// exact-erf GELU (HF ACT2FN["gelu"]) in the erfc form of gelu.cuh, fp32 result
+__device__ __forceinline__ float gelu_erfc(float x) {
+    const float a = fabsf(x);
+    float p = fmaf(9.250150469597429e-05f, a, -9.215229511028156e-05f);
+    p = fmaf(p, a, 0.00345434108749032f);
+    p = fmaf(p, a, 0.02103373408317566f);
+    p = fmaf(p, a, 0.04988996684551239f);
+    p = fmaf(p, a, 1.f);
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(p));
+    r *= r; r *= r; r *= r; r *= r;
+    return fmaf(a * r, -0.5f, fmaxf(x, 0.f));
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+    const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&v);
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(192, 1)
+lin_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW,
+                const __grid_constant__ CUtensorMap mapO, const float* __restrict__ bias, int M, int N, int K) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + LG_OFF_OUT + LG_OUT);
+    uint64_t* full = bars;                        // [STAGES]
+    uint64_t* empty = bars + LG_STAGES;           // [STAGES]
+    uint64_t* tfull = bars + 2 * LG_STAGES;       // [2] accumulator ready
+    uint64_t* tempty = bars + 2 * LG_STAGES + 2;  // [2] accumulator drained
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * LG_STAGES + 4);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int num_mt = (M + 127) / 128, num_nt = (N + LG_BN - 1) / LG_BN, num_t = num_mt * num_nt;
+    const int KB = (K + 63) / 64;
+
+    if (warp == 5) tmem_alloc(tmem_slot, 256);
+    if (tid == 128) {
+        for (int s = 0; s < LG_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+        mbar_fence_init();
+        tma_prefetch_desc(&mapA);
+        tma_prefetch_desc(&mapW);
+        tma_prefetch_desc(&mapO);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_trigger();
+
+    if (warp == 4) {
+        pdl_wait();
+        uint32_t it = 0;
+        for (int t = blockIdx.x; t < num_t; t += gridDim.x) {
+            const int mt = t / num_nt, nt = t - mt * num_nt;
+            for (int kb = 0; kb < KB; ++kb, ++it) {
+                const uint32_t s = it % LG_STAGES, ph = (it / LG_STAGES) & 1;
+                mbar_wait(&empty[s], ph ^ 1);
+                if (elect_one_sync()) {
+                    mbar_expect_tx(&full[s], LG_STAGE);
+                    tma_load_2d(sm + s * LG_STAGE, &mapA, &full[s], kb * 64, mt * 128);
+                    tma_load_2d(sm + s * LG_STAGE + LG_A, &mapW, &full[s], kb * 64, nt * LG_BN);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp == 5) {
+        constexpr uint32_t idesc = umma_idesc_f16(128, LG_BN, 0, 0, 1);
+        constexpr uint64_t tmpl = umma_smem_desc(0, 16, 1024, UMMA_LAYOUT_SW128);
+        uint32_t it = 0, tl = 0;
+        for (int t = blockIdx.x; t < num_t; t += gridDim.x, ++tl) {
+            const uint32_t acc = tl & 1, aph = (tl >> 1) & 1;
+            mbar_wait(&tempty[acc], aph ^ 1);
+            tc_fence_after();
+            for (int kb = 0; kb < KB; ++kb, ++it) {
+                const uint32_t s = it % LG_STAGES, ph = (it / LG_STAGES) & 1;
+                mbar_wait(&full[s], ph);
+                tc_fence_after();
+                if (elect_one_sync()) {
+                    const uint64_t da0 = umma_desc_at(tmpl, base + s * LG_STAGE);
+                    const uint64_t db0 = umma_desc_at(tmpl, base + s * LG_STAGE + LG_A);
+                    const int rem = K - kb * 64, ks = rem >= 64 ? 4 : (rem + 15) / 16;
+                    for (int k = 0; k < ks; ++k)
+                        umma_f16_ss(tmem_base + acc * LG_BN, da0 + 2 * k, db0 + 2 * k, idesc, (kb | k) ? 1u : 0u);
+                    umma_commit(&empty[s]);
+                    if (kb == KB - 1) umma_commit(&tfull[acc]);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        pdl_wait();
+        constexpr bool F32 = EPI == LIN_ADD_F32 || EPI == LIN_F32;
+        constexpr int BLKC = F32 ? 32 : 64;              // columns per 128-byte staging row
+        const int trow = warp * 32 + lane;
+        uint32_t tl = 0, nblk = 0;
+        for (int t = blockIdx.x; t < num_t; t += gridDim.x, ++tl) {
+            const int mt = t / num_nt, nt = t - mt * num_nt;
+            const uint32_t acc = tl & 1, aph = (tl >> 1) & 1;
+            mbar_wait(&tfull[acc], aph);
+            tc_fence_after();
+#pragma unroll 1
+            for (int blk = 0; blk < LG_BN / BLKC; ++blk) {
+                const int col0 = nt * LG_BN + blk * BLKC;
+                if (col0 >= N) break;                    // uniform
+                uint8_t* ob = sm + LG_OFF_OUT + (nblk & 1) * 16384;
+                if (tid == 0) tma_store_wait_read1();    // the store that last used this buffer has read it
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+                for (int hh = 0; hh < BLKC / 32; ++hh) {
+                    uint32_t r[32];
+                    tmem_ld32(tmem_base + acc * LG_BN + blk * BLKC + hh * 32 + ((uint32_t)(warp * 32) << 16), r);
+                    tmem_ld_wait();
+                    const int c = col0 + hh * 32;
+                    const bool live = c < N;             // N is a multiple of 32: a 32-column group is all in or all out
+                    float v[32];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (bias != nullptr && live) b4 = __ldg(reinterpret_cast<const float4*>(bias + c) + q);
+                        v[4 * q + 0] = __uint_as_float(r[4 * q + 0]) + b4.x;
+                        v[4 * q + 1] = __uint_as_float(r[4 * q + 1]) + b4.y;
+                        v[4 * q + 2] = __uint_as_float(r[4 * q + 2]) + b4.z;
+                        v[4 * q + 3] = __uint_as_float(r[4 * q + 3]) + b4.w;
+                    }
+                    if constexpr (EPI == LIN_GELU_BF16) {
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) v[e] = gelu_erfc(v[e]);
+                    }
+                    if constexpr (F32) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q)
+                            *reinterpret_cast<float4*>(ob + trow * 128 + ((q ^ (trow & 7)) << 4)) =
+                                make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            uint4 u;
+                            u.x = pack_bf16x2(v[8 * q + 0], v[8 * q + 1]);
+                            u.y = pack_bf16x2(v[8 * q + 2], v[8 * q + 3]);
+                            u.z = pack_bf16x2(v[8 * q + 4], v[8 * q + 5]);
+                            u.w = pack_bf16x2(v[8 * q + 6], v[8 * q + 7]);
+                            *reinterpret_cast<uint4*>(ob + trow * 128 + (((hh * 4 + q) ^ (trow & 7)) << 4)) = u;
+                        }
+                    }
+                }
+                fence_proxy_async();
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (tid == 0) {
+                    if constexpr (EPI == LIN_ADD_F32) tma_reduce_add_2d(&mapO, ob, col0, mt * 128);
+                    else tma_store_2d(&mapO, ob, col0, mt * 128);
+                    tma_store_commit();
+                }
+                ++nblk;
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+        }
+        if (tid == 0) tma_store_wait_all();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) tmem_dealloc(tmem_base, 256);
+}
+
+template <int EPI>
+static int launch_lin_epi(const void* A, const void* W, const float* bias, void* out, int M, int N, int K, cudaStream_t s) {
+    CUtensorMap mapA, mapW, mapO;
+    {
+        const uint64_t dims[2] = {(uint64_t)K, (uint64_t)M}, str[2] = {2, (uint64_t)K * 2};
+        const uint32_t box[2] = {64, 128};
+        M2T_TRY(make_tensor_map(&mapA, A, 2, 2, dims, str, box, 3));
+    }
+    {
+        const uint64_t dims[2] = {(uint64_t)K, (uint64_t)N}, str[2] = {2, (uint64_t)K * 2};
+        const uint32_t box[2] = {64, (uint32_t)LG_BN};
+        M2T_TRY(make_tensor_map(&mapW, W, 2, 2, dims, str, box, 3));
+    }
+    {
+        constexpr bool F32 = EPI == LIN_ADD_F32 || EPI == LIN_F32;
+        const int eb = F32 ? 4 : 2;
+        const uint64_t dims[2] = {(uint64_t)N, (uint64_t)M}, str[2] = {(uint64_t)eb, (uint64_t)N * eb};
+        const uint32_t box[2] = {(uint32_t)(F32 ? 32 : 64), 128};
+        M2T_TRY(make_tensor_map(&mapO, out, eb, 2, dims, str, box, 3));
+    }
+    M2T_ENSURE_SMEM(lin_umma_kernel<EPI>, LG_SMEM);
+    const int num_t = cdiv(M, 128) * cdiv(N, LG_BN);
+    int grid = device_sm_count();
+    if (grid > num_t) grid = num_t;
+    M2T_CUDA(launch_pdl(lin_umma_kernel<EPI>, dim3(grid), dim3(192), LG_SMEM, s, mapA, mapW, mapO, bias, M, N, K));
+    return M2T_OK;
+}
+
+// A bf16 [M][K], W bf16 [N][K], bias fp32 [N] or null; out: bf16 [M][N] (LIN_BF16, LIN_GELU_BF16) or fp32 [M][N]
+// (LIN_F32 overwrites, LIN_ADD_F32 accumulates).  K a multiple of 8 (16-byte rows), N a multiple of 32.
+int launch_lin_umma(int epi, const void* A, const void* W, const float* bias, void* out, int M, int N, int K,
+                    cudaStream_t s) {
+    if (M < 1 || N < 32 || N % 32 || K < 16 || K % 8) { set_error("lin_umma: bad shape M %d N %d K %d", M, N, K); return M2T_E_ARG; }
+    switch (epi) {
+        case LIN_BF16: return launch_lin_epi<LIN_BF16>(A, W, bias, out, M, N, K, s);
+        case LIN_GELU_BF16: return launch_lin_epi<LIN_GELU_BF16>(A, W, bias, out, M, N, K, s);
+        case LIN_ADD_F32: return launch_lin_epi<LIN_ADD_F32>(A, W, bias, out, M, N, K, s);
+        case LIN_F32: return launch_lin_epi<LIN_F32>(A, W, bias, out, M, N, K, s);
+    }
+    set_error("lin_umma: unknown epilogue %d", epi);
+    return M2T_E_ARG;
+}
+
+}  // namespace m2t
