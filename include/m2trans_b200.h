@@ -216,7 +216,9 @@ int m2t_clip_stage_linear(int epilogue, const void* d_a, const void* d_w, const 
  * layernorm: d_x fp32 tokens [B*h*w][C] -> bf16; merge = 0: LayerNorm(C) per token; merge = 1: the 2x2 patch-merging
  *   gather, [B*h*w/4][4C], LayerNorm(4C) (modeling_swin.py:333-343).
  * attention: d_qkv bf16 [B*h*w][3C] (q | k | v, head-major 32-wide slices) -> d_out bf16 [B*h*w][C]; d_bias fp32
- *   [heads][49][49] (the gathered relative-position table); shift 0 or 3 (cyclic shift + region mask, :556-582, :615). */
+ *   [heads][49][56]: the gathered relative-position table with rows padded to 56 and -1e30 in columns 49..55 (the
+ *   kernel's key tiles are 7 x 8 wide; the pad masks the 7 phantom keys); shift 0 or 3 (cyclic shift + region mask,
+ *   :556-582, :615); heads a multiple of 3. */
 int m2t_clip_stage_resize(const float* d_img, void* d_rows, int B, int H, int W, void* stream);
 int m2t_clip_stage_layernorm(const float* d_x, void* d_out, const float* d_gamma, const float* d_beta, int B,
                              int h, int w, int C, int merge, void* stream);

@@ -49,7 +49,7 @@ ClipLayout clip_layout() {
             ClipBlockW& W = L.blk[bi];
             W.ln1g = take(C * 4); W.ln1b = take(C * 4);
             W.wqkv = take(3 * C * C * 2); W.bqkv = take(3 * C * 4);
-            W.rpb = take((size_t)kHeads[s] * CL_WT * CL_WT * 4);
+            W.rpb = take((size_t)kHeads[s] * CL_WT * CL_RPB_PITCH * 4);
             W.wo = take(C * C * 2); W.bo = take(C * 4);
             W.ln2g = take(C * 4); W.ln2b = take(C * 4);
             W.w1 = take(4 * C * C * 2); W.b1 = take(4 * C * 4);
@@ -71,10 +71,10 @@ __global__ void clip_pack_kernel(int mode, const float* __restrict__ src, void* 
     switch (mode) {
         case CPK_F32: static_cast<float*>(dst)[i] = src[i]; break;
         case CPK_BF16: static_cast<__nv_bfloat16*>(dst)[i] = __float2bfloat16_rn(src[i]); break;
-        case CPK_RPB: {   // dst [heads = p0][49][49] from the table [169][heads] (modeling_swin.py:398-428)
-            const int j = (int)(i % CL_WT), q = (int)(i / CL_WT) % CL_WT, hd = (int)(i / (CL_WT * CL_WT));
+        case CPK_RPB: {   // dst [heads = p0][49][56] from the table [169][heads] (modeling_swin.py:398-428); pad columns -1e30
+            const int j = (int)(i % CL_RPB_PITCH), q = (int)(i / CL_RPB_PITCH) % CL_WT, hd = (int)(i / (CL_WT * CL_RPB_PITCH));
             const int idx = (q / CL_WIN - j / CL_WIN + CL_WIN - 1) * (2 * CL_WIN - 1) + (q % CL_WIN - j % CL_WIN + CL_WIN - 1);
-            static_cast<float*>(dst)[i] = src[idx * p0 + hd];
+            static_cast<float*>(dst)[i] = j < CL_WT ? src[idx * p0 + hd] : -1.0e30f;
         } break;
         case CPK_PROJ_T: {  // dst [768][512] from the head's weight [512][768]
             const int nn = (int)(i % CL_PROJ), k = (int)(i / CL_PROJ);
@@ -203,98 +203,6 @@ int launch_ln_merge(const float* X, __nv_bfloat16* out, const float* g, const fl
     }
     set_error("clip merge LN: channel count %d", C);
     return M2T_E_UNSUPPORTED;
-}
-
-// ---- window attention (modeling_swin.py:430-487, 598-640) ------------------------------------------------------------
-// One CTA per (image, window, head); thread i < 49 owns query token i of the window.  The cyclic shift of the odd layers,
-// the window partition and their inverses are index arithmetic on the token-major tensors; the shift mask (-100 between
-// tokens from different sides of the wrap, :556-582) is recomputed from the region ids.
-__device__ __forceinline__ void load32_bf16(const __nv_bfloat16* p, float* f, float scale) {
-    uint4 a, b;
-#pragma unroll
-    for (int hh = 0; hh < 2; ++hh) {
-        ldg256(p + 16 * hh, a, b);
-        const uint32_t u[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {      // bf16 -> fp32 is a 16-bit shift
-            f[16 * hh + 2 * e] = __uint_as_float(u[e] << 16) * scale;
-            f[16 * hh + 2 * e + 1] = __uint_as_float(u[e] & 0xffff0000u) * scale;
-        }
-    }
-}
-
-__global__ void __launch_bounds__(64)
-clip_attn_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, const float* __restrict__ rpb,
-                 int h, int w, int C, int shift) {
-    __shared__ __align__(16) float sK[CL_WT][CL_HD];
-    __shared__ __align__(16) float sV[CL_WT][CL_HD];
-    __shared__ int sId[CL_WT];
-    pdl_wait();
-    const int head = blockIdx.y, nwx = w / CL_WIN, nW = (h / CL_WIN) * nwx;
-    const int bimg = blockIdx.x / nW, wi = blockIdx.x - bimg * nW, wy = wi / nwx, wx = wi - wy * nwx;
-    const int i = threadIdx.x;
-    long row = 0;
-    float q[CL_HD];
-    if (i < CL_WT) {
-        const int y = wy * CL_WIN + i / CL_WIN, x = wx * CL_WIN + i % CL_WIN;     // coordinates in the shifted frame
-        int gy = y + shift, gx = x + shift;
-        if (gy >= h) gy -= h;
-        if (gx >= w) gx -= w;
-        row = ((long)bimg * h + gy) * w + gx;
-        const __nv_bfloat16* p = qkv + row * 3 * C + head * CL_HD;
-        load32_bf16(p, q, 0.17677669529663687f);        // head_dim^-1/2 (:462)
-        load32_bf16(p + C, sK[i], 1.f);
-        load32_bf16(p + 2 * C, sV[i], 1.f);
-        const int idy = y < h - CL_WIN ? 0 : (y < h - shift ? 1 : 2), idx = x < w - CL_WIN ? 0 : (x < w - shift ? 1 : 2);
-        sId[i] = idy * 3 + idx;
-    }
-    __syncthreads();
-    if (i >= CL_WT) return;
-    const float* bp = rpb + ((long)head * CL_WT + i) * CL_WT;
-    const int myid = sId[i];
-    float p[CL_WT];
-    float mx = -3.0e38f;
-#pragma unroll
-    for (int j = 0; j < CL_WT; ++j) {
-        float s = 0.f;
-#pragma unroll
-        for (int d4 = 0; d4 < CL_HD / 4; ++d4) {
-            const float4 k4 = *reinterpret_cast<const float4*>(&sK[j][4 * d4]);
-            s = fmaf(q[4 * d4], k4.x, s); s = fmaf(q[4 * d4 + 1], k4.y, s);
-            s = fmaf(q[4 * d4 + 2], k4.z, s); s = fmaf(q[4 * d4 + 3], k4.w, s);
-        }
-        s += __ldg(bp + j);
-        if (shift && sId[j] != myid) s -= 100.f;
-        p[j] = s;
-        mx = fmaxf(mx, s);
-    }
-    float sum = 0.f;
-#pragma unroll
-    for (int j = 0; j < CL_WT; ++j) { p[j] = __expf(p[j] - mx); sum += p[j]; }
-    float o[CL_HD];
-#pragma unroll
-    for (int d = 0; d < CL_HD; ++d) o[d] = 0.f;
-#pragma unroll
-    for (int j = 0; j < CL_WT; ++j) {
-#pragma unroll
-        for (int d4 = 0; d4 < CL_HD / 4; ++d4) {
-            const float4 v4 = *reinterpret_cast<const float4*>(&sV[j][4 * d4]);
-            o[4 * d4] = fmaf(p[j], v4.x, o[4 * d4]); o[4 * d4 + 1] = fmaf(p[j], v4.y, o[4 * d4 + 1]);
-            o[4 * d4 + 2] = fmaf(p[j], v4.z, o[4 * d4 + 2]); o[4 * d4 + 3] = fmaf(p[j], v4.w, o[4 * d4 + 3]);
-        }
-    }
-    const float inv = 1.f / sum;
-    __nv_bfloat16* op = out + row * C + head * CL_HD;
-#pragma unroll
-    for (int hh = 0; hh < 2; ++hh) {
-        uint32_t u[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const __nv_bfloat162 t = __floats2bfloat162_rn(o[16 * hh + 2 * e] * inv, o[16 * hh + 2 * e + 1] * inv);
-            u[e] = *reinterpret_cast<const uint32_t*>(&t);
-        }
-        stg256(op + 16 * hh, make_uint4(u[0], u[1], u[2], u[3]), make_uint4(u[4], u[5], u[6], u[7]));
-    }
 }
 
 // ---- final LN + mean pool + projection + L2 norm (+ logit) (modeling_swin.py:883-887; ref losses.py:71-77) ---------
@@ -430,7 +338,7 @@ int m2t_clip_pack_weights(const float* const* P, int n_params, void* d_packed, v
             const float* const* Q = P + pi;   // ln1.w ln1.b table q.w q.b k.w k.b v.w v.b o.w o.b ln2.w ln2.b fc1.w fc1.b fc2.w fc2.b
             M2T_TRY(run_cpack(CPK_F32, Q[0], pk + W.ln1g, C, 0, s));
             M2T_TRY(run_cpack(CPK_F32, Q[1], pk + W.ln1b, C, 0, s));
-            M2T_TRY(run_cpack(CPK_RPB, Q[2], pk + W.rpb, (long)kHeads[st] * CL_WT * CL_WT, kHeads[st], s));
+            M2T_TRY(run_cpack(CPK_RPB, Q[2], pk + W.rpb, (long)kHeads[st] * CL_WT * CL_RPB_PITCH, kHeads[st], s));
             for (int j = 0; j < 3; ++j) {
                 M2T_TRY(run_cpack(CPK_BF16, Q[3 + 2 * j], pk + W.wqkv + (size_t)j * C * C * 2, C * C, 0, s));
                 M2T_TRY(run_cpack(CPK_F32, Q[4 + 2 * j], pk + W.bqkv + (size_t)j * C * 4, C, 0, s));
@@ -491,10 +399,7 @@ int m2t_clip_stage_attention(const void* d_qkv, void* d_out, const float* d_bias
         return M2T_E_UNSUPPORTED;
     }
     M2T_TRY(check_device());
-    M2T_CUDA(launch_pdl(clip_attn_kernel, dim3((unsigned)(B * (h / CL_WIN) * (w / CL_WIN)), (unsigned)heads), dim3(64), 0,
-                        (cudaStream_t)stream, static_cast<const __nv_bfloat16*>(d_qkv), static_cast<__nv_bfloat16*>(d_out),
-                        d_bias, h, w, C, shift));
-    return M2T_OK;
+    return launch_clip_attn(d_qkv, d_out, d_bias, B, h, w, C, heads, shift, (cudaStream_t)stream);
 }
 
 int m2t_clip_encode_image(const void* d_packed, const float* d_img, int B, int H, int W, float* d_embed,
@@ -525,8 +430,7 @@ int m2t_clip_encode_image(const void* d_packed, const float* d_img, int B, int H
             const int shift = (b % 2 == 1 && h > CL_WIN) ? CL_WIN / 2 : 0;      // modeling_swin.py:546-554, :1037
             M2T_TRY(launch_ln(X, ws.Hn, F(Wt.ln1g), F(Wt.ln1b), M, C, s));
             M2T_TRY(launch_lin_umma(LIN_BF16, ws.Hn, Hf(Wt.wqkv), F(Wt.bqkv), ws.QKV, (int)M, 3 * C, C, s));
-            M2T_CUDA(launch_pdl(clip_attn_kernel, dim3((unsigned)(B * (h / CL_WIN) * (w / CL_WIN)), (unsigned)kHeads[st]), dim3(64),
-                                0, s, ws.QKV, ws.Ao, F(Wt.rpb), h, w, C, shift));
+            M2T_TRY(launch_clip_attn(ws.QKV, ws.Ao, F(Wt.rpb), B, h, w, C, kHeads[st], shift, s));
             M2T_TRY(launch_lin_umma(LIN_ADD_F32, ws.Ao, Hf(Wt.wo), F(Wt.bo), X, (int)M, C, C, s));
             M2T_TRY(launch_ln(X, ws.Hn, F(Wt.ln2g), F(Wt.ln2b), M, C, s));
             M2T_TRY(launch_lin_umma(LIN_GELU_BF16, ws.Hn, Hf(Wt.w1), F(Wt.b1), ws.G, (int)M, 4 * C, C, s));

@@ -17,9 +17,11 @@
 
 namespace m2t {
 
-constexpr int LG_BN = 128, LG_STAGES = 5;
+constexpr int LG_BN = 128, LG_STAGES = 4;
+constexpr int LG_NWG = 2;                         // epilogue warpgroups: column blocks blk % LG_NWG == wg
+constexpr int LG_EPI_WARPS = 4 * LG_NWG, LG_THREADS = 32 * (LG_EPI_WARPS + 2);
 constexpr uint32_t LG_A = 128 * 128, LG_B = LG_BN * 128, LG_STAGE = LG_A + LG_B;
-constexpr uint32_t LG_OUT = 2 * 16384;
+constexpr uint32_t LG_OUT = LG_NWG * 2 * 16384;
 constexpr uint32_t LG_OFF_OUT = LG_STAGES * LG_STAGE;
 constexpr uint32_t LG_SMEM = 1024 + LG_STAGES * LG_STAGE + LG_OUT + 256;
 
@@ -48,7 +50,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
 }
 
 template <int EPI>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(LG_THREADS, 1)
 lin_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW,
                 const __grid_constant__ CUtensorMap mapO, const float* __restrict__ bias, int M, int N, int K) {
     extern __shared__ uint8_t smem_raw[];
@@ -65,10 +67,11 @@ lin_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     const int num_mt = (M + 127) / 128, num_nt = (N + LG_BN - 1) / LG_BN, num_t = num_mt * num_nt;
     const int KB = (K + 63) / 64;
 
-    if (warp == 5) tmem_alloc(tmem_slot, 256);
-    if (tid == 128) {
+    constexpr int W_TMA = LG_EPI_WARPS, W_MMA = LG_EPI_WARPS + 1;
+    if (warp == W_MMA) tmem_alloc(tmem_slot, 256);
+    if (tid == W_TMA * 32) {
         for (int s = 0; s < LG_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], LG_EPI_WARPS); }
         mbar_fence_init();
         tma_prefetch_desc(&mapA);
         tma_prefetch_desc(&mapW);
@@ -80,7 +83,7 @@ lin_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     const uint32_t tmem_base = *tmem_slot;
     pdl_trigger();
 
-    if (warp == 4) {
+    if (warp == W_TMA) {
         pdl_wait();
         uint32_t it = 0;
         for (int t = blockIdx.x; t < num_t; t += gridDim.x) {
@@ -96,7 +99,7 @@ lin_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 __syncwarp();
             }
         }
-    } else if (warp == 5) {
+    } else if (warp == W_MMA) {
         constexpr uint32_t idesc = umma_idesc_f16(128, LG_BN, 0, 0, 1);
         constexpr uint64_t tmpl = umma_smem_desc(0, 16, 1024, UMMA_LAYOUT_SW128);
         uint32_t it = 0, tl = 0;
@@ -124,7 +127,10 @@ lin_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         pdl_wait();
         constexpr bool F32 = EPI == LIN_ADD_F32 || EPI == LIN_F32;
         constexpr int BLKC = F32 ? 32 : 64;              // columns per 128-byte staging row
-        const int trow = warp * 32 + lane;
+        const int wg = warp >> 2, wq = warp & 3;         // TMEM lanes 32 wq .. 32 wq + 31 belong to warps with id % 4 == wq
+        const int trow = wq * 32 + lane;
+        const bool issuer = (tid & 127) == 0;
+        const uint32_t bar_id = 1 + wg;
         uint32_t tl = 0, nblk = 0;
         for (int t = blockIdx.x; t < num_t; t += gridDim.x, ++tl) {
             const int mt = t / num_nt, nt = t - mt * num_nt;
@@ -132,16 +138,16 @@ lin_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             mbar_wait(&tfull[acc], aph);
             tc_fence_after();
 #pragma unroll 1
-            for (int blk = 0; blk < LG_BN / BLKC; ++blk) {
+            for (int blk = wg; blk < LG_BN / BLKC; blk += LG_NWG) {
                 const int col0 = nt * LG_BN + blk * BLKC;
-                if (col0 >= N) break;                    // uniform
-                uint8_t* ob = sm + LG_OFF_OUT + (nblk & 1) * 16384;
-                if (tid == 0) tma_store_wait_read1();    // the store that last used this buffer has read it
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (col0 >= N) break;                    // uniform within the warpgroup
+                uint8_t* ob = sm + LG_OFF_OUT + (wg * 2 + (nblk & 1)) * 16384;
+                if (issuer) tma_store_wait_read1();      // the store that last used this buffer has read it
+                asm volatile("bar.sync %0, 128;" :: "r"(bar_id) : "memory");
 #pragma unroll
                 for (int hh = 0; hh < BLKC / 32; ++hh) {
                     uint32_t r[32];
-                    tmem_ld32(tmem_base + acc * LG_BN + blk * BLKC + hh * 32 + ((uint32_t)(warp * 32) << 16), r);
+                    tmem_ld32(tmem_base + acc * LG_BN + blk * BLKC + hh * 32 + ((uint32_t)(wq * 32) << 16), r);
                     tmem_ld_wait();
                     const int c = col0 + hh * 32;
                     const bool live = c < N;             // N is a multiple of 32: a 32-column group is all in or all out
@@ -177,8 +183,8 @@ lin_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                     }
                 }
                 fence_proxy_async();
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                if (tid == 0) {
+                asm volatile("bar.sync %0, 128;" :: "r"(bar_id) : "memory");
+                if (issuer) {
                     if constexpr (EPI == LIN_ADD_F32) tma_reduce_add_2d(&mapO, ob, col0, mt * 128);
                     else tma_store_2d(&mapO, ob, col0, mt * 128);
                     tma_store_commit();
@@ -189,11 +195,11 @@ lin_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);
         }
-        if (tid == 0) tma_store_wait_all();
+        if (issuer) tma_store_wait_all();
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 5) tmem_dealloc(tmem_base, 256);
+    if (warp == W_MMA) tmem_dealloc(tmem_base, 256);
 }
 
 template <int EPI>
@@ -220,7 +226,7 @@ static int launch_lin_epi(const void* A, const void* W, const float* bias, void*
     const int num_t = cdiv(M, 128) * cdiv(N, LG_BN);
     int grid = device_sm_count();
     if (grid > num_t) grid = num_t;
-    M2T_CUDA(launch_pdl(lin_umma_kernel<EPI>, dim3(grid), dim3(192), LG_SMEM, s, mapA, mapW, mapO, bias, M, N, K));
+    M2T_CUDA(launch_pdl(lin_umma_kernel<EPI>, dim3(grid), dim3(LG_THREADS), LG_SMEM, s, mapA, mapW, mapO, bias, M, N, K));
     return M2T_OK;
 }
 

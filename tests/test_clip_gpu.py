@@ -83,13 +83,15 @@ def test_stage_attention(h, C, heads, shift):
     if shift:
         o = torch.roll(o, (shift, shift), (1, 2))
     ref = o.reshape(B * h * h, C)
-    qd, bd = qkv.cuda(), bias.cuda()
+    padded = torch.full((heads, 49, 56), -1.0e30)
+    padded[:, :, :49] = bias
+    qd, bd = qkv.cuda(), padded.cuda()
     out = torch.full((B * h * h, C), float("nan"), dtype=torch.bfloat16, device="cuda")
     _lib.check(lib.m2t_clip_stage_attention(qd.data_ptr(), out.data_ptr(), bd.data_ptr(), B, h, h, C, heads, shift,
                                             torch.cuda.current_stream().cuda_stream), "m2t_clip_stage_attention")
     d = float((out.float().cpu() - ref).abs().max())
     print(f"attention {h}x{h} C {C} shift {shift}: max-abs {d:.2e} (|ref| max {float(ref.abs().max()):.2f})")
-    assert d <= 2e-2                                   # bf16 rounding of outputs up to ~4; a wrong index gives O(1)
+    assert d <= 3e-2            # bf16 rounding of the probabilities (PV operand) and of outputs up to ~4; a wrong index gives O(1)
 
 
 @pytest.mark.parametrize("h,C,merge", [(56, 96, 0), (28, 192, 0), (14, 384, 0), (7, 768, 0), (56, 96, 1), (28, 192, 1), (14, 384, 1)])
