@@ -1,12 +1,14 @@
 // tcgen05 bf16 GEMM for the Linear layers of the MedCLIP image tower (Swin-T):
 //   Y[m][n] = epilogue( sum_k A[m][k] * W[n][k] + bias[n] )      A bf16 [M][K], W bf16 [N][K] (nn.Linear layout)
-// Persistent, warp-specialised CTAs (192 threads), tiles of 128 rows x 128 columns, K in blocks of 64 (128-byte swizzle):
-//   warp 4   : TMA producer, ring of LG_STAGES {A block, W block} stages.  K, M and N need not be multiples of the tile:
+// Persistent, warp-specialised CTAs (320 threads), tiles of 128 rows x 128 columns, K in blocks of 64 (128-byte swizzle):
+//   warp 8   : TMA producer, ring of LG_STAGES {A block, W block} stages.  K, M and N need not be multiples of the tile:
 //              the tensor maps zero-fill out-of-range elements (K = 96 -> a 64 block and a 32 + 32 zero block; only the
 //              MMAs that touch real columns are issued), and the TMA stores clip rows >= M and columns >= N
-//   warp 5   : single-thread tcgen05.mma issue, M=128 x N=128 x K=16, fp32 accumulators in TMEM (two of 128 columns: the
+//   warp 9   : single-thread tcgen05.mma issue, M=128 x N=128 x K=16, fp32 accumulators in TMEM (two of 128 columns: the
 //              epilogue of tile i overlaps the MMAs of tile i+1)
-//   warps 0-3: epilogue -- tcgen05.ld, + bias, optional GELU, conversion, 128-byte swizzled staging rows, TMA store.  The
+//   warps 0-7: epilogue, two warpgroups splitting the tile's column blocks -- tcgen05.ld, + bias, optional GELU,
+//              conversion, 128-byte swizzled staging rows, TMA store.  (Keeping the weight slab resident for K <= 384 was
+//              measured: 3-7 % on the stage-1 shapes, nothing on the pass; not kept.)  The
 //              residual form (X += Y) is a TMA reduce-add store of the fp32 tile: the read-modify-write happens in L2 and
 //              every element receives exactly one addend per GEMM, so the result does not depend on scheduling.
 #include <cuda_bf16.h>
