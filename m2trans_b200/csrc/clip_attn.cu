@@ -70,22 +70,24 @@ clip_attn_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
     __syncthreads();
     uint8_t* mq = sm[warp][0];
     // q | k | v rows of this head: 49 tokens x 4 chunks of 16 bytes each, rows 49..63 zero
-    // (8 tokens per pass and matrix: all 8 loads of a batch are issued before the first store waits on them)
+    // (cp.async: all 24 chunks of a lane are in flight at once, no staging registers)
+    const uint32_t sq = (uint32_t)__cvta_generic_to_shared(mq), sk = sq + CA_MAT, sv = sq + 2 * CA_MAT;
 #pragma unroll
     for (int m = 0; m < 3; ++m) {
         const __nv_bfloat16* src = qkv + m * C + head * CL_HD + (lane & 3) * 8;
-        uint4 v[8];
 #pragma unroll
         for (int p = 0; p < 8; ++p) {
             const int tok = p * 8 + (lane >> 2);
-            v[p] = make_uint4(0u, 0u, 0u, 0u);
-            if (tok < CL_WT) v[p] = __ldg(reinterpret_cast<const uint4*>(src + (long)sRow[tok] * 3 * C));
+            const uint32_t dst = sq + m * CA_MAT + ca_off(tok, lane & 3);
+            if (tok < CL_WT)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(src + (long)sRow[tok] * 3 * C) : "memory");
+            else
+                asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" :: "r"(dst), "r"(0u) : "memory");
         }
-#pragma unroll
-        for (int p = 0; p < 8; ++p) *reinterpret_cast<uint4*>(mq + m * CA_MAT + ca_off(p * 8 + (lane >> 2), lane & 3)) = v[p];
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncwarp();
-    const uint32_t sq = (uint32_t)__cvta_generic_to_shared(mq), sk = sq + CA_MAT, sv = sq + 2 * CA_MAT;
     const int g = lane >> 2, t = lane & 3;
     const float* bh = rpb + (long)head * CL_WT * 56;
     int idc[14];
