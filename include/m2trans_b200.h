@@ -225,6 +225,18 @@ int m2t_clip_stage_layernorm(const float* d_x, void* d_out, const float* d_gamma
 int m2t_clip_stage_attention(const void* d_qkv, void* d_out, const float* d_bias, int B, int h, int w, int C,
                              int heads, int shift, void* stream);
 
+/* ---- evaluation metrics of the test loop -----------------------------------
+ * Replaces ref test.py:103-116 for one batch: Y channel of SR and HR (ref utils.py:119-146; colors == 1 skips it),
+ * `shave` = args.scale border pixels cropped (test.py:109-110), x 255 when rgb_range == 1 (:111-112),
+ * utils.calc_psnr (utils.py:179-184) and utils.calc_ssim = pytorch_msssim.ssim(size_average=True) with its defaults
+ * (utils.py:232-234: 11-tap Gaussian, sigma 1.5, valid region, data_range 255).
+ * d_sr, d_hr: fp32 [B][colors][H][W]; d_out: fp32 [2 (B + 1)]: {psnr_b, ssim_b} per image, then {psnr, ssim} of the whole
+ * batch tensor as the reference computes them (for B = 1, the loader's batch size, the two coincide).
+ * d_workspace: m2t_metrics_workspace_bytes(B, H, W, shave) bytes, 16-byte aligned.  No host synchronisation. */
+size_t m2t_metrics_workspace_bytes(int B, int H, int W, int shave);
+int m2t_eval_psnr_ssim(const float* d_sr, const float* d_hr, int B, int colors, int H, int W, int shave,
+                       float rgb_range, float* d_out, void* d_workspace, void* stream);
+
 /* ---- hardware probes (development aids; tests/test_probes.py) ---------------------------
  * m2t_probe_umma: copies two raw shared-memory images (A, B operands), issues k_steps
  * tcgen05.mma (kind::f16, cta_group::1, M=128) with the given 64-bit shared-memory

@@ -1,0 +1,40 @@
+"""Oracle for the test-loop metrics against fixtures made by the reference's own utils.py."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+GOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "metrics_*.npz")))
+
+
+def test_fixtures_present():
+    assert len(GOLD) == 3
+
+
+@pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p) for p in GOLD])
+def test_oracle_matches_reference_fixture(path):
+    from oracle import metrics_oracle as M
+    z = np.load(path)
+    sr, hr, scale = torch.from_numpy(z["sr"]), torch.from_numpy(z["hr"]), int(z["scale"])
+    s, h = M.prepare(sr, hr, scale)
+    assert torch.equal(s, torch.from_numpy(z["sr_y"])) and torch.equal(h, torch.from_numpy(z["hr_y"]))
+    assert M.calc_psnr(s, h) == float(z["psnr"])
+    for i, p in enumerate(z["psnr_per_image"]):
+        assert M.calc_psnr(s[i:i + 1], h[i:i + 1]) == float(p)
+
+
+def test_ssim_known_answers():
+    from oracle import metrics_oracle as M
+    g = torch.Generator().manual_seed(0)
+    x = torch.rand(2, 1, 40, 52, generator=g) * 219 + 4080
+    assert abs(M.ssim(x, x, dtype=torch.float64) - 1.0) < 1e-12
+    y = x + 5 * torch.randn(x.shape, generator=g)
+    a, b = M.ssim(x, y, dtype=torch.float64), M.ssim(x, y, dtype=torch.float32)
+    assert 0.0 < a < 1.0
+    assert abs(a - b) < 2e-3            # the reference's float32 path is only this good on the 4080-offset Y channel
+    # shift invariance of the structure term: removing the offset changes only the (near 1) luminance term
+    c = M.ssim(x - 4080, y - 4080, dtype=torch.float64)
+    assert abs(a - c) < 0.05
+    assert M._gauss().sum().item() == pytest.approx(1.0, abs=1e-6)

@@ -1,0 +1,65 @@
+"""Device PSNR / SSIM of the test loop against the oracle and the reference-made fixtures."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "metrics_*.npz")))
+
+
+@pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p) for p in GOLD])
+def test_psnr_matches_reference_fixture(path):
+    from oracle import metrics_oracle as M
+    from m2trans_b200.metrics import psnr_ssim
+    z = np.load(path)
+    sr, hr, scale = torch.from_numpy(z["sr"]), torch.from_numpy(z["hr"]), int(z["scale"])
+    per, batch = psnr_ssim(sr.cuda(), hr.cuda(), scale)
+    per, batch = per.cpu(), batch.cpu()
+    assert abs(float(batch[0]) - float(z["psnr"])) <= 2e-4           # dB; fp32 Y and squared error, fp64 sums
+    assert np.abs(per[:, 0].numpy() - z["psnr_per_image"]).max() <= 2e-4
+    s, h = M.prepare(sr, hr, scale)
+    for i in range(sr.shape[0]):
+        assert abs(float(per[i, 1]) - M.ssim(s[i:i + 1], h[i:i + 1], dtype=torch.float64)) <= 2e-5
+    assert abs(float(batch[1]) - M.ssim(s, h, dtype=torch.float64)) <= 2e-5
+
+
+@pytest.mark.parametrize("b,c,h,w,scale,rr", [(1, 3, 512, 512, 4, 1.0), (3, 3, 270, 481, 3, 1.0), (2, 1, 64, 75, 2, 1.0),
+                                              (1, 3, 96, 43, 4, 255.0), (2, 3, 19, 19, 4, 1.0)])
+def test_psnr_ssim_against_oracle(b, c, h, w, scale, rr):
+    from oracle import metrics_oracle as M
+    from m2trans_b200.metrics import calc_psnr_ssim, psnr_ssim
+    g = torch.Generator().manual_seed(h + w)
+    hr = torch.rand(b, c, h, w, generator=g)
+    hr = torch.nn.functional.avg_pool2d(hr, 5, 1, 2)                    # some spatial structure
+    hr = (hr - hr.min()) / (hr.max() - hr.min()) * rr
+    sr = (hr + 0.02 * rr * torch.randn(hr.shape, generator=g)).clamp(0, rr)
+    per, batch = psnr_ssim(sr.cuda(), hr.cuda(), scale, rr)
+    p_ref, s_ref = M.test_loop_metrics(sr, hr, scale, rr, c, dtype=torch.float64)
+    p32, s32 = M.test_loop_metrics(sr, hr, scale, rr, c, dtype=torch.float32)
+    print(f"{(b, c, h, w)} x{scale}: psnr {float(batch[0]):.4f} (oracle {p_ref:.4f})  ssim {float(batch[1]):.6f} "
+          f"(oracle fp64 {s_ref:.6f}, fp32 {s32:.6f})")
+    assert abs(float(batch[0]) - p_ref) <= 2e-4
+    assert abs(float(batch[1]) - s_ref) <= 2e-5
+    if (h - 2 * scale - 10) * (w - 2 * scale - 10) >= 1000:      # the reference's own float32 arithmetic scatters: 1e-2 per pixel,
+        assert abs(float(batch[1]) - s32) <= 2e-3               # averaging out over the valid region
+    assert calc_psnr_ssim(sr.cuda(), hr.cuda(), scale, rr) == tuple(batch.tolist())
+    for i in range(b):
+        pi, si = M.test_loop_metrics(sr[i:i + 1], hr[i:i + 1], scale, rr, c, dtype=torch.float64)
+        assert abs(float(per[i, 0]) - pi) <= 2e-4 and abs(float(per[i, 1]) - si) <= 2e-5
+
+
+def test_identical_images_and_errors():
+    from m2trans_b200._lib import M2TError
+    from m2trans_b200.metrics import psnr_ssim
+    x = torch.rand(1, 3, 40, 40, device="cuda")
+    per, _ = psnr_ssim(x, x.clone(), 2)
+    assert float(per[0, 1]) == pytest.approx(1.0, abs=1e-6) and torch.isinf(per[0, 0])      # mse 0: the reference raises on log10(0)
+    with pytest.raises(M2TError):
+        psnr_ssim(x, x[:, :, :30], 2)
+    with pytest.raises(M2TError):
+        psnr_ssim(x[:, :, :14, :14].contiguous(), x[:, :, :14, :14].contiguous(), 2)        # 10 x 10 after shaving
+    with pytest.raises(M2TError):
+        psnr_ssim(x.cpu(), x.cpu(), 2)
