@@ -237,6 +237,12 @@ size_t m2t_metrics_workspace_bytes(int B, int H, int W, int shave);
 int m2t_eval_psnr_ssim(const float* d_sr, const float* d_hr, int B, int colors, int H, int W, int shave,
                        float rgb_range, float* d_out, void* d_workspace, void* stream);
 
+/* ---- loader conversion (device side) -----------------------------------------
+ * Replaces ndarray2tensor(img) / 255. of the benchmark loader (ref datas/benchmark.py:66-69, utils.py:237-240) on the
+ * device: d_src uint8 [B][H][W][colors] (the image arrays the loader keeps in RAM) -> d_dst fp32 [B][colors][H][W] =
+ * float(u8) / denom (IEEE division: bit-identical to torch).  colors 1 or 3.  3 bytes per pixel cross PCIe instead of 12. */
+int m2t_u8hwc_to_f32chw(const void* d_src, float* d_dst, int B, int H, int W, int colors, float denom, void* stream);
+
 /* ---- hardware probes (development aids; tests/test_probes.py) ---------------------------
  * m2t_probe_umma: copies two raw shared-memory images (A, B operands), issues k_steps
  * tcgen05.mma (kind::f16, cta_group::1, M=128) with the given 64-bit shared-memory
