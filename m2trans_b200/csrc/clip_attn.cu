@@ -1,5 +1,5 @@
 // Window attention of the MedCLIP image tower (Swin-T; modeling_swin.py:430-487, :598-640): 49 tokens x 32 dims per
-// (window, head).  One warp per (image, window, head), three heads per CTA; bf16 mma.sync.m16n8k16 with fp32 accumulators:
+// (window, head).  Two warps per (image, window, head), three heads per CTA; bf16 mma.sync.m16n8k16 with fp32 accumulators:
 //   S = Q K^T (64 x 56 padded, 16 query rows at a time) -> + relative-position bias, - 100 across the shift regions ->
 //   softmax on the accumulator fragments -> P re-used in registers as the A operand -> O = P V -> bf16
 // The tiles are 49 x 32: far below the 128-row tcgen05 tile (two windows per tile would waste three quarters of S), and
@@ -44,13 +44,15 @@ __device__ __forceinline__ float ex2(float x) {
     return y;
 }
 
-__global__ void __launch_bounds__(CA_WARPS * 32)
+__global__ void __launch_bounds__(CA_WARPS * 64, 6)
 clip_attn_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, const float* __restrict__ rpb,
                  int h, int w, int C, int shift) {
     __shared__ __align__(128) uint8_t sm[CA_WARPS][3][CA_MAT];
     __shared__ int sRow[CA_ROWS];
     __shared__ int sId[CA_ROWS];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // two warps per (window, head): each owns two of the four 16-row query tiles and loads half of the operand rows; the
+    // kernel is latency-bound (ncu: issue slots 27 % busy at 18 warps per SM), so the same shared memory now feeds 36 warps
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 6, half = (tid >> 5) & 1;
     const int head = blockIdx.y * CA_WARPS + warp, nwx = w / CL_WIN, nW = (h / CL_WIN) * nwx;
     const int bimg = blockIdx.x / nW, wi = blockIdx.x - bimg * nW, wy = wi / nwx, wx = wi - wy * nwx;
     if (tid < CA_ROWS) {
@@ -76,8 +78,8 @@ clip_attn_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
     for (int m = 0; m < 3; ++m) {
         const __nv_bfloat16* src = qkv + m * C + head * CL_HD + (lane & 3) * 8;
 #pragma unroll
-        for (int p = 0; p < 8; ++p) {
-            const int tok = p * 8 + (lane >> 2);
+        for (int p = 0; p < 4; ++p) {
+            const int tok = (half * 4 + p) * 8 + (lane >> 2);
             const uint32_t dst = sq + m * CA_MAT + ca_off(tok, lane & 3);
             if (tok < CL_WT)
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(src + (long)sRow[tok] * 3 * C) : "memory");
@@ -87,16 +89,13 @@ clip_attn_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
     asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncwarp();
+    asm volatile("bar.sync %0, 64;" :: "r"(1 + warp) : "memory");      // the pair's rows have landed
     const int g = lane >> 2, t = lane & 3;
     const float* bh = rpb + (long)head * CL_WT * 56;
-    int idc[14];
-#pragma unroll
-    for (int nt = 0; nt < 7; ++nt) { idc[2 * nt] = sId[nt * 8 + 2 * t]; idc[2 * nt + 1] = sId[nt * 8 + 2 * t + 1]; }
     constexpr float kScale = 0.17677669529663687f, kLog2e = 1.4426950408889634f;
 
 #pragma unroll 1
-    for (int mt = 0; mt < 4; ++mt) {
+    for (int mt = 2 * half; mt < 2 * half + 2; ++mt) {
         uint32_t qa[2][4];
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks)
@@ -122,10 +121,11 @@ clip_attn_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
             s[nt][0] = fmaf(s[nt][0], kScale, ba.x); s[nt][1] = fmaf(s[nt][1], kScale, ba.y);
             s[nt][2] = fmaf(s[nt][2], kScale, bb.x); s[nt][3] = fmaf(s[nt][3], kScale, bb.y);
             if (shift) {
-                if (idc[2 * nt] != id0) s[nt][0] -= 100.f;
-                if (idc[2 * nt + 1] != id0) s[nt][1] -= 100.f;
-                if (idc[2 * nt] != id1) s[nt][2] -= 100.f;
-                if (idc[2 * nt + 1] != id1) s[nt][3] -= 100.f;
+                const int c0 = sId[j], c1 = sId[j + 1];
+                if (c0 != id0) s[nt][0] -= 100.f;
+                if (c1 != id0) s[nt][1] -= 100.f;
+                if (c0 != id1) s[nt][2] -= 100.f;
+                if (c1 != id1) s[nt][3] -= 100.f;
             }
             mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
             mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
@@ -168,10 +168,11 @@ clip_attn_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
         }
     }
     __syncwarp();
-    for (int idx = lane; idx < CL_WT * 4; idx += 32) {
-        const int tok = idx >> 2, c = idx & 3;
-        *reinterpret_cast<uint4*>(out + (long)sRow[tok] * C + head * CL_HD + c * 8) =
-            *reinterpret_cast<const uint4*>(mq + ca_off(tok, c));
+    for (int idx = lane; idx < 32 * 4; idx += 32) {          // each warp stores the 32 rows its two tiles produced
+        const int tok = half * 32 + (idx >> 2), c = idx & 3;
+        if (tok < CL_WT)
+            *reinterpret_cast<uint4*>(out + (long)sRow[tok] * C + head * CL_HD + c * 8) =
+                *reinterpret_cast<const uint4*>(mq + ca_off(tok, c));
     }
 }
 
@@ -185,7 +186,7 @@ int launch_clip_attn(const void* qkv, void* out, const float* rpb, int B, int h,
         return M2T_E_UNSUPPORTED;
     }
     M2T_CUDA(launch_pdl(clip_attn_kernel, dim3((unsigned)(B * (h / CL_WIN) * (w / CL_WIN)), (unsigned)(heads / CA_WARPS)),
-                        dim3(CA_WARPS * 32), 0, s, static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), rpb,
+                        dim3(CA_WARPS * 64), 0, s, static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), rpb,
                         h, w, C, shift));
     return M2T_OK;
 }

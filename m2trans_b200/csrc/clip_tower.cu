@@ -130,6 +130,8 @@ clip_resize_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ ro
 // ---- LayerNorm: one warp per output row, the row held in registers ------------------------------------------------
 // MERGE: output row (b, i, j) of the half-resolution grid is the concatenation of input tokens (2i,2j), (2i+1,2j),
 // (2i,2j+1), (2i+1,2j+1) (modeling_swin.py:333-341), normalised over 4C.
+__host__ __device__ constexpr int ln_rows_per_warp(int npl) { return npl <= 6 ? 4 : 2; }
+
 template <int NPL, bool OUTF32, bool MERGE>
 __global__ void __launch_bounds__(256)
 clip_ln_kernel(const float* __restrict__ X, void* __restrict__ out, const float* __restrict__ g,
@@ -137,6 +139,57 @@ clip_ln_kernel(const float* __restrict__ X, void* __restrict__ out, const float*
     pdl_wait();
     constexpr int CT = NPL * 32;
     const int lane = threadIdx.x & 31;
+    if constexpr (!MERGE && NPL <= 6) {
+        // short rows (C = 96, 192): 4 rows per warp with all their loads in flight before the first reduction -- one
+        // 384-byte row per warp left the kernel latency-bound at half of the copy bandwidth (16 -> 13 us at C = 96, batch 32;
+        // C = 384 has too few rows per launch for it to matter and measured slightly worse)
+        constexpr int R = ln_rows_per_warp(NPL);
+        const long row0 = ((long)blockIdx.x * 8 + (threadIdx.x >> 5)) * R;
+        float u[R][NPL];
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int k = 0; k < NPL; ++k) u[r][k] = row0 + r < rows ? X[(row0 + r) * CT + lane + 32 * k] : 0.f;
+        float gam[NPL], bet[NPL];
+#pragma unroll
+        for (int k = 0; k < NPL; ++k) { gam[k] = __ldg(g + lane + 32 * k); bet[k] = __ldg(bta + lane + 32 * k); }
+        float mean[R], rstd[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            float s = 0.f;
+#pragma unroll
+            for (int k = 0; k < NPL; ++k) s += u[r][k];
+            mean[r] = s;
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1)
+#pragma unroll
+            for (int r = 0; r < R; ++r) mean[r] += __shfl_xor_sync(0xffffffffu, mean[r], o);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            mean[r] *= (1.f / CT);
+            float q = 0.f;
+#pragma unroll
+            for (int k = 0; k < NPL; ++k) { const float d = u[r][k] - mean[r]; q = fmaf(d, d, q); }
+            rstd[r] = q;
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1)
+#pragma unroll
+            for (int r = 0; r < R; ++r) rstd[r] += __shfl_xor_sync(0xffffffffu, rstd[r], o);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if (row0 + r >= rows) break;
+            const float rs = rsqrtf(rstd[r] * (1.f / CT) + CL_LN_EPS);
+#pragma unroll
+            for (int k = 0; k < NPL; ++k) {
+                const float y = fmaf((u[r][k] - mean[r]) * rs, gam[k], bet[k]);
+                if constexpr (OUTF32) static_cast<float*>(out)[(row0 + r) * CT + lane + 32 * k] = y;
+                else static_cast<__nv_bfloat16*>(out)[(row0 + r) * CT + lane + 32 * k] = __float2bfloat16_rn(y);
+            }
+        }
+        return;
+    }
     const long row = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (row >= rows) return;
     float v[NPL];
@@ -178,8 +231,9 @@ clip_ln_kernel(const float* __restrict__ X, void* __restrict__ out, const float*
 
 template <int NPL, bool OUTF32, bool MERGE>
 int launch_ln_t(const float* X, void* out, const float* g, const float* b, long rows, int h, int w, cudaStream_t s) {
-    M2T_CUDA(launch_pdl(clip_ln_kernel<NPL, OUTF32, MERGE>, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, s, X, out, g, b,
-                        rows, h, w));
+    const long per_cta = 8L * ((!MERGE && NPL <= 6) ? ln_rows_per_warp(NPL) : 1);
+    M2T_CUDA(launch_pdl(clip_ln_kernel<NPL, OUTF32, MERGE>, dim3((unsigned)((rows + per_cta - 1) / per_cta)), dim3(256), 0, s, X, out,
+                        g, b, rows, h, w));
     return M2T_OK;
 }
 
