@@ -173,6 +173,7 @@ def run_reference(args):
 def clip_pass_line(pk, batch=32, size=512, steps=10, warmup=3):
     """BASELINE configs[4] on this GPU: MedCLIP image-embedding pass over x4 SR outputs ([batch,3,512,512] -> 224x224 ->
     Swin-T -> [batch,512] -> logits); batch 32 is one GPU's share of the config's 256 images over 8 GPUs."""
+    import torch
     from m2trans_b200.medclip_image import MedCLIPVisionModelViT, synthetic_state_dict
     tower = MedCLIPVisionModelViT()
     tower.load_state_dict(synthetic_state_dict(0), strict=False)
