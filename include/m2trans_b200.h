@@ -195,8 +195,9 @@ int m2t_transblock_forward(const float* d_x, float* d_y, const float* const* d_p
  * projection_head.weight [512][768].
  * m2t_clip_encode_image: d_img fp32 [B][3][H][W] (values as the SR network returns them, no mean/std
  * normalisation: the reference applies none); d_embed fp32 [B][512] L2-normalised; d_text fp32 [512] (any norm)
- * and d_logits fp32 [B] are both given or both NULL; d_workspace m2t_clip_workspace_bytes(B) bytes, 1024-byte
- * aligned. */
+ * and d_logits fp32 [B] are both given or both NULL; d_workspace m2t_clip_workspace_bytes(B) bytes, 256-byte
+ * aligned; d_packed m2t_clip_packed_bytes() bytes, 256-byte aligned.  Asynchronous on `stream`; no allocation, no
+ * synchronisation (capturable in a CUDA graph). */
 int m2t_clip_param_count(void);
 size_t m2t_clip_packed_bytes(void);
 size_t m2t_clip_workspace_bytes(int B);

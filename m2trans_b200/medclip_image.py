@@ -112,6 +112,9 @@ class MedCLIPVisionModelViT(nn.Module):
                 _child(self, path).register_buffer("relative_position_index", _relative_position_index())
         self._packed = None
         self._packed_key = None
+        self._graphs = {}
+        self.cuda_graph = True               # replay a captured graph for small inputs (see _encode_graphed)
+        self.graph_max_pixels = 4 << 20      # B*H*W above which the input copy costs more than the launches
 
     def _params(self):
         sd = dict(self.named_parameters())
@@ -134,6 +137,7 @@ class MedCLIPVisionModelViT(nn.Module):
         _lib.check(lib.m2t_clip_pack_weights(ptrs, len(params), packed.data_ptr(),
                                              torch.cuda.current_stream(device).cuda_stream), "m2t_clip_pack_weights")
         self._packed, self._packed_key = packed, key
+        self._graphs = {}                    # captured graphs point at the previous blob
         return packed
 
     @torch.no_grad()
@@ -148,6 +152,8 @@ class MedCLIPVisionModelViT(nn.Module):
             raise M2TError(f"MedCLIPVisionModelViT: expected float32 [B,3,H,W], got {x.dtype} {tuple(x.shape)}")
         b, _, h, w = x.shape
         lib = _lib.load()
+        if self.cuda_graph and b * h * w <= self.graph_max_pixels and not torch.cuda.is_current_stream_capturing():
+            return self._encode_graphed(x, text_features)
         with torch.cuda.device(x.device):
             packed = self._pack(x.device)
             xc = x.contiguous()
@@ -165,6 +171,48 @@ class MedCLIPVisionModelViT(nn.Module):
                                                  torch.cuda.current_stream(x.device).cuda_stream),
                        "m2t_clip_encode_image")
         return embed if logits is None else (embed, logits)
+
+    def _encode_graphed(self, x, text_features):
+        """Small batches (the reference encodes one image per call, ref losses.py:45-46, :68): the 94 launches and their
+        tensor-map encodes cost more host time than the GPU needs, so the pass is captured once per (device, B, H, W,
+        with/without text) into a CUDA graph over static buffers and replayed; inputs are copied in, results cloned out."""
+        dev = x.device
+        with torch.cuda.device(dev):
+            packed = self._pack(dev)                  # drops the cached graphs when the weights changed
+            has_text = text_features is not None
+            t = None
+            if has_text:
+                t = text_features.to(device=dev, dtype=torch.float32).reshape(-1)
+                if t.numel() != PROJ:
+                    raise M2TError(f"MedCLIPVisionModelViT: text feature must have {PROJ} elements")
+            key = (dev.index, tuple(x.shape), has_text)
+            entry = self._graphs.get(key)
+            if entry is None:
+                sx = torch.empty_like(x, memory_format=torch.contiguous_format)
+                stext = torch.empty(PROJ, dtype=torch.float32, device=dev) if has_text else None
+                sx.copy_(x)
+                if has_text:
+                    stext.copy_(t)
+                self.cuda_graph = False
+                try:
+                    side = torch.cuda.Stream(dev)
+                    side.wait_stream(torch.cuda.current_stream(dev))
+                    with torch.cuda.stream(side):
+                        self.encode_image(sx, stext)                      # warm-up outside the capture
+                    torch.cuda.current_stream(dev).wait_stream(side)
+                    graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph):
+                        out = self.encode_image(sx, stext)
+                finally:
+                    self.cuda_graph = True
+                entry = (graph, sx, stext, out, packed)
+                self._graphs[key] = entry
+            graph, sx, stext, out, _ = entry
+            sx.copy_(x)
+            if has_text:
+                stext.copy_(t)
+            graph.replay()
+            return (out[0].clone(), out[1].clone()) if has_text else out.clone()
 
     def forward(self, pixel_values, **kwargs):
         return self.encode_image(pixel_values)

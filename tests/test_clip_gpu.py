@@ -216,3 +216,33 @@ def test_encode_image_argument_errors():
         tower.encode_image(torch.zeros(1, 1, 224, 224, device="cuda"))
     with pytest.raises(M2TError):
         tower.encode_image(torch.zeros(1, 3, 224, 224, device="cuda"), torch.zeros(100, device="cuda"))
+
+
+def test_small_batch_graph_replay_equals_eager():
+    """Inputs up to graph_max_pixels replay a captured CUDA graph (the reference encodes one image per call); the result is
+    bit-identical to the eager launches, follows new inputs and text features, and is re-captured when the weights change."""
+    from m2trans_b200.medclip_image import MedCLIPVisionModelViT, synthetic_state_dict
+    from m2trans_b200.synthetic import synthetic_input
+    tower = MedCLIPVisionModelViT()
+    tower.load_state_dict(synthetic_state_dict(seed=6), strict=False)
+    tower = tower.cuda()
+    xs = [synthetic_input(1, 224, 224, seed=s).cuda() for s in (1, 2, 3)]
+    texts = [torch.randn(512, generator=torch.Generator().manual_seed(s)).cuda() for s in (1, 2, 3)]
+    got = [tower.encode_image(x, t) for x, t in zip(xs, texts)]
+    assert len(tower._graphs) == 1
+    plain = [tower.encode_image(x) for x in xs]
+    assert len(tower._graphs) == 2
+    tower.cuda_graph = False
+    for x, t, (e, l), p in zip(xs, texts, got, plain):
+        e2, l2 = tower.encode_image(x, t)
+        assert torch.equal(e, e2) and torch.equal(l, l2) and torch.equal(p, e2)
+    tower.cuda_graph = True
+    tower.load_state_dict(synthetic_state_dict(seed=7), strict=False)
+    e_new = tower.encode_image(xs[0])
+    tower.cuda_graph = False
+    assert torch.equal(e_new, tower.encode_image(xs[0])) and not torch.equal(e_new, plain[0])
+    big = torch.rand(20, 3, 512, 512, device="cuda")                      # above graph_max_pixels: eager, nothing cached
+    tower.cuda_graph = True
+    n = len(tower._graphs)
+    tower.encode_image(big)
+    assert len(tower._graphs) == n

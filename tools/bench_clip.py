@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--no-graph", action="store_true", help="eager launches even for small inputs")
     args = ap.parse_args()
     world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
@@ -35,6 +36,7 @@ def main():
     tower = MedCLIPVisionModelViT()
     tower.load_state_dict(synthetic_state_dict(0), strict=False)
     tower = tower.cuda()
+    tower.cuda_graph = not args.no_graph
     x = torch.rand(args.batch, 3, args.size, args.size, device="cuda", generator=torch.Generator("cuda").manual_seed(rank))
     text = torch.randn(512, device="cuda")
     for _ in range(args.warmup):
@@ -62,7 +64,7 @@ def main():
         print(json.dumps({"metric": "medclip_image_pass", "n_gpus": world, "batch_per_gpu": args.batch,
                           "input": [3, args.size, args.size], "ms_per_step": mean_ms, "ms_median_rank0": ms[len(ms) // 2],
                           "ms_min_rank0": ms[0], "ms_max_rank0": ms[-1], "images_per_s": world * args.batch / mean_ms * 1e3,
-                          "tflops": world * args.batch * GFLOP_PER_IMAGE / mean_ms, "scaling": "weak", "dtype": "bf16",
+                          "tflops": world * args.batch * GFLOP_PER_IMAGE / mean_ms, "scaling": "weak", "dtype": "bf16", "cuda_graph": bool(tower._graphs),
                           "timing": "CUDA events, mean over the timed steps, max over ranks"}))
     if world > 1:
         dist.destroy_process_group()
