@@ -19,8 +19,9 @@ def _oracle_params(sd):
 @pytest.mark.parametrize("epi", [0, 1, 2, 3])
 @pytest.mark.parametrize("M,N,K", [(300, 96, 48), (3136, 288, 96), (1000, 384, 96), (784, 192, 768), (129, 3072, 768),
                                    (196, 768, 3072), (49, 512 + 256, 1536),
-                                   # enough row tiles for the weight-resident walk (K <= 384)
-                                   (40000, 288, 96), (20001, 96, 384), (3000, 1152, 384), (9000, 768, 192)])
+                                   # many row tiles: wide outputs take the 256-column tile (ragged last column block too)
+                                   (40000, 288, 96), (20001, 96, 384), (3000, 1152, 384), (9000, 768, 192),
+                                   (50000, 384, 96), (30001, 576, 192), (25000, 192, 768)])
 def test_stage_linear(epi, M, N, K):
     """The tcgen05 Linear on shapes of the tower (ragged M, N and K against the 128 x 128 x 64 tile)."""
     from m2trans_b200 import _lib
