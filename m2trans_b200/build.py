@@ -25,6 +25,8 @@ FLAGS = [
 ]
 if os.environ.get("M2T_CONV_WGS"):          # tuning switch: epilogue warpgroups of the ff conv (1 or 2)
     FLAGS.append("-DM2T_CONV_WGS=" + os.environ["M2T_CONV_WGS"])
+for _d in os.environ.get("M2T_DEFS", "").split():   # tuning builds: extra -D definitions (e.g. LG_NWG_OVERRIDE=1)
+    FLAGS.append("-D" + _d)
 if os.environ.get("M2T_TIMING") == "1":      # development builds: clock64 stamps in the attention kernel
     FLAGS.append("-DM2T_TIMING")
 

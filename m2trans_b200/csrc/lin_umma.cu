@@ -20,8 +20,14 @@
 
 namespace m2t {
 
-constexpr int LG_BN = 128, LG_STAGES = 4;
-constexpr int LG_NWG = 2;                         // epilogue warpgroups: column blocks blk % LG_NWG == wg
+#ifndef LG_STAGES_OVERRIDE
+#define LG_STAGES_OVERRIDE 4
+#endif
+#ifndef LG_NWG_OVERRIDE
+#define LG_NWG_OVERRIDE 2
+#endif
+constexpr int LG_BN = 128, LG_STAGES = LG_STAGES_OVERRIDE;
+constexpr int LG_NWG = LG_NWG_OVERRIDE;                        // epilogue warpgroups: column blocks blk % LG_NWG == wg
 constexpr int LG_EPI_WARPS = 4 * LG_NWG, LG_THREADS = 32 * (LG_EPI_WARPS + 2);
 constexpr uint32_t LG_A = 128 * 128, LG_B = LG_BN * 128, LG_STAGE = LG_A + LG_B;
 constexpr uint32_t LG_OUT = LG_NWG * 2 * 16384;
