@@ -221,6 +221,9 @@ int m2t_clip_stage_linear(int epilogue, const void* d_a, const void* d_w, const 
  *   kernel's key tiles are 7 x 8 wide; the pad masks the 7 phantom keys); shift 0 or 3 (cyclic shift + region mask,
  *   :556-582, :615); heads a multiple of 3. */
 int m2t_clip_stage_resize(const float* d_img, void* d_rows, int B, int H, int W, void* stream);
+/* Development aid: 128 clock64 stamps of CTA 0 of the last epilogue-0 Linear launch (library built with M2T_TIMING=1;
+ * zeros otherwise); layout in csrc/lin_umma.cu. */
+int m2t_debug_lin_timing(long long* host128);
 int m2t_clip_stage_layernorm(const float* d_x, void* d_out, const float* d_gamma, const float* d_beta, int B,
                              int h, int w, int C, int merge, void* stream);
 int m2t_clip_stage_attention(const void* d_qkv, void* d_out, const float* d_bias, int B, int h, int w, int C,

@@ -75,6 +75,7 @@ SIGNATURES = {
     "m2t_clip_encode_image": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "m2t_clip_stage_linear": (_i, [_i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "m2t_clip_stage_resize": (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    "m2t_debug_lin_timing": (_i, [C.POINTER(C.c_longlong)]),
     "m2t_clip_stage_layernorm": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "m2t_clip_stage_attention": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "m2t_metrics_workspace_bytes": (_sz, [_i, _i, _i, _i]),

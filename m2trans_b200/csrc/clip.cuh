@@ -9,6 +9,8 @@ enum { LIN_BF16 = 0, LIN_GELU_BF16 = 1, LIN_ADD_F32 = 2, LIN_F32 = 3 };
 int launch_lin_umma(int epi, const void* A, const void* W, const float* bias, void* out, int M, int N, int K,
                     cudaStream_t s);
 
+int read_lin_timing(long long* host128);      // clock64 stamps of the last LIN_BF16 launch (M2T_TIMING builds; zeros otherwise)
+
 // window attention (clip_attn.cu): qkv bf16 [tokens][3C], out bf16 [tokens][C], rpb fp32 [heads][49][CL_RPB_PITCH]
 int launch_clip_attn(const void* qkv, void* out, const float* rpb, int B, int h, int w, int C, int heads, int shift,
                      cudaStream_t s);

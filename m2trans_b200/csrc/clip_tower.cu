@@ -426,6 +426,11 @@ int m2t_clip_stage_linear(int epilogue, const void* d_a, const void* d_w, const 
     return launch_lin_umma(epilogue, d_a, d_w, d_bias, d_out, M, N, K, (cudaStream_t)stream);
 }
 
+int m2t_debug_lin_timing(long long* host128) {
+    if (!host128) { set_error("lin timing: null pointer"); return M2T_E_ARG; }
+    return read_lin_timing(host128);
+}
+
 int m2t_clip_stage_resize(const float* d_img, void* d_rows, int B, int H, int W, void* stream) {
     if (!d_img || !d_rows || B < 1 || H < 2 || W < 2) { set_error("clip resize: bad argument"); return M2T_E_ARG; }
     M2T_TRY(check_device());
