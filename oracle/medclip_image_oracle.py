@@ -1,5 +1,5 @@
 """CPU oracle for the MedCLIP image-embedding pass (ref losses.py:42-81).  TEST INFRASTRUCTURE ONLY:
-imported by tests/, __graft_entry__.smoke() and tools/; never by the product path.
+imported by tests/ and __graft_entry__.smoke() only; never by the product path.
 
 PARITY UNPINNED against the real thing: the arithmetic of `encode_image` lives in the third-party `medclip` package
 (unpinned `pip install medclip`, ref README.md:42) on top of transformers==4.24.0 (ref environment.yml:176) with weights

@@ -1,5 +1,5 @@
 """Development aid: parity of the default path against the CPU oracle over several seeded checkpoints and inputs.
-usage: python tools/parity_sweep.py [scale] [H] [W] [n_seeds]"""
+usage: python tests/parity_sweep.py [scale] [H] [W] [n_seeds]"""
 import sys
 import types
 
