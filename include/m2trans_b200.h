@@ -210,6 +210,11 @@ int m2t_clip_encode_image(const void* d_packed, const float* d_img, int B, int H
  * tile. */
 int m2t_clip_stage_linear(int epilogue, const void* d_a, const void* d_w, const float* d_bias, void* d_out,
                           int M, int N, int K, void* stream);
+/* The fused MLP of stages 1-2 on its own: d_x fp32 [M][C] += W2 . gelu(W1 . A + b1) + b2 with A bf16 [M][C], W1 bf16 [4C][C],
+ * W2 bf16 [C][4C], biases fp32; C = 96 or 192 (M2T_E_UNSUPPORTED otherwise).  The hidden [M][4C] tensor is rounded to bf16 as
+ * in the two-launch form but never written to memory. */
+int m2t_clip_stage_mlp(const void* d_a, const void* d_w1, const float* d_b1, const void* d_w2, const float* d_b2,
+                       float* d_x, int M, int C, void* stream);
 /* The other kernels of the tower on their own (stage-level tests; the end-to-end embedding of a random-weight tower
  * only resolves errors above ~1e-3, these resolve an indexing slip exactly).
  * resize: d_img fp32 [B][3][H][W] -> d_rows bf16 [B*56*56][48], the 4x4 patch rows (column c*16 + ky*4 + kx) of the

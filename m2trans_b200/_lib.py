@@ -74,6 +74,7 @@ SIGNATURES = {
     "m2t_clip_pack_weights": (_i, [C.POINTER(_vp), _i, _vp, _vp]),
     "m2t_clip_encode_image": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "m2t_clip_stage_linear": (_i, [_i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "m2t_clip_stage_mlp": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
     "m2t_clip_stage_resize": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "m2t_debug_lin_timing": (_i, [C.POINTER(C.c_longlong)]),
     "m2t_clip_stage_layernorm": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),

@@ -9,6 +9,9 @@ enum { LIN_BF16 = 0, LIN_GELU_BF16 = 1, LIN_ADD_F32 = 2, LIN_F32 = 3 };
 int launch_lin_umma(int epi, const void* A, const void* W, const float* bias, void* out, int M, int N, int K,
                     cudaStream_t s);
 
+// fused MLP (mlp_umma.cu): X fp32 [M][C] += W2 . gelu(W1 . A + b1) + b2, C = 96 or 192; the hidden tensor stays on the SM
+int launch_mlp_umma(const void* A, const void* W1, const float* b1, const void* W2, const float* b2, float* X, int M, int C,
+                    cudaStream_t s);
 int read_lin_timing(long long* host128);      // clock64 stamps of the last LIN_BF16 launch (M2T_TIMING builds; zeros otherwise)
 
 // window attention (clip_attn.cu): qkv bf16 [tokens][3C], out bf16 [tokens][C], rpb fp32 [heads][49][CL_RPB_PITCH]

@@ -23,6 +23,12 @@ namespace {
 constexpr int kDepth[CL_STAGES] = {2, 2, 6, 2};
 constexpr int kHeads[CL_STAGES] = {3, 6, 12, 24};
 
+// M2T_CLIP_UNFUSED_MLP=1: stages 1-2 run fc1 / fc2 as two Linear launches like stages 3-4 (A/B measurements)
+bool clip_unfused_mlp() {
+    static const bool v = [] { const char* e = getenv("M2T_CLIP_UNFUSED_MLP"); return e && e[0] == '1'; }();
+    return v;
+}
+
 struct ClipBlockW {
     size_t ln1g, ln1b, wqkv, bqkv, rpb, wo, bo, ln2g, ln2b, w1, b1, w2, b2;
 };
@@ -426,6 +432,13 @@ int m2t_clip_stage_linear(int epilogue, const void* d_a, const void* d_w, const 
     return launch_lin_umma(epilogue, d_a, d_w, d_bias, d_out, M, N, K, (cudaStream_t)stream);
 }
 
+int m2t_clip_stage_mlp(const void* d_a, const void* d_w1, const float* d_b1, const void* d_w2, const float* d_b2, float* d_x,
+                       int M, int C, void* stream) {
+    if (!d_a || !d_w1 || !d_b1 || !d_w2 || !d_b2 || !d_x) { set_error("clip mlp: null pointer"); return M2T_E_ARG; }
+    M2T_TRY(check_device());
+    return launch_mlp_umma(d_a, d_w1, d_b1, d_w2, d_b2, d_x, M, C, (cudaStream_t)stream);
+}
+
 int m2t_debug_lin_timing(long long* host128) {
     if (!host128) { set_error("lin timing: null pointer"); return M2T_E_ARG; }
     return read_lin_timing(host128);
@@ -492,8 +505,12 @@ int m2t_clip_encode_image(const void* d_packed, const float* d_img, int B, int H
             M2T_TRY(launch_clip_attn(ws.QKV, ws.Ao, F(Wt.rpb), B, h, w, C, kHeads[st], shift, s));
             M2T_TRY(launch_lin_umma(LIN_ADD_F32, ws.Ao, Hf(Wt.wo), F(Wt.bo), X, (int)M, C, C, s));
             M2T_TRY(launch_ln(X, ws.Hn, F(Wt.ln2g), F(Wt.ln2b), M, C, s));
-            M2T_TRY(launch_lin_umma(LIN_GELU_BF16, ws.Hn, Hf(Wt.w1), F(Wt.b1), ws.G, (int)M, 4 * C, C, s));
-            M2T_TRY(launch_lin_umma(LIN_ADD_F32, ws.G, Hf(Wt.w2), F(Wt.b2), X, (int)M, C, 4 * C, s));
+            if (C <= 192 && !clip_unfused_mlp()) {       // stages 1-2 are HBM-bound: the [tokens][4C] tensor stays on the SM
+                M2T_TRY(launch_mlp_umma(ws.Hn, Hf(Wt.w1), F(Wt.b1), Hf(Wt.w2), F(Wt.b2), X, (int)M, C, s));
+            } else {
+                M2T_TRY(launch_lin_umma(LIN_GELU_BF16, ws.Hn, Hf(Wt.w1), F(Wt.b1), ws.G, (int)M, 4 * C, C, s));
+                M2T_TRY(launch_lin_umma(LIN_ADD_F32, ws.G, Hf(Wt.w2), F(Wt.b2), X, (int)M, C, 4 * C, s));
+            }
         }
         if (st < CL_STAGES - 1) {
             M2T_TRY(launch_ln_merge(X, ws.Hn, F(L.mrg[st].ng), F(L.mrg[st].nb), M / 4, C, h, w, s));

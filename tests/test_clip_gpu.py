@@ -48,6 +48,30 @@ def test_stage_linear(epi, M, N, K):
     assert d <= tol
 
 
+@pytest.mark.parametrize("M,C", [(128, 96), (300, 96), (3136, 96), (40000, 96), (784, 192), (1000, 192), (30001, 192)])
+def test_stage_mlp(M, C):
+    """Fused fc1 -> GELU -> fc2 + residual (stages 1-2): the hidden tensor is rounded to bf16 on the SM exactly as the
+    two-launch form rounds it in memory."""
+    from m2trans_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(M + C)
+    a = torch.randn(M, C, generator=g).bfloat16().cuda()
+    w1 = (torch.randn(4 * C, C, generator=g) / C ** 0.5).bfloat16().cuda()
+    w2 = (torch.randn(C, 4 * C, generator=g) / (4 * C) ** 0.5).bfloat16().cuda()
+    b1, b2 = torch.randn(4 * C, generator=g).cuda(), torch.randn(C, generator=g).cuda()
+    x0 = torch.randn(M, C, generator=g).cuda()
+    hid = torch.nn.functional.gelu(a.float() @ w1.float().t() + b1).bfloat16().float()
+    ref = x0 + hid @ w2.float().t() + b2
+    x = x0.clone()
+    _lib.check(lib.m2t_clip_stage_mlp(a.data_ptr(), w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), x.data_ptr(),
+                                      M, C, torch.cuda.current_stream().cuda_stream), "m2t_clip_stage_mlp")
+    torch.cuda.synchronize()
+    d = float((x - ref).abs().max())
+    print(f"mlp M {M} C {C}: max-abs {d:.2e}")
+    assert d <= 2e-2          # a GELU value on a bf16 rounding tie flips one hidden element by an ulp (<= 1.6e-2 x |w2| ~ 0.05)
+    assert float((x - ref).abs().mean()) <= 2e-4
+
+
 def test_stage_linear_no_bias():
     from m2trans_b200 import _lib
     lib = _lib.load()
