@@ -8,7 +8,8 @@
 //   patch embed  lin_umma K=48           -> fp32 X [3136][96], LayerNorm in place
 //   12 x layer   LN -> bf16 | qkv GEMM -> bf16 [tokens][3C] | window attention (SIMT, 49 tokens x 32 dims per head, shift and
 //                window partition/reverse as index arithmetic) -> bf16 | proj GEMM, reduce-add into X | LN -> bf16 |
-//                fc1 GEMM + GELU -> bf16 [tokens][4C] | fc2 GEMM, reduce-add into X
+//                fc1 GEMM + GELU -> bf16 [tokens][4C] | fc2 GEMM, reduce-add into X  (stages 1-2: one fused kernel, mlp_umma.cu,
+//                the [tokens][4C] tensor stays on the SM)
 //   3 x merging  gather 2x2 + LN(4C) -> bf16 | reduction GEMM -> fp32 X' [tokens/4][2C]
 //   final        LN(768) + mean over the 49 tokens + projection + L2 norm (+ logit) in one kernel per image
 // The residual stream X stays fp32; GEMM operands are bf16 with fp32 accumulation (north_star: "bf16 tcgen05 ViT forward").
