@@ -11,7 +11,7 @@
 //                fc1 GEMM + GELU -> bf16 [tokens][4C] | fc2 GEMM, reduce-add into X  (stages 1-2: one fused kernel, mlp_umma.cu,
 //                the [tokens][4C] tensor stays on the SM)
 //   3 x merging  gather 2x2 + LN(4C) -> bf16 | reduction GEMM -> fp32 X' [tokens/4][2C]
-//   final        LN(768) + mean over the 49 tokens + projection + L2 norm (+ logit) in one kernel per image
+//   final        LN(768) + mean over the 49 tokens + projection (8 CTAs per image, 64 outputs each), then L2 norm (+ logit)
 // The residual stream X stays fp32; GEMM operands are bf16 with fp32 accumulation (north_star: "bf16 tcgen05 ViT forward").
 #include <cuda_bf16.h>
 
@@ -279,10 +279,11 @@ __device__ __forceinline__ float block_sum_256(float v, float* red) {      // fi
     return t;
 }
 
+constexpr int CL_PSLICE = 64;       // projection outputs per CTA: grid (B, 512 / 64); every CTA redoes the image's LN + pool
+
 __global__ void __launch_bounds__(256)
 clip_final_kernel(const float* __restrict__ X, const float* __restrict__ g, const float* __restrict__ bta,
-                  const float* __restrict__ projT, const float* __restrict__ text, float* __restrict__ embed,
-                  float* __restrict__ logits) {
+                  const float* __restrict__ projT, float* __restrict__ embed, float* __restrict__ n2part) {
     __shared__ float part[8][CL_FEAT];
     __shared__ float pooled[CL_FEAT];
     __shared__ float red[8];
@@ -321,28 +322,64 @@ clip_final_kernel(const float* __restrict__ X, const float* __restrict__ g, cons
         pooled[e] = t * (1.f / CL_WT);
     }
     __syncthreads();
-    float y0 = 0.f, y1 = 0.f;
-    for (int k = 0; k < CL_FEAT; ++k) {
+    // projection: this CTA's 64 of the 512 outputs; thread = (4 outputs, 48 of the 768 inputs), float4 weight loads.  One CTA
+    // per image with a 768-long dependent load loop per thread was latency-bound (40 us at batch 32 on 32 of the 148 SMs).
+    const int c4 = tid & 15, ks = tid >> 4;
+    float* pp = &part[0][0];                              // re-used: [16 k slices][64 outputs]
+#pragma unroll 1
+    for (int unit = blockIdx.y; unit < CL_PROJ / CL_PSLICE; unit += gridDim.y) {      // large batches: fewer, fatter CTAs
+    const int c0 = unit * CL_PSLICE;
+    float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+    for (int k = ks * 48; k < ks * 48 + 48; ++k) {
         const float pk = pooled[k];
-        y0 = fmaf(pk, __ldg(projT + (long)k * CL_PROJ + tid), y0);
-        y1 = fmaf(pk, __ldg(projT + (long)k * CL_PROJ + tid + 256), y1);
+        const float4 wv = __ldg(reinterpret_cast<const float4*>(projT + (long)k * CL_PROJ + c0) + c4);
+        y.x = fmaf(pk, wv.x, y.x); y.y = fmaf(pk, wv.y, y.y); y.z = fmaf(pk, wv.z, y.z); y.w = fmaf(pk, wv.w, y.w);
     }
-    const float n2 = block_sum_256(y0 * y0 + y1 * y1, red);
-    const float inv = 1.f / sqrtf(n2);
-    y0 *= inv; y1 *= inv;
-    embed[b * CL_PROJ + tid] = y0;
-    embed[b * CL_PROJ + tid + 256] = y1;
-    if (text != nullptr && logits != nullptr) {
-        const float t0 = __ldg(text + tid), t1 = __ldg(text + tid + 256);
-        const float tn2 = block_sum_256(t0 * t0 + t1 * t1, red);
-        const float dot = block_sum_256(y0 * t0 + y1 * t1, red);
-        if (tid == 0) logits[b] = dot / sqrtf(tn2);
+    __syncthreads();
+    *reinterpret_cast<float4*>(pp + ks * CL_PSLICE + 4 * c4) = y;
+    __syncthreads();
+    float yo = 0.f;
+    if (tid < CL_PSLICE) {
+#pragma unroll
+        for (int q = 0; q < 16; ++q) yo += pp[q * CL_PSLICE + tid];       // fixed order
+        embed[b * CL_PROJ + c0 + tid] = yo;                                // un-normalised; clip_norm_logit_kernel finishes
+    }
+    const float n2 = block_sum_256(tid < CL_PSLICE ? yo * yo : 0.f, red);
+    if (tid == 0) n2part[b * (CL_PROJ / CL_PSLICE) + unit] = n2;
+    }
+}
+
+// embedding /= its L2 norm (partial sums of squares added in a fixed order); logit = embedding . text / |text|
+__global__ void __launch_bounds__(CL_PROJ)
+clip_norm_logit_kernel(float* __restrict__ embed, const float* __restrict__ n2part, const float* __restrict__ text,
+                       float* __restrict__ logits) {
+    __shared__ float red[2][CL_PROJ / 32];
+    pdl_wait();
+    const int tid = threadIdx.x;
+    const long b = blockIdx.x;
+    float n2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < CL_PROJ / CL_PSLICE; ++c) n2 += n2part[b * (CL_PROJ / CL_PSLICE) + c];
+    const float e = embed[b * CL_PROJ + tid] * (1.f / sqrtf(n2));
+    embed[b * CL_PROJ + tid] = e;
+    if (text == nullptr || logits == nullptr) return;
+    const float t = __ldg(text + tid);
+    float dot = e * t, tt = t * t;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) { dot += __shfl_xor_sync(0xffffffffu, dot, o); tt += __shfl_xor_sync(0xffffffffu, tt, o); }
+    if ((tid & 31) == 0) { red[0][tid >> 5] = dot; red[1][tid >> 5] = tt; }
+    __syncthreads();
+    if (tid == 0) {
+        float d = 0.f, q = 0.f;
+        for (int k = 0; k < CL_PROJ / 32; ++k) { d += red[0][k]; q += red[1][k]; }
+        logits[b] = d / sqrtf(q);
     }
 }
 
 struct ClipWs {
     __nv_bfloat16 *Ape, *Hn, *QKV, *Ao, *G;
-    float *X0, *X1;
+    float *X0, *X1, *n2part;
     size_t total;
 };
 
@@ -358,6 +395,7 @@ ClipWs clip_ws(void* base, int B) {
     w.QKV = reinterpret_cast<__nv_bfloat16*>(take(T * 3 * CL_EMBED * 2));
     w.Ao = reinterpret_cast<__nv_bfloat16*>(take(T * CL_EMBED * 2));
     w.G = reinterpret_cast<__nv_bfloat16*>(take(T * 4 * CL_EMBED * 2));
+    w.n2part = reinterpret_cast<float*>(take((size_t)B * (CL_PROJ / CL_PSLICE) * 4));
     w.total = off;
     return w;
 }
@@ -520,8 +558,11 @@ int m2t_clip_encode_image(const void* d_packed, const float* d_img, int B, int H
             h /= 2; w /= 2; C *= 2; M /= 4;
         }
     }
-    M2T_CUDA(launch_pdl(clip_final_kernel, dim3((unsigned)B), dim3(256), 0, s, (const float*)X, F(L.lng), F(L.lnb), F(L.projT),
-                        d_text, d_embed, d_logits));
+    const int nsl = B >= 256 ? 1 : B >= 128 ? 2 : B >= 64 ? 4 : 8;      // every CTA re-reads its image's 150 KB: split only to fill the SMs
+    M2T_CUDA(launch_pdl(clip_final_kernel, dim3((unsigned)B, (unsigned)nsl), dim3(256), 0, s, (const float*)X, F(L.lng),
+                        F(L.lnb), F(L.projT), d_embed, ws.n2part));
+    M2T_CUDA(launch_pdl(clip_norm_logit_kernel, dim3((unsigned)B), dim3(CL_PROJ), 0, s, d_embed, (const float*)ws.n2part, d_text,
+                        d_logits));
     return M2T_OK;
 }
 
