@@ -6,7 +6,7 @@
 // Data flow per image (all buffers in HBM, token-major):
 //   resize       fp32 [3][H][W]          -> bf16 patch rows [3136][48]   (the 4x4/4 patch conv's im2col, written directly)
 //   patch embed  lin_umma K=48           -> fp32 X [3136][96], LayerNorm in place
-//   12 x layer   LN -> bf16 | qkv GEMM -> bf16 [tokens][3C] | window attention (SIMT, 49 tokens x 32 dims per head, shift and
+//   12 x layer   LN -> bf16 | qkv GEMM -> bf16 [tokens][3C] | window attention (mma.sync, 49 tokens x 32 dims per head, shift and
 //                window partition/reverse as index arithmetic) -> bf16 | proj GEMM, reduce-add into X | LN -> bf16 |
 //                fc1 GEMM + GELU -> bf16 [tokens][4C] | fc2 GEMM, reduce-add into X  (stages 1-2: one fused kernel, mlp_umma.cu,
 //                the [tokens][4C] tensor stays on the SM)
