@@ -57,6 +57,7 @@ extern "C" {
  * max-abs 2.7e-3 -> 1.7e-3) for ~10 % of the forward time.  Default: on for x2 / x3, whose single-stage tail leaves
  * less margin under the 2e-3 bar, off for x4.  These bits force it either way. */
 #define M2T_VAR_SPLIT_QKV16  (1u << 7) /* branch 1: separate qkv kernel + attention instead of the fused attn16_qkv kernel */
+#define M2T_VAR_SPLIT_QKV    (1u << 8) /* branches 2-4: separate qkv GEMM + attention kernels (QKV through HBM) instead of attn_z */
 #define M2T_VAR_PRECISE_ON   (1u << 5)
 #define M2T_VAR_PRECISE_OFF  (1u << 6)
 
@@ -155,6 +156,14 @@ int m2t_stage_qkv(uint32_t variant, const void* d_Z, const void* d_wqkv, void* d
 /* TBlock attention core (ref :310-332) on QKV [B,h,w,3C] -> O [B,h,w,C], fp16 */
 int m2t_stage_attn(uint32_t variant, int C, const void* d_QKV, const float* d_relf,
                    const void* d_relx, void* d_O, int B, int h, int w, void* stream);
+/* One whole CFTM branch k = branch+1 in {2,3,4} (ref :143-161 with :307-332 inside) as ONE kernel: qkv conv, halo
+ * attention and the branch glue, with the contractions re-associated so that q, k, v are never formed (attn_z.cu).
+ *   d_T      t_k, fp16 space-to-depth [B, h, w, C]  (C = 64: level 1, h = Hp/2;  C = 256: level 2, h = Hp/4)
+ *   d_mq     fp16 [32+C][C]  (m2t_packed_offset "body.i.attnK.mq"),  d_wv  fp16 [C][C] (the v rows of "wqkv_f")
+ *   d_Y      fp16 NHWC [B, Hp, Wp, 64]: channels 16*branch.. receive y_k = attention + t_k
+ *   d_Tnext  fp16 level-2 space-to-depth [B, Hp/4, Wp/4, 256] holding n_{k+1}/2; completed in place to t_{k+1}; or NULL */
+int m2t_stage_attn_z(int C, const void* d_T, const void* d_mq, const void* d_wv, void* d_Y, void* d_Tnext,
+                     int branch, int B, int h, int w, void* stream);
 /* CFTM.feed_forward + residual (ref :124-126,:164) + next block's InstanceNorm sums */
 int m2t_stage_ffconv(uint32_t variant, const void* d_Y, const void* d_ffw, const float* d_ffb,
                      const float* d_Xin, float* d_Xout, double* d_stats, int B, int Hp, int Wp,

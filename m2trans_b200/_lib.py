@@ -23,6 +23,7 @@ VAR_SIMT_ALL = 0xF
 VAR_UNFUSED_TAIL = 1 << 4
 VAR_PRECISE_ON, VAR_PRECISE_OFF = 1 << 5, 1 << 6
 VAR_SPLIT_QKV16 = 1 << 7
+VAR_SPLIT_QKV = 1 << 8
 PHASE_HEAD, PHASE_BODY, PHASE_TAIL, PHASE_ALL = 1, 2, 4, 7
 
 
@@ -63,6 +64,7 @@ SIGNATURES = {
     "m2t_stage_branch_post": (_i, [_i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "m2t_stage_qkv": (_i, [_u32, _vp, _vp, _vp, _i, _i, _vp]),
     "m2t_stage_attn": (_i, [_u32, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "m2t_stage_attn_z": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "m2t_stage_ffconv": (_i, [_u32, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "m2t_tail_scratch_bytes": (_sz, [_i, _i, _i, _i]),
     "m2t_stage_tail": (_i, [_u32, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp]),

@@ -145,6 +145,7 @@ size_t m2t_packed_offset(int scale, int n_blocks, const char* name) {
         if (!strcmp(what, "wqkv_f")) return A.wqkv_f;
         if (!strcmp(what, "relf")) return A.relf;
         if (!strcmp(what, "relx")) return A.relx;
+        if (!strcmp(what, "mq")) return A.mq;
         return (size_t)-1;
     }
     if (sscanf(name, "body.%d.%31s", &i, what) == 2 && i >= 0 && i < n_blocks) {
@@ -214,7 +215,9 @@ int m2t_plan_create(const m2t_cfg* cfg, m2t_plan** out) {
     p->ws_bytes = off;
     const int tail_passes = (g.B + chunk - 1) / chunk;
     const bool qkv16_fused = !(cfg->variant & (M2T_VAR_SIMT_ATTN | M2T_VAR_SIMT_QKV | M2T_VAR_SPLIT_QKV16));
-    const int per_block = (cfg->variant & M2T_VAR_SIMT_ATTN) ? (1 + 4 * 4 + 1) : (1 + 4 * 2 + 1 - (qkv16_fused ? 1 : 0));
+    const bool qkv_fused = !(cfg->variant & (M2T_VAR_SIMT_ATTN | M2T_VAR_SIMT_QKV | M2T_VAR_SPLIT_QKV));
+    const int per_block = (cfg->variant & M2T_VAR_SIMT_ATTN) ? (1 + 4 * 4 + 1)
+                                                             : (1 + 4 * 2 + 1 - (qkv16_fused ? 1 : 0) - (qkv_fused ? 3 : 0));
     // tail per image chunk: x3 and the unfused variants run up [, up], border, out; otherwise [up,] fused
     const bool tail_fused = cfg->scale != 3 && !(cfg->variant & (M2T_VAR_SIMT_TAIL | M2T_VAR_UNFUSED_TAIL));
     const int per_tail = tail_fused ? (cfg->scale == 4 ? 2 : 1) : (cfg->scale == 4 ? 4 : 3);
@@ -359,6 +362,12 @@ int m2t_forward_phases(const m2t_plan* plan, const void* d_packed, const float* 
                                               reinterpret_cast<const __half*>(W + A.relx), g.B, h, w, s, fz));
                     continue;
                 }
+                if (a > 0 && !(var & (M2T_VAR_SIMT_QKV | M2T_VAR_SPLIT_QKV))) {
+                    // branches 2-4: qkv conv inside the attention kernel, q / k / v never formed (attn_z.cu)
+                    M2T_TRY(launch_attn_z(C, Tb[a], reinterpret_cast<const __half*>(W + A.mq),
+                                          reinterpret_cast<const __half*>(W + A.wqkv_f) + (size_t)2 * C * C, g.B, h, w, s, fz));
+                    continue;
+                }
                 M2T_TRY(run_qkv(var, Tb[a], reinterpret_cast<const __half*>(W + A.wqkv_f), QKV, g.B * h * w, C, s));
                 M2T_TRY(launch_attn_umma(C, QKV, reinterpret_cast<const __half*>(W + A.relx), nullptr, g.B, h, w, s, &fz));
             }
@@ -484,6 +493,20 @@ int m2t_stage_attn(uint32_t variant, int C, const void* d_QKV, const float* d_re
     M2T_TRY(check_device());
     return run_attn(variant, C, static_cast<const __half*>(d_QKV), d_relf, static_cast<const __half*>(d_relx),
                     static_cast<__half*>(d_O), B, h, w, (cudaStream_t)stream);
+}
+
+int m2t_stage_attn_z(int C, const void* d_T, const void* d_mq, const void* d_wv, void* d_Y, void* d_Tnext, int branch,
+                     int B, int h, int w, void* stream) {
+    M2T_TRY(check_device());
+    if (!d_T || !d_mq || !d_wv || !d_Y) { set_error("stage_attn_z: null pointer"); return M2T_E_ARG; }
+    if (C != 64 && C != 256) { set_error("stage_attn_z: C=%d", C); return M2T_E_UNSUPPORTED; }
+    if (branch < 1 || branch > 3 || B < 1) { set_error("stage_attn_z: branch %d, B %d", branch, B); return M2T_E_ARG; }
+    const int lv = C == 64 ? 1 : 2;
+    AttnFuse fz{};
+    fz.T = static_cast<const __half*>(d_T); fz.Y = static_cast<__half*>(d_Y); fz.Tnext = static_cast<__half*>(d_Tnext);
+    fz.branch = branch; fz.Hp = h << lv; fz.Wp = w << lv;
+    return launch_attn_z(C, fz.T, static_cast<const __half*>(d_mq), static_cast<const __half*>(d_wv), B, h, w,
+                         (cudaStream_t)stream, fz);
 }
 
 int m2t_stage_ffconv(uint32_t variant, const void* d_Y, const void* d_ffw, const float* d_ffb, const float* d_Xin,

@@ -110,6 +110,9 @@ struct AttnW {
     size_t wqkv_f; // fp16 [3C][C]   the same with the Haar DWT folded into the columns and the IWT into the v rows
     size_t relf;   // fp32 [20][C/2] rows 0..9 rel_h, rows 10..19 rel_w
     size_t relx;   // fp16 [32][C]   rows 0..9 [rel_h|0], 10..19 [0|rel_w], 20..31 zero (MMA operand form)
+    size_t mq;     // fp16 [32+C][C] attn_z.cu: rows 0..19 = Wq'^T rel (10 rel_h, 10 rel_w terms), 20..31 zero, rows 32.. =
+                   //                (Wq'^T Wk')^T, i.e. mq[32+n][k] = sum_c Wq'[c][k] Wk'[c][n]; Wq', Wk' = the folded, q-scaled
+                   //                rows of wqkv_f before their fp16 rounding
 };
 struct BlockW {
     AttnW attn[4];
@@ -126,6 +129,7 @@ struct PackedLayout {
     size_t t3w, t3b; // x4 only: fp16 [256][64], fp32 [256]
     size_t tcw;      // fp16 [9][16][64] final 3x3 conv, rows 3..15 zero
     size_t fold_scratch;
+    size_t fold_scratch2;   // fp32 [2C][C]: folded q (scaled) and k rows for the mq products
     size_t total;
 };
 int make_packed_layout(int scale, int n_blocks, PackedLayout* out);
@@ -190,6 +194,11 @@ int launch_attn_umma(int C, const __half* QKV, const __half* relx, __half* O, in
 // attn16_qkv.cu : branch 1 with the qkv conv inside the attention kernel (fused glue only)
 int launch_attn16_qkv(const __half* T, const __half* Wqkv, const __half* relx, int B, int h, int w, cudaStream_t s,
                       const AttnFuse& fz);
+
+// attn_z.cu : branches 2-4 (C = 64 / 256) with the qkv conv inside the attention kernel, contractions re-associated so
+// that q, k, v never exist (fused glue only).  MQ = AttnW::mq, WV = the v rows of AttnW::wqkv_f.
+int launch_attn_z(int C, const __half* T, const __half* MQ, const __half* WV, int B, int h, int w, cudaStream_t s,
+                  const AttnFuse& fz);
 
 int read_attn_timing(long long* host64);   // development aid, zeros unless built with -DM2T_TIMING (256 values)
 int read_tail_timing(long long* host64);   // the same for the fused tail kernel (64 values)

@@ -21,6 +21,7 @@ int make_packed_layout(int scale, int n_blocks, PackedLayout* L) {
             L->blk[i].attn[a].wqkv_f = take((size_t)3 * C * C * 2);
             L->blk[i].attn[a].relf = take((size_t)20 * (C / 2) * 4);
             L->blk[i].attn[a].relx = take((size_t)32 * C * 2);
+            L->blk[i].attn[a].mq = take((size_t)(32 + C) * C * 2);
         }
         L->blk[i].ffw = take((size_t)9 * NF * NF * 2);
         L->blk[i].ffw2 = take((size_t)2 * 9 * NF * NF * 2);
@@ -36,6 +37,7 @@ int make_packed_layout(int scale, int n_blocks, PackedLayout* L) {
     }
     L->tcw = take((size_t)9 * 16 * NF * 2);
     L->fold_scratch = take((size_t)768 * 256 * 4);   // fp32 staging for the Haar folding at pack time
+    L->fold_scratch2 = take((size_t)512 * 256 * 4);
     L->total = off;
     return M2T_OK;
 }
@@ -132,13 +134,38 @@ __global__ void fold_rows_kernel(const float* __restrict__ W, float* __restrict_
     tmp[i] = acc;
 }
 // step 2: columns of all rows: out[n][(s,k)] = sum_band tmp[n][band*16 + k] * g[s][band]; q rows scaled
-__global__ void fold_cols_kernel(const float* __restrict__ tmp, __half* __restrict__ out, int C, int L, float qscale) {
+__global__ void fold_cols_kernel(const float* __restrict__ tmp, __half* __restrict__ out, float* __restrict__ out32,
+                                 int C, int L, float qscale) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= 3 * C * C) return;
     const int n = i / C, j = i - n * C, nb = C / NB, s = j / NB, k = j % NB;
     float acc = 0.f;
     for (int band = 0; band < nb; ++band) acc = fmaf(tmp[(long)n * C + band * NB + k], haar_g(L, s, band), acc);
-    out[i] = __float2half_rn(acc * (n < C ? qscale : 1.f));
+    const float v = acc * (n < C ? qscale : 1.f);
+    out[i] = __float2half_rn(v);
+    if (n < 2 * C) out32[i] = v;                    // unrounded q / k rows for mq_kernel
+}
+
+// attn_z.cu operand (AttnW::mq): fp16 [32 + C][C].  qk = fp32 [2C][C]: rows 0..C-1 = Wq' (folded, scaled), C..2C-1 = Wk'.
+//   row r < 10        mq[r][k] = sum_{c < C/2}  Wq'[c][k] rel_h[r][c]              (ref :322: rel_h on the first half of k)
+//   row 10 <= r < 20  mq[r][k] = sum_{c >= C/2} Wq'[c][k] rel_w[r-10][c-C/2]       (ref :323)
+//   row 32 + n        mq[32+n][k] = sum_c Wq'[c][k] Wk'[c][n]
+// Sums in fp64, one fp16 rounding at the end.
+__global__ void mq_kernel(const float* __restrict__ qk, const float* __restrict__ relh, const float* __restrict__ relw,
+                          __half* __restrict__ out, int C) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (32 + C) * C) return;
+    const int n = i / C, k = i - n * C, hc = C / 2;
+    double acc = 0.0;
+    if (n < 10) {
+        for (int c = 0; c < hc; ++c) acc += (double)qk[(long)c * C + k] * (double)relh[n * hc + c];
+    } else if (n < 20) {
+        for (int c = hc; c < C; ++c) acc += (double)qk[(long)c * C + k] * (double)relw[(n - 10) * hc + (c - hc)];
+    } else if (n >= 32) {
+        const float* wk = qk + (long)C * C;
+        for (int c = 0; c < C; ++c) acc += (double)qk[(long)c * C + k] * (double)wk[(long)c * C + (n - 32)];
+    }
+    out[i] = __float2half_rn((float)acc);
 }
 
 static int run_pack(int mode, const float* src, const float* src2, void* dst, int n, int p0, int p1, float scale,
@@ -174,9 +201,12 @@ int pack_weights_impl(const PackedLayout& L, const float* const* P, int n_params
                 float* tmp = reinterpret_cast<float*>(packed + L.fold_scratch);
                 fold_rows_kernel<<<cdiv(3 * C * C, 256), 256, 0, s>>>(wq, tmp, C, branch_level(a));
                 M2T_LAUNCH_CHECK("fold_rows_kernel");
-                fold_cols_kernel<<<cdiv(3 * C * C, 256), 256, 0, s>>>(tmp, reinterpret_cast<__half*>(packed + A.wqkv_f), C,
+                float* qk32 = reinterpret_cast<float*>(packed + L.fold_scratch2);
+                fold_cols_kernel<<<cdiv(3 * C * C, 256), 256, 0, s>>>(tmp, reinterpret_cast<__half*>(packed + A.wqkv_f), qk32, C,
                                                                      branch_level(a), qscale);
                 M2T_LAUNCH_CHECK("fold_cols_kernel");
+                mq_kernel<<<cdiv((32 + C) * C, 256), 256, 0, s>>>(qk32, relh, relw, reinterpret_cast<__half*>(packed + A.mq), C);
+                M2T_LAUNCH_CHECK("mq_kernel");
             }
             M2T_TRY(run_pack(PK_COPY_F32, relh, nullptr, packed + A.relf, 10 * hc, 0, 0, 1.f, s));
             M2T_TRY(run_pack(PK_COPY_F32, relw, nullptr, packed + A.relf + (size_t)10 * hc * 4, 10 * hc, 0, 0, 1.f, s));

@@ -285,3 +285,24 @@ def test_fused_branch1_equals_split_kernels(scale, shape):
     from m2trans_b200.synthetic import synthetic_input
     x = synthetic_input(shape[0], shape[2], shape[3], seed=11).cuda()
     assert torch.equal(_model(scale, 2)(x), _model(scale, 2, variant=_lib.VAR_SPLIT_QKV16)(x))
+
+
+@pytest.mark.parametrize("scale,shape", [(4, (2, 3, 40, 72)), (3, (1, 3, 33, 47)), (2, (1, 3, 96, 72)), (4, (1, 3, 224, 288))])
+def test_attn_z_agrees_with_split_kernels(scale, shape):
+    """Branches 2-4 run as one kernel each with the contractions re-associated (attn_z.cu, q/k/v never formed);
+    M2T_VAR_SPLIT_QKV selects the qkv GEMM + attention pair.  Different rounding points, same mathematics: the SR
+    outputs agree far inside the parity bar and both meet it."""
+    from m2trans_b200 import _lib
+    from oracle import m2trans_oracle as O
+    from m2trans_b200.synthetic import synthetic_input, synthetic_state_dict
+    x = synthetic_input(shape[0], shape[2], shape[3], seed=13)
+    ref = O.forward(synthetic_state_dict(scale, 2), x[:1])
+    mz, ms = _model(scale, 2), _model(scale, 2, variant=_lib.VAR_SPLIT_QKV)
+    yz, ys = mz(x.cuda()), ms(x.cuda())
+    assert mz.module.last_launches < ms.module.last_launches
+    d = float((yz - ys).abs().max())
+    pz, az = _metrics(yz[:1].cpu(), ref)
+    ps, as_ = _metrics(ys[:1].cpu(), ref)
+    print(f"x{scale} {shape}: attn_z vs split max-abs {d:.2e}; vs oracle attn_z {pz:.1f} dB / {az:.2e}, split {ps:.1f} dB / {as_:.2e}")
+    assert d <= 1.5e-3
+    assert pz >= PSNR_MIN and az <= MAXABS_MAX and ps >= PSNR_MIN and as_ <= MAXABS_MAX

@@ -1,0 +1,124 @@
+"""attn_z.cu (one CFTM branch as one kernel, q/k/v never formed) against a torch restatement of the SAME
+re-associated arithmetic (fp16 operands where the kernel rounds, fp32 elsewhere), through m2t_stage_attn_z.
+Covers odd window-row counts (phantom lower window), several images, both channel counts, with and without
+a next branch.  The whole-forward tests check the same kernel against the oracle and against the two-kernel path."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+h16 = lambda t: t.half().float()
+
+
+def _reference(T, MQ, WV, H, C, branch, Hp, Wp):
+    """T [B,h,w,C] fp16; MQ [32+C][C] fp16; WV [C][C] fp16; H = n_{k+1}/2 level-2 s2d [B,Hp/4,Wp/4,256] fp16 or None."""
+    B, h, w, _ = T.shape
+    L = 1 if C == 64 else 2
+    S = 1 << L
+    z = T.float()
+    zp = torch.zeros(B, h + 2, w + 2, C)
+    zp[:, 1:-1, 1:-1] = z
+    mq, wv = MQ.float(), WV.float()
+    Y = torch.zeros(B, Hp, Wp, 16)
+    Tn = H.float().clone() if H is not None else None
+    for b in range(B):
+        for wy in range(h // 8):
+            for wx in range(w // 8):
+                zq = z[b, wy * 8:wy * 8 + 8, wx * 8:wx * 8 + 8].reshape(64, C)
+                zk = zp[b, wy * 8:wy * 8 + 10, wx * 8:wx * 8 + 10].reshape(100, C)
+                qa = zq @ mq.t()                                   # [64, 32 + C]
+                A = h16(qa[:, 32:])
+                s = A @ zk.t() + (qa[:, 0:10, None] + qa[:, None, 10:20]).reshape(64, 100)
+                e = torch.exp2((s - s.max(-1, keepdim=True).values) * 1.4426950408889634)
+                pz = h16((h16(e) @ zk) / e.sum(-1, keepdim=True))
+                o = pz @ wv.t() + zq                                # y_k in space-to-depth order [64, C]
+                o = o.reshape(8, 8, S, S, 16)                       # [qy][qx][dy][dx][k]
+                yfull = o.permute(0, 2, 1, 3, 4).reshape(8 * S, 8 * S, 16)
+                Y[b, wy * 8 * S:(wy + 1) * 8 * S, wx * 8 * S:(wx + 1) * 8 * S] = yfull
+    if Tn is not None:
+        # t_{k+1} = n_{k+1}/2 + y_k/2 in level-2 space-to-depth order: channel (fy&3)*4+(fx&3) of pixel (fy>>2, fx>>2)
+        y2 = Y.reshape(B, Hp // 4, 4, Wp // 4, 4, 16).permute(0, 1, 3, 2, 4, 5).reshape(B, Hp // 4, Wp // 4, 256)
+        Tn = Tn + 0.5 * y2
+    return Y, Tn
+
+
+@pytest.mark.parametrize("C,B,h,w,has_next", [(64, 1, 16, 16, True), (64, 2, 32, 48, True), (256, 1, 8, 8, True),
+                                               (256, 2, 24, 16, True), (256, 3, 40, 24, False), (64, 1, 16, 32, False),
+                                               (256, 5, 56, 72, True)])
+def test_attn_z_matches_torch(C, B, h, w, has_next):
+    from m2trans_b200 import _lib
+    lib = _lib.load()
+    L = 1 if C == 64 else 2
+    Hp, Wp = h << L, w << L
+    g = torch.Generator().manual_seed(C * 1000 + h * 10 + w)
+    T = torch.randn(B, h, w, C, generator=g).half()
+    MQ = torch.zeros(32 + C, C)
+    MQ[:20] = torch.randn(20, C, generator=g) * 0.15
+    MQ[32:] = torch.randn(C, C, generator=g) * (0.5 / C)
+    MQ = MQ.half()
+    WV = (torch.randn(C, C, generator=g) * (1.0 / C) ** 0.5).half()
+    branch = 1 if C == 64 else 2
+    H = (torch.randn(B, Hp // 4, Wp // 4, 256, generator=g) * 0.5).half() if has_next else None
+    Yd = torch.full((B, Hp, Wp, 64), 7.0, dtype=torch.float16, device="cuda")
+    Hd = H.cuda().clone() if has_next else None
+    Td, MQd, WVd = T.cuda(), MQ.cuda(), WV.cuda()
+    _lib.check(lib.m2t_stage_attn_z(C, Td.data_ptr(), MQd.data_ptr(), WVd.data_ptr(), Yd.data_ptr(),
+                                    Hd.data_ptr() if has_next else None, branch, B, h, w, None), "m2t_stage_attn_z")
+    torch.cuda.synchronize()
+    Yr, Tr = _reference(T, MQ, WV, H, C, branch, Hp, Wp)
+    got = Yd.float().cpu()
+    assert torch.isfinite(got).all()
+    err = (got[..., 16 * branch:16 * branch + 16] - Yr).abs().max().item()
+    print(f"attn_z C={C} B={B} {h}x{w}: y max-abs {err:.2e} (rms of y {Yr.pow(2).mean().sqrt():.3f})")
+    assert err <= 6e-3                                             # fp16 output rounding of |y| <= ~6 plus operand noise
+    other = torch.cat((got[..., :16 * branch], got[..., 16 * branch + 16:]), -1)
+    assert (other == 7.0).all()                                    # other branches' channels untouched
+    if has_next:
+        terr = (Hd.float().cpu() - Tr).abs().max().item()
+        print(f"   t_next max-abs {terr:.2e}")
+        assert terr <= 4e-3
+
+
+def _haar_g(L):
+    sgn = [[1, 1, 1, 1], [-1, -1, 1, 1], [-1, 1, -1, 1], [1, -1, -1, 1]]
+    n = 4 ** L
+    G = torch.zeros(n, n, dtype=torch.float64)                      # [s][band]
+    for s in range(n):
+        for band in range(n):
+            if L == 1:
+                dy, dx = s >> 1, s & 1
+                G[s, band] = 0.5 * sgn[band][dy + 2 * dx]
+            else:
+                dy, dx = s >> 2, s & 3
+                P, p = (dy >> 1) + 2 * (dx >> 1), (dy & 1) + 2 * (dx & 1)
+                G[s, band] = 0.25 * sgn[band >> 2][P] * sgn[band & 3][p]
+    return G
+
+
+@pytest.mark.parametrize("attn,C", [(2, 64), (3, 256)])
+def test_packed_mq_matches_its_definition(attn, C):
+    """pack.cu mq_kernel: rows 0..19 = Wq'^T rel, rows 32.. = (Wq'^T Wk')^T with the Haar folding and the q scale."""
+    import types
+    from m2trans_b200 import _lib
+    from m2trans_b200.M2Trans_network import M2Trans
+    from m2trans_b200.synthetic import synthetic_state_dict
+    lib = _lib.load()
+    sd = synthetic_state_dict(4, 0)
+    m = M2Trans(types.SimpleNamespace(scale=4, rgb_range=1.0, colors=3, n_feats=64, n_blocks=8)).cuda()
+    m.load_state_dict(sd, strict=True)
+    m(torch.rand(1, 3, 32, 32, device="cuda"))
+    st = m._m2t.per_device[torch.cuda.current_device()]
+    off = lib.m2t_packed_offset(4, 8, f"body.5.attn{attn}.mq".encode())
+    base = (-st.packed.data_ptr()) % 256
+    got = st.packed[base + off: base + off + (32 + C) * C * 2].view(torch.float16).view(32 + C, C).float().cpu()
+    L = 1 if C == 64 else 2
+    Gk = torch.kron(_haar_g(L), torch.eye(16, dtype=torch.float64))                  # [s*16+k][band*16+k]
+    W = sd[f"body.5.attn{attn}.qkv_conv.weight"].reshape(3 * C, C).double()
+    Wq, Wk = (W[:C] * C ** -0.5) @ Gk.t(), W[C:2 * C] @ Gk.t()
+    half = C // 2
+    want = torch.zeros(32 + C, C, dtype=torch.float64)
+    want[:10] = sd[f"body.5.attn{attn}.rel_h"].reshape(10, half).double() @ Wq[:half]
+    want[10:20] = sd[f"body.5.attn{attn}.rel_w"].reshape(10, half).double() @ Wq[half:]
+    want[32:] = (Wq.t() @ Wk).t()
+    err = (got.double() - want).abs().max().item()
+    print(f"mq attn{attn}: max-abs {err:.2e}, max |mq| {want.abs().max().item():.3f}")
+    assert err <= 1e-3 * max(1.0, want.abs().max().item())
