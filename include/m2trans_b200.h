@@ -287,6 +287,10 @@ int m2t_debug_profile_forward(const m2t_plan* plan, const void* d_packed, const 
  * softmax done, glue operands issued, O ready, epilogue done).  All zero unless the library was
  * built with M2T_TIMING=1 (development builds only). */
 int m2t_debug_attn_timing(long long* host64);
+/* attn_z.cu stamps: 3 x 64 values (branches 2..4); CTA 0, epilogue thread 0, pairs it < 6 at [10 it + 0..8]: pair start, A ready,
+ * AQ written, S ready, P written, PZ ready, PZ written, O ready, pair done; [60], [61] kernel entry / prologue done.  Zeros
+ * unless the library was built with M2T_TIMING=1. */
+int m2t_debug_az_timing(long long* host192);
 /* m2t_probe_tma: builds a tiled tensor map over d_tensor (dims / strides_bytes / box given
  * innermost first, HOST arrays of `rank` entries; swizzle 0 none, 1 32B, 2 64B, 3 128B), loads
  * one box at `coords` (may be negative / out of bounds: zero fill) into 1024-byte-aligned

@@ -160,6 +160,9 @@ class CFTM(nn.Module):
         raise M2TError("CFTM is executed by M2Trans.forward (fused kernels); it has no standalone forward")
 
 
+_MAX_PLANS = 12
+
+
 class _DeviceState:
     """Per-device engine state shared by DataParallel replicas: packed weights + plans."""
 
@@ -198,6 +201,8 @@ class M2Trans(nn.Module):
         self.kernel_variant = int(getattr(args, "kernel_variant", _lib.VAR_DEFAULT))
         # replay the forward's launch sequence from a CUDA graph (set False, or M2T_CUDA_GRAPH=0, for eager launches)
         self.cuda_graph = bool(getattr(args, "cuda_graph", os.environ.get("M2T_CUDA_GRAPH", "1") != "0"))
+        # concurrent image groups inside the graph (0 = automatic, see _image_groups)
+        self.image_groups = int(getattr(args, "image_groups", os.environ.get("M2T_IMAGE_GROUPS", "0")))
 
         rgb_mean = (0.4488, 0.4371, 0.4040)
         rgb_std = (1.0, 1.0, 1.0)
@@ -254,6 +259,7 @@ class M2Trans(nn.Module):
                             "whose dimensions in the checkpoint are {}.".format(name, own[name].size(), param.size()))
             elif strict and "tail" not in name:
                 raise KeyError('unexpected key "{}" in state_dict'.format(name))
+        self.invalidate()                                   # own[name].copy_() bumps _version; belt and braces
         if strict:
             missing = set(own.keys()) - set(state_dict.keys())
             if missing:
@@ -327,8 +333,8 @@ class M2Trans(nn.Module):
         st.packed, st.packed_key = packed, key
         return packed
 
-    def _plan(self, st: _DeviceState, b: int, h: int, w: int, device) -> dict:
-        key = (b, h, w, self.kernel_variant)
+    def _plan(self, st: _DeviceState, b: int, h: int, w: int, device, group: int = 0) -> dict:
+        key = (b, h, w, self.kernel_variant, group)
         plan = st.plans.get(key)
         if plan is None:
             lib = _lib.load()
@@ -337,12 +343,42 @@ class M2Trans(nn.Module):
             handle = C.c_void_p()
             _lib.check(lib.m2t_plan_create(C.byref(cfg), C.byref(handle)), "m2t_plan_create")
             ws = torch.empty(lib.m2t_workspace_bytes(handle) + 256, dtype=torch.uint8, device=device)
-            plan = {"handle": handle, "ws": ws, "launches": lib.m2t_plan_num_launches(handle)}
-            if len(st.plans) >= 8:                      # bound the workspace cache
+            plan = {"handle": handle, "ws": ws, "launches": lib.m2t_plan_num_launches(handle), "uses": 0}
+            while len(st.plans) >= _MAX_PLANS:          # bound the workspace cache: evict the least recently used
                 old = st.plans.pop(next(iter(st.plans)))
                 lib.m2t_plan_destroy(old["handle"])
-            st.plans[key] = plan
+        else:
+            del st.plans[key]                           # re-insert: dict order = recency
+        st.plans[key] = plan
         return plan
+
+    def invalidate(self) -> None:
+        """Drop the packed weights and captured graphs; the next forward re-packs from the current parameters.
+        Needed after IN-PLACE edits through `.data` (p.data.mul_(2), p.data.copy_(...)): those keep the tensor's
+        address and version counter, so the (data_ptr, _version) cache key cannot see them.  load_state_dict, .to(),
+        .cuda(), .half()/.float() and optimiser-style in-place ops on the Parameters themselves are detected."""
+        with self._m2t.lock:
+            for st in self._m2t.per_device.values():
+                st.packed_key = None
+                for plan in st.plans.values():
+                    plan.pop("graph", None)
+                    plan.pop("graph_key", None)
+
+    repack = invalidate
+
+    def _apply(self, fn, *args, **kwargs):              # .to() / .cuda() / .float(): parameters are replaced or rewritten
+        out = super()._apply(fn, *args, **kwargs)
+        if "_m2t" in self.__dict__:
+            self.invalidate()
+        return out
+
+    def _image_groups(self, b: int, h: int, w: int) -> int:
+        """Frames are independent (InstanceNorm is per image), so a batch may run as G concurrent chains of b/G frames
+        on G streams inside one CUDA graph (args.image_groups / M2T_IMAGE_GROUPS).  Measured on B200 it does not pay:
+        cfg2 1.414 ms with one chain, 1.450 with two, 1.63 with four (the big-shared-memory kernels of two chains
+        cannot share an SM, so the chains mostly serialise and pay twice the fixed costs); cfg3 gains 3 %.  Default 1."""
+        g = self.image_groups
+        return max(1, min(g if g > 0 else 1, b))
 
     @torch.no_grad()
     def forward(self, x):
@@ -357,38 +393,79 @@ class M2Trans(nn.Module):
         with torch.cuda.device(device), self._m2t.lock:
             st = self._device_state(device)
             packed = self._packed_weights(st, device)
-            plan = self._plan(st, b, h, w, device)
-            self.last_launches = plan["launches"]
-            out_shape = (b, 3, h * self.scale, w * self.scale)
+            s = self.scale
+            replica = "_former_parameters" in self.__dict__
+            stream = torch.cuda.current_stream(device)
+            y = torch.empty((b, 3, h * s, w * s), dtype=torch.float32, device=device)
+            # image groups: contiguous chunks of the batch, each with its own plan / workspace
+            ng = 1 if (replica or not self.cuda_graph) else self._image_groups(b, h, w)
+            bounds = [(b * i) // ng for i in range(ng + 1)]
+            plans = [self._plan(st, bounds[i + 1] - bounds[i], h, w, device, group=i) for i in range(ng)]
+            self.last_launches = sum(p["launches"] for p in plans)
+            in_px, out_px = 3 * h * w, 3 * h * s * w * s
 
-            def launch(xin, yout):
-                _lib.check(lib.m2t_forward(plan["handle"], _aligned_ptr(packed), xin.data_ptr(), yout.data_ptr(),
-                                           _aligned_ptr(plan["ws"]), _stream_ptr(device)), "m2t_forward")
-
-            # DataParallel replicas run concurrently in one thread per device; graph capture is a process-wide mode
-            # (another thread's allocation invalidates it), so replicas launch eagerly.
-            if not self.cuda_graph or torch.cuda.is_current_stream_capturing() or "_former_parameters" in self.__dict__:
-                y = torch.empty(out_shape, dtype=torch.float32, device=device)
-                launch(x, y)
-                return y
-            # CUDA-graph replay (m2t_forward never synchronises or allocates).  Only the CFTM blocks are captured: they
-            # touch nothing but the plan's workspace and the packed weights, so the graph is independent of the caller's
-            # tensors.  The head conv (1 launch, reads x) and the tail (2-3 launches per image chunk, writes y) are
-            # launched directly on the caller's tensors around the replay: no staging copy in, no 50 MB clone out.
-            def phases(mask, xin, yout):
+            def phases(plan, mask, gi):
+                xin = x.data_ptr() + 4 * in_px * bounds[gi] if mask & _lib.PHASE_HEAD else None
+                yout = y.data_ptr() + 4 * out_px * bounds[gi] if mask & _lib.PHASE_TAIL else None
                 _lib.check(lib.m2t_forward_phases(plan["handle"], _aligned_ptr(packed), xin, yout,
                                                   _aligned_ptr(plan["ws"]), _stream_ptr(device), mask), "m2t_forward_phases")
 
-            y = torch.empty(out_shape, dtype=torch.float32, device=device)
-            if plan.get("graph_key") != packed.data_ptr():
-                launch(x, y)                                 # eager warm-up: one-time attribute / driver lookups
-                graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph):
-                    phases(_lib.PHASE_BODY, None, None)
-                plan.update(graph=graph, graph_key=packed.data_ptr())
-            phases(_lib.PHASE_HEAD, x.data_ptr(), None)
-            plan["graph"].replay()
-            phases(_lib.PHASE_TAIL, None, y.data_ptr())
+            # A plan's workspace is shared by every forward of that shape: a forward issued on another stream must wait
+            # for the previous user of the workspace (multi-stream pipelining, per-thread default streams).
+            for plan in plans:
+                last = plan.get("last")
+                if last is not None and last[0] != stream.cuda_stream:
+                    stream.wait_event(last[1])
+            head = plans[0]
+            head["uses"] += 1
+            # DataParallel replicas run concurrently in one thread per device and re-pack on every call: they launch
+            # eagerly.  So does the FIRST forward of a shape (one-off shapes, e.g. an eval loop over frames of varying
+            # size, never pay for a capture), and any forward issued while the caller is capturing a graph itself.
+            eager = (not self.cuda_graph or replica or torch.cuda.is_current_stream_capturing()
+                     or (head.get("graph_key") != packed.data_ptr() and head["uses"] < 2))
+            if not eager and head.get("graph_key") != packed.data_ptr():
+                # CUDA-graph capture of the CFTM blocks only: they touch nothing but the plan's workspace and the packed
+                # weights, so the graph is independent of the caller's tensors.  The head conv (reads x) and the tail
+                # (writes y) are launched directly on the caller's tensors around the replay.
+                try:
+                    graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                        main = torch.cuda.current_stream(device)
+                        if ng > 1:
+                            fork = torch.cuda.Event()
+                            fork.record(main)
+                            side = head.setdefault("side_streams", [torch.cuda.Stream(device) for _ in range(ng - 1)])
+                            joins = []
+                            for gi in range(1, ng):
+                                side[gi - 1].wait_event(fork)
+                                with torch.cuda.stream(side[gi - 1]):
+                                    phases(plans[gi], _lib.PHASE_BODY, gi)
+                                    ev = torch.cuda.Event()
+                                    ev.record(side[gi - 1])
+                                    joins.append(ev)
+                        phases(plans[0], _lib.PHASE_BODY, 0)
+                        for ev in (joins if ng > 1 else []):
+                            main.wait_event(ev)
+                    head.update(graph=graph, graph_key=packed.data_ptr())
+                except Exception:                        # capture refused (another capture in flight, ...): stay eager
+                    head.pop("graph", None)
+                    head["graph_key"] = None
+                    head["uses"] = 0
+                    eager = True
+            if eager:
+                for gi, plan in enumerate(plans):
+                    phases(plan, _lib.PHASE_ALL, gi)
+            else:
+                for gi, plan in enumerate(plans):
+                    phases(plan, _lib.PHASE_HEAD, gi)
+                head["graph"].replay()
+                for gi, plan in enumerate(plans):
+                    phases(plan, _lib.PHASE_TAIL, gi)
+            if not torch.cuda.is_current_stream_capturing():
+                done = torch.cuda.Event()
+                done.record(stream)
+                for plan in plans:
+                    plan["last"] = (stream.cuda_stream, done)
             return y
 
     @torch.no_grad()
@@ -412,22 +489,29 @@ class M2Trans(nn.Module):
         return buf.value.decode()
 
     def engine_tensor(self, x_shape, name: str) -> torch.Tensor:
-        """Test hook: view of an internal NHWC tensor ('res', 'x' fp32; 'y' fp16) of the plan that
-        served the last forward of shape `x_shape` on the current device."""
+        """Test hook: copy of an internal NHWC tensor ('res', 'x' fp32; 'y' fp16) of the plan(s) that served the
+        last forward of shape `x_shape` on the current device (one plan per image group, concatenated)."""
         lib = _lib.load()
         b, _, h, w = x_shape
         st = self._device_state(torch.device("cuda", torch.cuda.current_device()))
-        plan = st.plans[(b, h, w, self.kernel_variant)]
-        hp, wp = C.c_int(), C.c_int()
-        _lib.check(lib.m2t_plan_padded(plan["handle"], C.byref(hp), C.byref(wp)), "m2t_plan_padded")
-        off = lib.m2t_workspace_offset(plan["handle"], name.encode())
-        if off == C.c_size_t(-1).value:
-            raise KeyError(name)
-        base = _aligned_offset(plan["ws"]) + off
-        n = b * hp.value * wp.value * 64
-        if name == "y":
-            return plan["ws"][base: base + n * 2].view(torch.float16).view(b, hp.value, wp.value, 64)
-        return plan["ws"][base: base + n * 4].view(torch.float32).view(b, hp.value, wp.value, 64)
+        replica = "_former_parameters" in self.__dict__
+        ng = 1 if (replica or not self.cuda_graph) else self._image_groups(b, h, w)
+        parts = []
+        for gi in range(ng):
+            bg = (b * (gi + 1)) // ng - (b * gi) // ng
+            plan = st.plans[(bg, h, w, self.kernel_variant, gi)]
+            hp, wp = C.c_int(), C.c_int()
+            _lib.check(lib.m2t_plan_padded(plan["handle"], C.byref(hp), C.byref(wp)), "m2t_plan_padded")
+            off = lib.m2t_workspace_offset(plan["handle"], name.encode())
+            if off == C.c_size_t(-1).value:
+                raise KeyError(name)
+            base = _aligned_offset(plan["ws"]) + off
+            n = bg * hp.value * wp.value * 64
+            if name == "y":
+                parts.append(plan["ws"][base: base + n * 2].view(torch.float16).view(bg, hp.value, wp.value, 64))
+            else:
+                parts.append(plan["ws"][base: base + n * 4].view(torch.float32).view(bg, hp.value, wp.value, 64))
+        return torch.cat(parts, 0) if len(parts) > 1 else parts[0]
 
 
 def _aligned_offset(t: torch.Tensor) -> int:

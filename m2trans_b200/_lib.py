@@ -86,6 +86,7 @@ SIGNATURES = {
     "m2t_u8hwc_to_f32chw": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _vp]),
     "m2t_probe_umma": (_i, [_vp, _u32, _vp, _u32, _u64, _u64, _u32, _u32, _i, _u32, _i, _vp, _vp]),
     "m2t_debug_attn_timing": (_i, [C.POINTER(C.c_longlong)]),
+    "m2t_debug_az_timing": (_i, [C.POINTER(C.c_longlong)]),
     "m2t_debug_profile_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_char_p, _sz]),
     "m2t_probe_tma": (_i, [_vp, _i, _i, C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u32), _i,
                            C.POINTER(C.c_int32), _vp, _u32, _vp]),

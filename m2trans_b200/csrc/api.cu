@@ -538,4 +538,9 @@ int m2t_debug_attn_timing(long long* host64) {
     return read_qkv_timing(host64 + 384);
 }
 
+int m2t_debug_az_timing(long long* host192) {
+    if (!host192) { set_error("null pointer"); return M2T_E_ARG; }
+    return read_az_timing(host192);
+}
+
 }  // extern "C"

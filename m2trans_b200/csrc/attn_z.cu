@@ -106,6 +106,8 @@ __device__ __forceinline__ AzPair az_pair(int p, const AzDiv& nwx, const AzDiv& 
     return c;
 }
 
+__device__ __forceinline__ void az_prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // TMEM [this warp's 32 lanes][64 columns] fp32 (times scale) -> fp16 row m of a 128-byte-swizzled K-major chunk
 __device__ __forceinline__ void az_cvt_chunk(uint32_t taddr, uint8_t* chunk, int m, float scale) {
     uint32_t r[64];
@@ -125,6 +127,13 @@ __device__ __forceinline__ void az_cvt_chunk(uint32_t taddr, uint8_t* chunk, int
         *reinterpret_cast<uint4*>(row + ((q ^ (m & 7)) << 4)) = u;
     }
 }
+
+#ifdef M2T_TIMING
+__device__ long long g_az_dbg[3 * 64];     // per branch 2..4: CTA 0, epilogue thread 0: stamps [10 it + slot], it < 6; [60], [61] prologue
+#define M2T_ZT(slot) do { if (blockIdx.x == 0 && tid == 0 && it < 6) g_az_dbg[64 * (fz.branch - 1) + (slot) + 10 * it] = clock64(); } while (0)
+#else
+#define M2T_ZT(slot) do { } while (0)
+#endif
 
 template <int C, bool LO>
 __global__ void __launch_bounds__(AzCfg<C>::THREADS, AzCfg<C>::MIN_CTAS)
@@ -149,10 +158,14 @@ attn_z_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ 
     uint64_t* pzs_ready = bars + 15;         // PZ / sum written to smem
     uint64_t* o_full = bars + 16;
     uint64_t* pair_done = bars + 17;         // O consumed and the tile no longer needed
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+    uint64_t* x_full = bars + 18;            // [4] extra MQ slots in the operand region (free from o_full to a_full)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
     float* sinv = reinterpret_cast<float*>(sm + CF::OFF_INV);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+#ifdef M2T_TIMING
+    if (blockIdx.x == 0 && tid == 0) g_az_dbg[64 * (fz.branch - 1) + 60] = clock64();
+#endif
     const int nwx_i = w / BLK, nwy = h / BLK, npy = (nwy + 1) / 2;
     const AzDiv nwx((uint32_t)nwx_i), per_img((uint32_t)(npy * nwx_i));
 
@@ -174,6 +187,7 @@ attn_z_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ 
         mbar_init(pzs_ready, CF::NEPI);
         mbar_init(o_full, 1);
         mbar_init(pair_done, CF::NEPI);
+        for (int s = 0; s < 4; ++s) mbar_init(&x_full[s], 1);
         mbar_fence_init();
         tma_prefetch_desc(&mapT);
         tma_prefetch_desc(&mapMQ);
@@ -184,6 +198,9 @@ attn_z_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ 
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     pdl_trigger();
+#ifdef M2T_TIMING
+    if (blockIdx.x == 0 && tid == 0) g_az_dbg[64 * (fz.branch - 1) + 61] = clock64();
+#endif
 
     if (warp == 4) {
         // ---- TMA producer ------------------------------------------------------------------------------------
@@ -198,7 +215,18 @@ attn_z_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ 
             __syncwarp();
             ++g;
         };
-        auto mq_box = [&](int i) { ring_load(&mapMQ, i / 3, (i % 3) * 128); };     // i = 0..11: (kb, 128-row slab)
+        // MQ box i = 0..11 is (K chunk i / 3, 128-row slab i % 3).  Boxes 4..7 of every pair go to four extra slots in
+        // the operand region, which nobody uses between the previous pair's last O MMA and this pair's A conversion:
+        // eight boxes are in flight before the first MMA instead of four (the stream is latency-bound: a slot round
+        // trip is ~2 K cycles against 256 cycles of MMA per box).
+        auto mq_box = [&](int i) { ring_load(&mapMQ, i / 3, (i % 3) * 128); };
+        auto mq_xbox = [&](int i) {
+            if (elect_one_sync()) {
+                mbar_expect_tx(&x_full[i - 4], AZ_SLOT);
+                tma_load_2d(sm + CF::OFF_OPER + (i - 4) * AZ_SLOT, &mapMQ, &x_full[i - 4], (i / 3) * 64, (i % 3) * 128);
+            }
+            __syncwarp();
+        };
         if constexpr (!RING) {
             if (elect_one_sync()) {                      // constants: loaded while the previous kernel drains
                 mbar_expect_tx(w_full, CF::W_BYTES);
@@ -212,7 +240,11 @@ attn_z_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ 
             const AzPair pc = az_pair(p, nwx, per_img);
             // the first four weight boxes do not wait for this pair's MMAs (the ring has four slots), the tile does
             // not wait for the ring: issuing in this order cannot deadlock and lets the weights run ahead
-            if constexpr (RING) { mq_box(0); mq_box(1); mq_box(2); mq_box(3); }
+            if constexpr (RING) {
+                mq_box(0); mq_box(1); mq_box(2); mq_box(3);
+                mbar_wait(o_full, (it & 1) ^ 1);           // the previous pair's O MMAs have read PZ: the operand region is free
+                mq_xbox(4); mq_xbox(5); mq_xbox(6); mq_xbox(7);
+            }
             if (it == 0) pdl_wait();
             mbar_wait(pair_done, (it & 1) ^ 1);
             if (elect_one_sync()) {
@@ -222,7 +254,7 @@ attn_z_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ 
             }
             __syncwarp();
             if constexpr (RING) {
-                for (int i = 4; i < 3 * NBLK; ++i) mq_box(i);
+                for (int i = 8; i < 3 * NBLK; ++i) mq_box(i);
                 for (int i = 0; i < 2 * NBLK; ++i) ring_load(&mapWV, i / 2, (i % 2) * 128);
             }
         }
@@ -241,22 +273,25 @@ attn_z_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ 
             tc_fence_after();
             // phase 1: [QR | A] = Zq . MQ^T
             if constexpr (RING) {
-                for (int i = 0; i < 3 * NBLK; ++i, ++g) {
+                for (int i = 0; i < 3 * NBLK; ++i) {
                     const int kb = i / 3, sl = i % 3;
+                    const bool extra = i >= 4 && i < 8;                  // boxes 4..7 sit in the operand region
                     const uint32_t s = g % CF::NSLOT, ph = (g / CF::NSLOT) & 1;
-                    mbar_wait(&r_full[s], ph);
+                    if (extra) mbar_wait(&x_full[i - 4], it & 1);
+                    else mbar_wait(&r_full[s], ph);
                     tc_fence_after();
                     if (elect_one_sync()) {
                         const uint64_t da0 = umma_desc_at(tmpl_q, base + CF::OFF_TILE + kb * AZ_CHUNK + AZ_QOFF);
-                        const uint64_t db0 = umma_desc_at(tmpl, base + CF::OFF_W + s * AZ_SLOT);
+                        const uint64_t db0 = umma_desc_at(tmpl, extra ? base + CF::OFF_OPER + (i - 4) * AZ_SLOT : base + CF::OFF_W + s * AZ_SLOT);
                         const uint32_t idesc = sl < 2 ? umma_idesc_f16(128, 128) : umma_idesc_f16(128, 32);
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
                             umma_f16_ss(tmem_base + sl * 128, da0 + 2 * k, db0 + 2 * k, idesc, (kb | k) ? 1u : 0u);
-                        umma_commit(&r_empty[s]);
+                        if (!extra) umma_commit(&r_empty[s]);
                         if (i == 3 * NBLK - 1) umma_commit(a_full);
                     }
                     __syncwarp();
+                    if (!extra) ++g;
                 }
             } else {
                 if (elect_one_sync()) {
@@ -347,8 +382,10 @@ attn_z_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ 
         pdl_wait();
         for (int p = blockIdx.x; p < npairs; p += gridDim.x, ++it) {
             // ---- phase 2: A -> fp16 operand tile ---------------------------------------------------------------------
+            M2T_ZT(0);
             mbar_wait(a_full, it & 1);
             tc_fence_after();
+            M2T_ZT(1);
 #pragma unroll 1
             for (int c = ch0; c < ch0 + CH_N; ++c)
                 az_cvt_chunk(tmem_base + lane_sel + CF::TM_A + c * 64, oper + c * AZ_OPCH, m, 1.f);
@@ -356,12 +393,14 @@ attn_z_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ 
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(aq_ready);
+            M2T_ZT(2);
 
             // ---- phase 4: softmax over this window's 100 keys ------------------------------------------------------------
             float inv;
             if (!helper) {
                 mbar_wait(s_full, it & 1);
                 tc_fence_after();
+                M2T_ZT(3);
                 float sv[104];
                 uint32_t ab[24];
                 {
@@ -439,23 +478,15 @@ attn_z_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ 
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(p_ready);
+                M2T_ZT(4);
             } else {
                 mbar_wait(p_ready, it & 1);                 // the primaries have published 1/sum of this pair
                 inv = sinv[m];
             }
 
-            // ---- phase 6: PZ / sum -> fp16 operand tile ---------------------------------------------------------------
-            mbar_wait(pz_full, it & 1);
-            tc_fence_after();
-#pragma unroll 1
-            for (int c = ch0; c < ch0 + CH_N; ++c)
-                az_cvt_chunk(tmem_base + lane_sel + CF::TM_A + c * 64, oper + c * AZ_OPCH, m, inv);
-            fence_proxy_async();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(pzs_ready);
-
-            // ---- phase 8: fused branch glue (ref :143-161), as in attn_umma_kernel ---------------------------------------
+            // ---- glue set-up, issued early: the n_{k+1}/2 segments of Tnext (and the first t_k residuals) depend only on
+            //      earlier kernels, so their loads go out now and land under the PZ / O MMAs (issued just before the O
+            //      accumulator was read they cost 1-2 K cycles per 64-channel block, 6-10 K per pair in branch 3) -----------
             // With the Haar transforms folded into the weights the accumulator row IS IWT^L(attention) in space-to-depth
             // order: column s*16+k belongs to pixel s = dy*2^L + dx of this level pixel's 2^L x 2^L block.
             //   y_k = O' + t_k -> Y[..., 16k..16k+15];   t_{k+1} = n_{k+1}/2 (pre-filled) + y_k/2 -> Tnext in place
@@ -482,7 +513,7 @@ attn_z_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ 
 #pragma unroll
                 for (int j = 0; j < JN; ++j) ldg256(fz.Tnext + tnext_off(nb * SPB + j0 + j), dst[2 * j], dst[2 * j + 1]);
             };
-            uint4 lcur[2 * JN], lnxt[2 * JN];                 // rounding residuals of t_k (precise mode)
+            uint4 lcur[2 * JN], lnxt[2 * JN];                 // rounding residuals of t_k (precise mode), one block ahead
             auto load_l = [&](int nb, uint4* dst) {
 #pragma unroll
                 for (int j = 0; j < JN; ++j) {
@@ -491,12 +522,42 @@ attn_z_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ 
                 }
             };
             if (valid) {
+                // Tnext was written by branch_prep_all several kernels ago and has usually left L2: pull every segment
+                // this thread will touch back into L2 now (no registers held), block 0 also into registers
+                if (has_next) {
+#pragma unroll
+                    for (int nb = 1; nb < NBLK; ++nb)
+#pragma unroll
+                        for (int j = 0; j < JN; ++j) az_prefetch_l2(fz.Tnext + tnext_off(nb * SPB + j0 + j));
+                    load_h(0, hcur);
+                }
+                if constexpr (LO) {
+#pragma unroll
+                    for (int nb = 1; nb < NBLK; ++nb)
+#pragma unroll
+                        for (int j = 0; j < JN; ++j) az_prefetch_l2(fz.Tlo + trow_off + (nb * SPB + j0 + j) * NB);
+                }
                 load_l(0, lcur);
-                if (has_next) load_h(0, hcur);
             }
+
+            // ---- phase 6: PZ / sum -> fp16 operand tile ---------------------------------------------------------------
+            mbar_wait(pz_full, it & 1);
+            tc_fence_after();
+            M2T_ZT(5);
+#pragma unroll 1
+            for (int c = ch0; c < ch0 + CH_N; ++c)
+                az_cvt_chunk(tmem_base + lane_sel + CF::TM_A + c * 64, oper + c * AZ_OPCH, m, inv);
+            fence_proxy_async();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(pzs_ready);
+            M2T_ZT(6);
+
+            // ---- phase 8: fused branch glue (ref :143-161), as in attn_umma_kernel ---------------------------------------
             mbar_wait(o_full, it & 1);
             mbar_wait(tile_full, it & 1);                     // completed long ago: makes the TMA-written t_k rows visible here
             tc_fence_after();
+            M2T_ZT(7);
 #pragma unroll 1
             for (int nb = 0; nb < NBLK; ++nb) {
                 if (valid && nb + 1 < NBLK) {
@@ -572,6 +633,7 @@ attn_z_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ 
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(pair_done);
+            M2T_ZT(8);
         }
     }
     tc_fence_before();
@@ -610,6 +672,15 @@ int launch_attn_z_c(const __half* T, const __half* MQ, const __half* WV, int B, 
 }
 
 }  // namespace
+
+#ifdef M2T_TIMING
+int read_az_timing(long long* host64) {
+    M2T_CUDA(cudaMemcpyFromSymbol(host64, g_az_dbg, sizeof(long long) * 192));
+    return M2T_OK;
+}
+#else
+int read_az_timing(long long* host64) { memset(host64, 0, sizeof(long long) * 192); return M2T_OK; }
+#endif
 
 // T: t_k space-to-depth fp16 [B,h,w,C]; MQ: fp16 [C+32][C] (AttnW::mq); WV: fp16 [C][C] (the v rows of AttnW::wqkv_f)
 int launch_attn_z(int C, const __half* T, const __half* MQ, const __half* WV, int B, int h, int w, cudaStream_t s,

@@ -203,7 +203,8 @@ int launch_attn_z(int C, const __half* T, const __half* MQ, const __half* WV, in
 int read_attn_timing(long long* host64);   // development aid, zeros unless built with -DM2T_TIMING (256 values)
 int read_tail_timing(long long* host64);   // the same for the fused tail kernel (64 values)
 int read_conv_timing(long long* host64);   // the same for the tcgen05 ff conv (64 values)
-int read_qkv_timing(long long* host64);    // the same for the 256-channel qkv GEMM (64 values)
+int read_qkv_timing(long long* host64);
+int read_az_timing(long long* host64);     // the same for attn_z (192 values: 64 per branch 2..4)    // the same for the 256-channel qkv GEMM (64 values)
 
 // conv_simt.cu : X_out = conv3x3_zero(Y) + bias + X_in, plus InstanceNorm partial sums
 // res/xr (optional): also write xr = fp16(Xout + res), the tail's first GEMM operand (ref :70)

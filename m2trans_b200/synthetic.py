@@ -51,10 +51,17 @@ def state_dict_spec(scale: int, n_blocks: int = 8, n_feats: int = N_FEATS, color
     return spec
 
 
+# (out_gain, out_shift) per scale for which the SR output of the seeded checkpoints lies inside (0, 1) for ~95 % of
+# the pixels: with the plain initialisation about half of every output is clamped to 0, which hides errors.
+UNCLAMPED_TAIL = {2: (0.7, 0.004), 3: (0.7, 0.004), 4: (1.5, 0.02)}
+
+
 def synthetic_state_dict(scale: int, seed: int = 0, n_blocks: int = 8, qkv_gain: float = 1.0,
-                         rgb_range: float = 1.0) -> "OrderedDict[str, torch.Tensor]":
+                         rgb_range: float = 1.0, out_gain: float = 1.0, out_shift: float = 0.0) -> "OrderedDict[str, torch.Tensor]":
     """Reference-shaped fp32 state dict.  `qkv_gain` > 1 gives the "sharp softmax"
-    stress checkpoint of SURVEY.md section 8c."""
+    stress checkpoint of SURVEY.md section 8c.  `out_gain` / `out_shift` rescale and offset the weights of the last
+    3x3 conv (w * gain + shift): its inputs are GELU outputs with a positive mean, so a positive shift moves the SR
+    image into the interior of [0, 1] like a trained network's output (see UNCLAMPED_TAIL)."""
     g = torch.Generator(device="cpu")
     g.manual_seed(1000 * scale + seed)
     sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
@@ -79,6 +86,8 @@ def synthetic_state_dict(scale: int, seed: int = 0, n_blocks: int = 8, qkv_gain:
             prefix = key[: key.rfind(".") + 1]
             bound = 1.0 / math.sqrt(fan_in_of[prefix])
             t = (torch.rand(shape, generator=g) * 2.0 - 1.0) * bound
+        if key == ("tail.6.weight" if scale == 4 else "tail.3.weight") and (out_gain != 1.0 or out_shift != 0.0):
+            t = t * out_gain + out_shift
         sd[key] = t.float().contiguous()
     return sd
 
@@ -112,6 +121,8 @@ def synthetic_input(batch: int, h: int, w: int, seed: int = 33, kind: str = "uni
         base = torch.nn.functional.interpolate(lo, size=(h, w), mode="bilinear", align_corners=True)
         sp = torch.rand(batch, 3, h, w, generator=g)
         return (base * (0.35 + 0.65 * sp)).clamp(0.0, 1.0).float()
+    if kind == "flat":        # low contrast: InstanceNorm divides by a small sigma and amplifies whatever noise there is
+        return (0.5 + 0.02 * (torch.rand(batch, 3, h, w, generator=g) - 0.5)).float()
     raise ValueError(kind)
 
 

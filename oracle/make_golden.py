@@ -47,19 +47,21 @@ def weight_checksum(sd) -> np.ndarray:
     return np.array([s, a], dtype=np.float64)
 
 
-def full_forward_case(name, scale, seed, shape, qkv_gain=1.0, kind="uniform"):
-    ckpt = reference_checkpoint(scale, seed, qkv_gain=qkv_gain)
+def full_forward_case(name, scale, seed, shape, qkv_gain=1.0, kind="uniform", out_gain=1.0, out_shift=0.0):
+    if ONLY and not any(o in name for o in ONLY):
+        return
+    ckpt = reference_checkpoint(scale, seed, qkv_gain=qkv_gain, out_gain=out_gain, out_shift=out_shift)
     model = torch.nn.DataParallel(refnet.M2Trans(ref_args(scale)))
     model.load_state_dict(ckpt["model_state_dict"], strict=True)   # as ref test.py:70
     model.eval()
     x = synthetic_input(*shape, seed=33 + seed, kind=kind)
     y = model.module(x)
-    sd = synthetic_state_dict(scale, seed, qkv_gain=qkv_gain)
-    np.savez(os.path.join(OUT, name + ".npz"), x=x.numpy(), y=y.contiguous().numpy(),
-             scale=np.int64(scale), seed=np.int64(seed), qkv_gain=np.float64(qkv_gain),
-             wsum=weight_checksum(sd))
+    sd = synthetic_state_dict(scale, seed, qkv_gain=qkv_gain, out_gain=out_gain, out_shift=out_shift)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), x=x.numpy(), y=y.contiguous().numpy(),
+                        scale=np.int64(scale), seed=np.int64(seed), qkv_gain=np.float64(qkv_gain),
+                        out_gain=np.float64(out_gain), out_shift=np.float64(out_shift), wsum=weight_checksum(sd))
     print(name, tuple(x.shape), "->", tuple(y.shape), "min/max", float(y.min()), float(y.max()),
-          "clamped0", float((y == 0).float().mean()))
+          "clamped0", float((y == 0).float().mean()), "clamped1", float((y == 1).float().mean()))
 
 
 def unit_cases():
@@ -103,11 +105,14 @@ def state_dict_manifest():
     print("manifest", len(lines), "entries")
 
 
+ONLY = [a for a in sys.argv[1:] if not a.startswith("-")]      # substrings of the fixture names to (re)generate
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
-    state_dict_manifest()
-    unit_cases()
+    if not ONLY:
+        state_dict_manifest()
+        unit_cases()
     full_forward_case("fwd_x2_64x64", 2, 0, (1, 64, 64))                    # BASELINE configs[0]
     full_forward_case("fwd_x3_40x50", 3, 1, (1, 40, 50))                    # ragged: pads to 64x64
     full_forward_case("fwd_x4_24x40", 4, 2, (1, 24, 40))                    # ragged: pads to 32x64
@@ -116,3 +121,20 @@ if __name__ == "__main__":
     # by 1.0 at 3.0 on the [0,1] output), so a parity bar there measures nothing.
     full_forward_case("fwd_x4_32x32_sharp", 4, 3, (1, 32, 32), qkv_gain=1.5)
     full_forward_case("fwd_x4_b2_32x32_speckle", 4, 0, (2, 32, 32), kind="speckle")
+    # Unclamped fixtures.  With the plain initialisation 46-65 % of every output above is clamped to exactly 0, where any
+    # implementation is trivially exact; these checkpoints rescale / offset the last conv (synthetic.UNCLAMPED_TAIL) so
+    # that ~95 % of the SR pixels lie strictly inside (0, 1) and the 50 dB / 2e-3 bar bites on the whole image.
+    from m2trans_b200.synthetic import UNCLAMPED_TAIL as UT  # noqa: E402
+    full_forward_case("unc_x2_64x64", 2, 0, (1, 64, 64), out_gain=UT[2][0], out_shift=UT[2][1])
+    full_forward_case("unc_x3_40x50", 3, 1, (1, 40, 50), out_gain=UT[3][0], out_shift=UT[3][1])
+    full_forward_case("unc_x4_24x40", 4, 2, (1, 24, 40), out_gain=UT[4][0], out_shift=UT[4][1])
+    full_forward_case("unc_x4_b2_32x32_speckle", 4, 0, (2, 32, 32), kind="speckle", out_gain=UT[4][0], out_shift=UT[4][1])
+    # sharp softmax (qkv gain 1.5) on speckle frames, x4 and x3
+    full_forward_case("unc_x4_32x32_sharp_speckle", 4, 3, (1, 32, 32), qkv_gain=1.5, kind="speckle",
+                      out_gain=UT[4][0], out_shift=0.6 * UT[4][1])
+    full_forward_case("unc_x3_64x40_sharp_speckle", 3, 5, (1, 64, 40), qkv_gain=1.5, kind="speckle",
+                      out_gain=UT[3][0], out_shift=0.6 * UT[3][1])
+    # low contrast (InstanceNorm divides by a small sigma)
+    full_forward_case("unc_x2_48x64_flat", 2, 4, (1, 48, 64), kind="flat", out_gain=UT[2][0], out_shift=UT[2][1])
+    # one frame of BASELINE configs[1] at its full size
+    full_forward_case("unc_x4_128x128_cfg2_frame", 4, 6, (1, 128, 128), out_gain=UT[4][0], out_shift=UT[4][1])

@@ -22,7 +22,7 @@ def test_graph_replay_matches_eager_and_survives_reuse():
     assert graphed.cuda_graph and not eager.cuda_graph
     xs = [synthetic_input(2, 40, 56, seed=s).cuda() for s in (1, 2, 3)]
     outs = []
-    for x in xs + xs[:1]:                               # 4 calls: capture on the first, replay afterwards
+    for x in xs + xs[:1]:                               # 4 calls: eager first, capture on the second, replay afterwards
         ye, yg = eager(x), graphed(x)
         assert yg.shape == ye.shape
         # fp64 atomics order can flip a few fp16 roundings: same tolerance as run-to-run determinism
