@@ -204,22 +204,25 @@ int m2t_plan_create(const m2t_cfg* cfg, m2t_plan** out) {
     for (int a = 0; a < 4; ++a) p->o_lo[a] = take(P * NB * 2);   // fp16 rounding residuals of t_1..t_4 (residual path)
     p->o_stats = take((size_t)(cfg->n_blocks + 1) * g.B * NF * 2 * sizeof(double));
     p->o_munorm = take((size_t)g.B * NF * sizeof(float2));
-    // tail scratch: process images in chunks of at most ~2 GiB of intermediates
-    const size_t per_img = m2t_tail_scratch_bytes(cfg->scale, 1, g.Hp, g.Wp);
-    int chunk = (int)(((size_t)2 << 30) / per_img);
+    // tail scratch: only what the selected tail variant really writes (the fused x2 tail needs none, the fused x4 tail
+    // only T1); images go through the tail in equal chunks of at most ~2 GiB of intermediates (32-bit element indices)
+    const bool tail_fused = cfg->scale != 3 && !(cfg->variant & (M2T_VAR_SIMT_TAIL | M2T_VAR_UNFUSED_TAIL));
+    const size_t per_img = tail_fused ? (cfg->scale == 4 ? tail_t1_bytes(4, 1, g.Hp, g.Wp) : 0)
+                                      : m2t_tail_scratch_bytes(cfg->scale, 1, g.Hp, g.Wp);
+    int chunk = per_img ? (int)(((size_t)2 << 30) / per_img) : g.B;
     if (chunk < 1) chunk = 1;
     if (chunk > g.B) chunk = g.B;
+    const int tail_passes = (g.B + chunk - 1) / chunk;
+    chunk = (g.B + tail_passes - 1) / tail_passes;                // equal passes
     p->tail_chunk = chunk;
     p->o_xr = take(P * NF * 2);
-    p->o_t1 = take(m2t_tail_scratch_bytes(cfg->scale, chunk, g.Hp, g.Wp));
+    p->o_t1 = take(tail_fused ? per_img * chunk + 256 : m2t_tail_scratch_bytes(cfg->scale, chunk, g.Hp, g.Wp));
     p->ws_bytes = off;
-    const int tail_passes = (g.B + chunk - 1) / chunk;
     const bool qkv16_fused = !(cfg->variant & (M2T_VAR_SIMT_ATTN | M2T_VAR_SIMT_QKV | M2T_VAR_SPLIT_QKV16));
     const bool qkv_fused = !(cfg->variant & (M2T_VAR_SIMT_ATTN | M2T_VAR_SIMT_QKV | M2T_VAR_SPLIT_QKV));
     const int per_block = (cfg->variant & M2T_VAR_SIMT_ATTN) ? (1 + 4 * 4 + 1)
                                                              : (1 + 4 * 2 + 1 - (qkv16_fused ? 1 : 0) - (qkv_fused ? 3 : 0));
     // tail per image chunk: x3 and the unfused variants run up [, up], border, out; otherwise [up,] fused
-    const bool tail_fused = cfg->scale != 3 && !(cfg->variant & (M2T_VAR_SIMT_TAIL | M2T_VAR_UNFUSED_TAIL));
     const int per_tail = tail_fused ? (cfg->scale == 4 ? 2 : 1) : (cfg->scale == 4 ? 4 : 3);
     p->n_launches = 1 /*head*/ + cfg->n_blocks * per_block + tail_passes * per_tail;
     *out = p;
@@ -273,10 +276,14 @@ static int run_tail(uint32_t variant, int scale, const PackedLayout& L, const ui
     const int pad1 = scale == 4 ? 0 : 1;
     if (tc && scale != 3 && !(variant & M2T_VAR_UNFUSED_TAIL)) {
         // last PixelShuffle(2) stage + GELU + 3x3 conv + clamp + crop in one kernel (tail_fused.cu)
-        if (scale == 2) return launch_tail_fused(XR, w0, b0p, wc, y, B, g.Hp, g.Wp, hout, wout, b0, rgb_range, s);
+        const bool tiled = (variant & M2T_VAR_TILE_TAIL) != 0;
+        if (scale == 2) return tiled ? launch_tail_fused(XR, w0, b0p, wc, y, B, g.Hp, g.Wp, hout, wout, b0, rgb_range, s)
+                                     : launch_tail_strip(XR, w0, b0p, wc, y, B, g.Hp, g.Wp, hout, wout, b0, rgb_range, s);
         M2T_TRY(launch_tail_up_umma(XR, w0, b0p, T1, B, g.Hp, g.Wp, 2, 0, s));
-        return launch_tail_fused(T1, reinterpret_cast<const __half*>(W + L.t3w), reinterpret_cast<const float*>(W + L.t3b),
-                                 wc, y, B, 2 * g.Hp, 2 * g.Wp, hout, wout, b0, rgb_range, s);
+        const __half* w3 = reinterpret_cast<const __half*>(W + L.t3w);
+        const float* b3 = reinterpret_cast<const float*>(W + L.t3b);
+        return tiled ? launch_tail_fused(T1, w3, b3, wc, y, B, 2 * g.Hp, 2 * g.Wp, hout, wout, b0, rgb_range, s)
+                     : launch_tail_strip(T1, w3, b3, wc, y, B, 2 * g.Hp, 2 * g.Wp, hout, wout, b0, rgb_range, s);
     }
     if (tc) M2T_TRY(launch_tail_up_umma(XR, w0, b0p, T1, B, g.Hp, g.Wp, r0, pad1, s));
     else M2T_TRY(launch_tail_up_simt(XR, w0, b0p, T1, B, g.Hp, g.Wp, r0, pad1, s));

@@ -241,6 +241,10 @@ int launch_tail_out_umma(const __half* T, const __half* Wc, float* y, int Bc, in
 int launch_tail_fused(const __half* A, const __half* W1, const float* bias, const __half* Wc, float* y, int Bc, int h,
                       int w, int hout, int wout, int b0, float rgb_range, cudaStream_t s);
 
+// tail_strip.cu : the same stage as tail_fused, strip-marching with warp-specialised GELU / conv-epilogue roles
+int launch_tail_strip(const __half* A, const __half* W1, const float* bias, const __half* Wc, float* y, int Bc, int h,
+                      int w, int hout, int wout, int b0, float rgb_range, cudaStream_t s);
+
 // pack.cu
 int pack_weights_impl(const PackedLayout& L, const float* const* params, int n_params, uint8_t* packed,
                       cudaStream_t s);

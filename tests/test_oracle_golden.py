@@ -46,13 +46,25 @@ def test_cftm(golden_dir):
 
 
 FWD = ["fwd_x2_64x64", "fwd_x3_40x50", "fwd_x4_24x40", "fwd_x4_32x32_sharp", "fwd_x4_b2_32x32_speckle"]
+# reference outputs of checkpoints whose last conv is rescaled / offset so that ~95 % of the SR pixels lie strictly inside
+# (0, 1): with the plain initialisation half of every output is clamped to 0, where any implementation is exact
+UNCLAMPED = ["unc_x2_64x64", "unc_x3_40x50", "unc_x4_24x40", "unc_x4_b2_32x32_speckle", "unc_x4_32x32_g125_speckle",
+             "unc_x3_64x40_g125_speckle", "unc_x4_32x32_sharp_speckle", "unc_x3_64x40_sharp_speckle", "unc_x2_48x64_flat",
+             "unc_x4_128x128_cfg2_frame"]
 
 
-@pytest.mark.parametrize("name", FWD)
+def golden_state_dict(g):
+    """The seeded checkpoint a fixture was generated with (older fixtures carry no out_gain / out_shift)."""
+    kw = {"qkv_gain": float(g["qkv_gain"])}
+    if "out_gain" in g.files:
+        kw.update(out_gain=float(g["out_gain"]), out_shift=float(g["out_shift"]))
+    return synthetic_state_dict(int(g["scale"]), int(g["seed"]), **kw)
+
+
+@pytest.mark.parametrize("name", FWD + UNCLAMPED)
 def test_forward(golden_dir, name):
     g = _load(golden_dir, name + ".npz")
-    scale, seed, gain = int(g["scale"]), int(g["seed"]), float(g["qkv_gain"])
-    sd = synthetic_state_dict(scale, seed, qkv_gain=gain)
+    sd = golden_state_dict(g)
     # the seeded weights are the ones the fixture was generated with
     np.testing.assert_allclose(_wsum(sd), g["wsum"], rtol=1e-12)
     y = O.forward(sd, torch.from_numpy(g["x"]))
@@ -60,6 +72,9 @@ def test_forward(golden_dir, name):
     ref = torch.from_numpy(g["y"])
     assert O.max_abs(y, ref) <= 2e-5
     assert O.psnr(y, ref) >= 90.0
+    if name in UNCLAMPED:                              # the fixture really is unclamped
+        clamped = float(((ref <= 0.0) | (ref >= 1.0)).float().mean())
+        assert clamped <= (0.16 if ("sharp" in name or "g125" in name) else 0.05), clamped
 
 
 def test_forward_accepts_dataparallel_prefix(golden_dir):
