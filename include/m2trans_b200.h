@@ -191,6 +191,13 @@ int m2t_stage_tail(uint32_t variant, int scale, int n_blocks, const void* d_pack
 size_t m2t_transblock_workspace_bytes(int B, int N, int dim);
 int m2t_transblock_forward(const float* d_x, float* d_y, const float* const* d_params, int n_params,
                            int B, int N, int dim, int num_heads, void* d_workspace, void* stream);
+/* The two sub-modules of util/rlutrans.py on their own (the reference only calls them from TransBlock.forward, but they
+ * are public classes): EffAttention.forward (ref :47-66; d_params = reduce.weight, qkv.weight, proj.weight, proj.bias;
+ * workspace as for the block) and Mlp.forward (ref :21-27; d_params = fc1.weight, fc1.bias, fc2.weight, fc2.bias). */
+int m2t_rlutrans_attention(const float* d_x, float* d_y, const float* const* d_params, int n_params, int B, int N, int dim,
+                           int num_heads, void* d_workspace, void* stream);
+int m2t_rlutrans_mlp(const float* d_x, float* d_y, const float* const* d_params, int n_params, long tokens, int dim,
+                     int hidden, void* stream);
 
 /* ---- MedCLIP image-embedding pass ------------------------------------------
  * Replaces the image side of SemanticLoss.__call__ (ref losses.py:53-54 bicubic resize to 224x224 with
@@ -261,6 +268,9 @@ int m2t_eval_psnr_ssim(const float* d_sr, const float* d_hr, int B, int colors, 
  * device: d_src uint8 [B][H][W][colors] (the image arrays the loader keeps in RAM) -> d_dst fp32 [B][colors][H][W] =
  * float(u8) / denom (IEEE division: bit-identical to torch).  colors 1 or 3.  3 bytes per pixel cross PCIe instead of 12. */
 int m2t_u8hwc_to_f32chw(const void* d_src, float* d_dst, int B, int H, int W, int colors, float denom, void* stream);
+/* The inverse, for writing SR batches out as images: fp32 CHW -> uint8 HWC, dst = clamp(rint(src * scale), 0, 255)
+ * (round half to even, like torch.round).  4x fewer bytes over PCIe than the fp32 batch. */
+int m2t_f32chw_to_u8hwc(const float* d_src, void* d_dst, int B, int H, int W, int colors, float scale, void* stream);
 
 /* ---- hardware probes (development aids; tests/test_probes.py) ---------------------------
  * m2t_probe_umma: copies two raw shared-memory images (A, B operands), issues k_steps

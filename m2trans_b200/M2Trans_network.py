@@ -113,9 +113,15 @@ class TBlock(nn.Module):
         h, w multiples of 8 -> [B,C,h,w] fp32.  (The reference pads other sizes, ref :297-302;
         inside M2Trans that never triggers.)"""
         _require_cuda_f32(x, "TBlock.forward")
+        if x.dim() != 4 or x.shape[1] not in (16, 64, 256) or x.shape[1] != 2 * self.rel_h.shape[-1]:
+            raise M2TError(f"TBlock.forward: unsupported shape {tuple(x.shape)} for a block of {2 * self.rel_h.shape[-1]} channels")
+        h0, w0 = x.shape[2:]
+        pad_r, pad_b = (8 - w0 % 8) % 8, (8 - h0 % 8) % 8
+        if pad_r or pad_b:                                   # ref :297-302: reflect pad right / bottom to a multiple of the block
+            if pad_r >= w0 or pad_b >= h0:
+                raise M2TError(f"TBlock.forward: reflect padding {h0}x{w0} to multiples of 8 needs pad < size (the reference raises too)")
+            x = F.pad(x, (0, pad_r, 0, pad_b), mode="reflect")
         b, c, h, w = x.shape
-        if c not in (16, 64, 256) or h % 8 or w % 8 or (b * h * w) % 64:
-            raise M2TError(f"TBlock.forward: unsupported shape {tuple(x.shape)}")
         lib = _lib.load()
         with torch.cuda.device(x.device):
             st = _stream_ptr(x.device)
@@ -135,7 +141,10 @@ class TBlock(nn.Module):
                        "m2t_stage_qkv")
             _lib.check(lib.m2t_stage_attn(variant, c, qkv.data_ptr(), relf.data_ptr(), relx.data_ptr(), o.data_ptr(),
                                           b, h, w, st), "m2t_stage_attn")
-            return o.float().permute(0, 3, 1, 2).contiguous()
+            out = o.float().permute(0, 3, 1, 2)
+            if pad_r or pad_b:
+                out = out[:, :, :h0, :w0]                    # ref :339
+            return out.contiguous()
 
 
 class CFTM(nn.Module):
@@ -156,8 +165,61 @@ class CFTM(nn.Module):
         self.down = DWT()
         self.up = IWT()
 
+    @torch.no_grad()
     def forward(self, x):
-        raise M2TError("CFTM is executed by M2Trans.forward (fused kernels); it has no standalone forward")
+        """ref :132-164 on the engine, for calling a block on its own (`model.body[i](x)`): x [B,64,H,W] fp32 CUDA with H, W
+        multiples of 32 (what M2Trans.forward hands its blocks after check_image_size; the two Haar levels and the 8x8
+        attention blocks need it) -> same shape.  Runs the same kernels as M2Trans.forward through a one-block plan: the
+        input goes into the plan's fp32 NHWC residual stream, its InstanceNorm sums are formed here (inside M2Trans the
+        producing kernel's epilogue supplies them), and the block output is read back from the stream."""
+        _require_cuda_f32(x, "CFTM.forward")
+        if x.dim() != 4 or x.shape[1] != 64 or x.shape[2] % 32 or x.shape[3] % 32:
+            raise M2TError(f"CFTM.forward: expected [B,64,H,W] with H, W multiples of 32, got {tuple(x.shape)}")
+        from ._params import state_tensors
+        lib = _lib.load()
+        b, _, h, w = x.shape
+        dev = x.device
+        own = [p.detach() for p in state_tensors(self)]
+        if len(own) != 14 or any(p.device != dev or p.dtype != torch.float32 for p in own):
+            raise M2TError("CFTM.forward: the block's 14 parameters must be float32 on the input's device")
+        with torch.cuda.device(dev):
+            st = self.__dict__.setdefault("_m2t_block", {})
+            key = tuple((p.data_ptr(), p._version) for p in own)
+            if st.get("key") != key or st.get("dev") != dev:
+                # a one-block x2 model around this block: head / tail / mean-shift tensors are never touched by the body
+                z = lambda *shape: torch.zeros(shape, dtype=torch.float32, device=dev)
+                full = [z(3, 3, 1, 1), z(3), z(3, 3, 1, 1), z(3), z(64, 3, 3, 3), z(64)] + [p.contiguous() for p in own] + \
+                       [z(256, 64, 1, 1), z(256), z(3, 64, 3, 3)]
+                ptrs = (C.c_void_p * len(full))(*[t.data_ptr() for t in full])
+                packed = torch.empty(lib.m2t_packed_weight_bytes(2, 1) + 256, dtype=torch.uint8, device=dev)
+                _lib.check(lib.m2t_pack_weights(2, 1, ptrs, len(full), _aligned_ptr(packed), _stream_ptr(dev)), "m2t_pack_weights")
+                st.update(key=key, dev=dev, packed=packed, plans={})
+            plan = st["plans"].get((b, h, w))
+            if plan is None:
+                cfg = m2t_cfg(2, 64, 1, 3, b, h, w, _lib.VAR_DEFAULT, 1.0)
+                handle = C.c_void_p()
+                _lib.check(lib.m2t_plan_create(C.byref(cfg), C.byref(handle)), "m2t_plan_create")
+                ws = torch.empty(lib.m2t_workspace_bytes(handle) + 256, dtype=torch.uint8, device=dev)
+                if len(st["plans"]) >= 4:
+                    lib.m2t_plan_destroy(st["plans"].pop(next(iter(st["plans"])))["handle"])
+                plan = st["plans"][(b, h, w)] = {"handle": handle, "ws": ws}
+            ws, base = plan["ws"], _aligned_offset(plan["ws"])
+
+            def view(name, nbytes, dtype):
+                off = base + lib.m2t_workspace_offset(plan["handle"], name.encode())
+                return ws[off: off + nbytes].view(dtype)
+            n = b * h * w * 64
+            xin = x.permute(0, 2, 3, 1).contiguous()                                   # NHWC
+            view("res", n * 4, torch.float32).copy_(xin.reshape(-1))
+            stats = view("stats", 2 * b * 64 * 2 * 8, torch.float64).view(2, b, 64, 2)
+            xd = xin.double().reshape(b, h * w, 64)
+            stats.zero_()
+            stats[0, :, :, 0] = xd.sum(1)
+            stats[0, :, :, 1] = (xd * xd).sum(1)
+            _lib.check(lib.m2t_forward_phases(plan["handle"], _aligned_ptr(st["packed"]), None, None, _aligned_ptr(ws),
+                                              _stream_ptr(dev), _lib.PHASE_BODY), "m2t_forward_phases")
+            out = view("x", n * 4, torch.float32).view(b, h, w, 64).permute(0, 3, 1, 2).contiguous()
+        return out
 
 
 _MAX_PLANS = 12

@@ -71,6 +71,8 @@ SIGNATURES = {
     "m2t_stage_tail": (_i, [_u32, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp]),
     "m2t_transblock_workspace_bytes": (_sz, [_i, _i, _i]),
     "m2t_transblock_forward": (_i, [_vp, _vp, C.POINTER(_vp), _i, _i, _i, _i, _i, _vp, _vp]),
+    "m2t_rlutrans_attention": (_i, [_vp, _vp, C.POINTER(_vp), _i, _i, _i, _i, _i, _vp, _vp]),
+    "m2t_rlutrans_mlp": (_i, [_vp, _vp, C.POINTER(_vp), _i, C.c_long, _i, _i, _vp]),
     "m2t_clip_param_count": (_i, []),
     "m2t_clip_packed_bytes": (_sz, []),
     "m2t_clip_workspace_bytes": (_sz, [_i]),
@@ -85,6 +87,7 @@ SIGNATURES = {
     "m2t_metrics_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "m2t_eval_psnr_ssim": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp]),
     "m2t_u8hwc_to_f32chw": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _vp]),
+    "m2t_f32chw_to_u8hwc": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _vp]),
     "m2t_probe_umma": (_i, [_vp, _u32, _vp, _u32, _u64, _u64, _u32, _u32, _i, _u32, _i, _vp, _vp]),
     "m2t_debug_attn_timing": (_i, [C.POINTER(C.c_longlong)]),
     "m2t_debug_az_timing": (_i, [C.POINTER(C.c_longlong)]),

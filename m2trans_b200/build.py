@@ -35,13 +35,37 @@ def sources():
     return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
 
 
-def _stale() -> bool:
+def source_hash() -> str:
+    """sha256 over every file the library is built from (sources, headers, the public header) and the compiler flags.
+    The hash is compiled into the library (`m2t_version()` ends with it), so whether a .so belongs to this tree is a
+    property of its content, not of file modification times (which are arbitrary after a checkout or a copy)."""
+    import hashlib
+    h = hashlib.sha256()
+    deps = sources() + sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + \
+        sorted(glob.glob(os.path.join(HERE, "..", "include", "*.h")))
+    for d in deps:
+        h.update(os.path.basename(d).encode() + b"\0")
+        with open(d, "rb") as f:
+            h.update(f.read())
+    h.update(" ".join(FLAGS).encode())
+    return h.hexdigest()[:16]
+
+
+HASH_TAG = b"m2t-src-hash:"
+
+
+def built_hash() -> str:
+    """The source hash a built library carries (searched in the file's bytes: no dlopen needed), or ''."""
     if not os.path.exists(LIB):
-        return True
-    t = os.path.getmtime(LIB)
-    deps = sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + \
-        glob.glob(os.path.join(HERE, "..", "include", "*.h")) + [os.path.abspath(__file__)]
-    return any(os.path.getmtime(d) > t for d in deps)
+        return ""
+    with open(LIB, "rb") as f:
+        blob = f.read()
+    i = blob.find(HASH_TAG)
+    return blob[i + len(HASH_TAG): i + len(HASH_TAG) + 16].decode("ascii", "replace") if i >= 0 else ""
+
+
+def _stale() -> bool:
+    return built_hash() != source_hash()
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -51,9 +75,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
     procs = []
+    tag = source_hash()
     for src in sources():
         obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
         cmd = [NVCC, *FLAGS, "-c", src, "-o", obj]
+        if os.path.basename(src) == "api.cu":
+            cmd.insert(1, f'-DM2T_SRC_HASH="{tag}"')
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd), flush=True)

@@ -107,7 +107,11 @@ static inline size_t tail_t2_bytes(int scale, int B, int Hp, int Wp) {
 extern "C" {
 
 const char* m2t_last_error(void) { return g_err; }
-const char* m2t_version(void) { return "m2trans_b200 0.1 (sm_100a)"; }
+#ifndef M2T_SRC_HASH
+#define M2T_SRC_HASH "unhashed-build"
+#endif
+// the build script compiles the sha256 of the sources in (m2trans_b200/build.py: source_hash / built_hash)
+const char* m2t_version(void) { return "m2trans_b200 0.2 (sm_100a) m2t-src-hash:" M2T_SRC_HASH; }
 
 int m2t_query_device(int* sm_major, int* sm_minor, int* sm_count) {
     int dev = 0;
@@ -243,6 +247,7 @@ size_t m2t_workspace_offset(const m2t_plan* plan, const char* name) {
     if (!strcmp(name, "res")) return plan->o_res;
     if (!strcmp(name, "x")) return plan->o_x;
     if (!strcmp(name, "y")) return plan->o_y;
+    if (!strcmp(name, "stats")) return plan->o_stats;      // fp64 [n_blocks + 1][B][64][2] InstanceNorm sums (sum, sum of squares)
     return (size_t)-1;
 }
 
@@ -437,7 +442,7 @@ int m2t_debug_profile_forward(const m2t_plan* plan, const void* d_packed, const 
     for (const auto& a : agg) {
         const char* name = "?";
         cudaFuncGetName(&name, a.fn);
-        const int w = snprintf(text + off, cap - off, "%9.1f us %5.1f%%  x%-3d %.60s\n", a.ms * 1e3f, 100.f * a.ms / total, a.n, name);
+        const int w = snprintf(text + off, cap - off, "%9.1f us %5.1f%%  x%-3d %.150s\n", a.ms * 1e3f, 100.f * a.ms / total, a.n, name);
         if (w < 0 || (size_t)w >= cap - off) break;
         off += (size_t)w;
     }
@@ -504,10 +509,10 @@ int m2t_stage_attn(uint32_t variant, int C, const void* d_QKV, const float* d_re
 
 int m2t_stage_attn_z(int C, const void* d_T, const void* d_mq, const void* d_wv, void* d_Y, void* d_Tnext, int branch,
                      int B, int h, int w, void* stream) {
-    M2T_TRY(check_device());
     if (!d_T || !d_mq || !d_wv || !d_Y) { set_error("stage_attn_z: null pointer"); return M2T_E_ARG; }
     if (C != 64 && C != 256) { set_error("stage_attn_z: C=%d", C); return M2T_E_UNSUPPORTED; }
     if (branch < 1 || branch > 3 || B < 1) { set_error("stage_attn_z: branch %d, B %d", branch, B); return M2T_E_ARG; }
+    M2T_TRY(check_device());
     const int lv = C == 64 ? 1 : 2;
     AttnFuse fz{};
     fz.T = static_cast<const __half*>(d_T); fz.Y = static_cast<__half*>(d_Y); fz.Tnext = static_cast<__half*>(d_Tnext);

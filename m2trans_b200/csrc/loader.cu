@@ -34,10 +34,37 @@ u8hwc_to_f32chw_scalar_kernel(const uint8_t* __restrict__ src, float* __restrict
     for (int c = 0; c < colors; ++c) dst[(b * colors + c) * plane + o] = __fdiv_rn((float)__ldg(src + px * colors + c), denom);
 }
 
+// fp32 CHW in [0, 1] -> uint8 HWC, the inverse conversion: what writing the SR batch to image files does
+// (round-to-nearest-even of x * scale, clamped to [0, 255]).  One thread per pixel: three strided 4-byte loads
+// (coalesced across the warp), three 1-byte stores into 3 consecutive bytes.
+__global__ void __launch_bounds__(256)
+f32chw_to_u8hwc_kernel(const float* __restrict__ src, uint8_t* __restrict__ dst, long npx, long plane, int colors, float scale) {
+    const long px = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (px >= npx) return;
+    const long b = px / plane, o = px - b * plane;
+    for (int c = 0; c < colors; ++c) {
+        const int v = __float2int_rn(src[(b * colors + c) * plane + o] * scale);
+        dst[px * colors + c] = (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
+    }
+}
+
 }  // namespace
 }  // namespace m2t
 
 using namespace m2t;
+
+extern "C" int m2t_f32chw_to_u8hwc(const float* d_src, void* d_dst, int B, int H, int W, int colors, float scale, void* stream) {
+    if (!d_src || !d_dst) { set_error("u8 writer: null pointer"); return M2T_E_ARG; }
+    if (B < 1 || H < 1 || W < 1 || (colors != 1 && colors != 3) || !(scale > 0.f)) {
+        set_error("u8 writer: bad B %d H %d W %d colors %d scale %g", B, H, W, colors, (double)scale);
+        return M2T_E_ARG;
+    }
+    M2T_TRY(check_device());
+    const long plane = (long)H * W, npx = plane * B;
+    f32chw_to_u8hwc_kernel<<<(unsigned)((npx + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_src, static_cast<uint8_t*>(d_dst), npx, plane, colors, scale);
+    M2T_LAUNCH_CHECK("f32chw_to_u8hwc");
+    return M2T_OK;
+}
 
 extern "C" int m2t_u8hwc_to_f32chw(const void* d_src, float* d_dst, int B, int H, int W, int colors, float denom, void* stream) {
     if (!d_src || !d_dst) { set_error("u8 loader: null pointer"); return M2T_E_ARG; }

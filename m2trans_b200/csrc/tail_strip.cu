@@ -206,14 +206,14 @@ tail_strip_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
                 const bool valid = ay >= 0 && ay < h && ax >= 0 && ax < w;
                 const uint32_t buf = g & 1;
                 uint8_t* ub = sm + TS_OFF_U + buf * TS_UBUF;
-                // Half of the warps of every SM sub-partition take the even U rows first, the others the odd rows: TMEM reads
-                // (64 B/clk per SM: 128 KB of accumulators per step = 2 K cycles) and the FMA-bound GELU (3 K cycles per
-                // step) then overlap across warps instead of alternating in lockstep.
+                // Measured and not kept: starting half of the warps on the odd rows (220 vs 213 us at cfg2) and reading the
+                // accumulator in 16-column chunks one chunk ahead of the GELU (248 us).  ncu: the E1 warps sit in the GELU
+                // code 96 % of the time with `math` (FMA-pipe throttle) and `not selected` as their stalls; the kernel is
+                // bound by instruction issue (316 K warp instructions per sub-partition at cfg2, 70 % issue utilisation).
 #pragma unroll 1
-                for (int hi = 0; hi < 2; ++hi) {
-                    const int hf = hi ^ (wg & 1);                              // hf = sub-pixel row uu
+                for (int hf = 0; hf < 2; ++hf) {                               // hf = sub-pixel row uu
                     mbar_wait(&acc_full[hf], g & 1);
-                    if (hi == 0) mbar_wait(&u_empty[buf], ((g >> 1) & 1) ^ 1);
+                    if (hf == 0) mbar_wait(&u_empty[buf], ((g >> 1) & 1) ^ 1);
                     tc_fence_after();
                     uint32_t rr[32];
                     tmem_ld32(tmem_base + hf * 128 + vv * NF + c0 + lanef, rr);

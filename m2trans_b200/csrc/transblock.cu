@@ -111,7 +111,7 @@ struct TbParams {           // TransBlock.state_dict() order
 constexpr int TBQ_SMEM = (TB_DIM * TB_DIM + TB_DIM * 3 * TB_DIM + 2 * TB_TOK * TB_PITCH) * 4;
 
 __global__ void __launch_bounds__(TB_THREADS)
-tb_qkv_kernel(const float* __restrict__ x, TbParams P, float* __restrict__ qkv, long total) {
+tb_qkv_kernel(const float* __restrict__ x, TbParams P, float* __restrict__ qkv, long total, int with_ln) {
     extern __shared__ __align__(16) float smf[];
     float* s_wr = smf;                               // [64][64]
     float* s_wq = s_wr + TB_DIM * TB_DIM;            // [64][192]
@@ -126,8 +126,10 @@ tb_qkv_kernel(const float* __restrict__ x, TbParams P, float* __restrict__ qkv, 
         __syncthreads();                             // weights ready / previous tile's s_x, s_r consumed
         load_tile(s_x, x, tok0, total);
         __syncthreads();
-        layer_norm_tile(s_x, s_x, P.ln1_w, P.ln1_b); // ref :85 norm1
-        __syncthreads();
+        if (with_ln) {                               // standalone EffAttention.forward (ref :47) starts at reduce
+            layer_norm_tile(s_x, s_x, P.ln1_w, P.ln1_b); // ref :85 norm1
+            __syncthreads();
+        }
         float acc[8][4];
 #pragma unroll
         for (int t = 0; t < 8; ++t) { acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f; }
@@ -238,7 +240,9 @@ tb_attn_kernel(const float* __restrict__ qkv, float* __restrict__ o, int N, int 
 constexpr int TBO_SMEM = (TB_DIM * TB_DIM + TB_DIM * TB_HID + TB_HID * TB_DIM + 2 * TB_TOK * TB_PITCH + TB_TOK * TB_HPITCH) * 4;
 
 __global__ void __launch_bounds__(TB_THREADS)
-tb_out_kernel(const float* __restrict__ x, const float* __restrict__ o, TbParams P, float* __restrict__ y, long total) {
+tb_out_kernel(const float* __restrict__ x, const float* __restrict__ o, TbParams P, float* __restrict__ y, long total, int mode) {
+    // mode 0: the TransBlock tail (proj + residual, LN2, Mlp + residual);  mode 1: EffAttention.forward's tail, y = proj(o)
+    // (ref :65);  mode 2: Mlp.forward, y = fc2(ReLU(fc1(x))) (ref :21-27; x comes in through `o`)
     extern __shared__ __align__(16) float smf[];
     float* s_wp = smf;                               // proj^T [64][64]
     float* s_w1 = s_wp + TB_DIM * TB_DIM;            // fc1^T  [64][16]
@@ -246,12 +250,12 @@ tb_out_kernel(const float* __restrict__ x, const float* __restrict__ o, TbParams
     float* s_a = s_w2 + TB_HID * TB_DIM;             // [64][68]
     float* s_x1 = s_a + TB_TOK * TB_PITCH;           // [64][68]
     float* s_h = s_x1 + TB_TOK * TB_PITCH;           // [64][20]
-    load_wT(s_wp, P.proj_w, TB_DIM, TB_DIM);
-    load_wT(s_w1, P.fc1_w, TB_HID, TB_DIM);
-    load_wT(s_w2, P.fc2_w, TB_DIM, TB_HID);
+    if (mode != 2) load_wT(s_wp, P.proj_w, TB_DIM, TB_DIM);
+    if (mode != 1) { load_wT(s_w1, P.fc1_w, TB_HID, TB_DIM); load_wT(s_w2, P.fc2_w, TB_DIM, TB_HID); }
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-    const float4 bp = make_float4(__ldg(P.proj_b + tx * 4), __ldg(P.proj_b + tx * 4 + 1), __ldg(P.proj_b + tx * 4 + 2), __ldg(P.proj_b + tx * 4 + 3));
-    const float4 b2 = make_float4(__ldg(P.fc2_b + tx * 4), __ldg(P.fc2_b + tx * 4 + 1), __ldg(P.fc2_b + tx * 4 + 2), __ldg(P.fc2_b + tx * 4 + 3));
+    float4 bp = make_float4(0.f, 0.f, 0.f, 0.f), b2 = bp;
+    if (mode != 2) bp = make_float4(__ldg(P.proj_b + tx * 4), __ldg(P.proj_b + tx * 4 + 1), __ldg(P.proj_b + tx * 4 + 2), __ldg(P.proj_b + tx * 4 + 3));
+    if (mode != 1) b2 = make_float4(__ldg(P.fc2_b + tx * 4), __ldg(P.fc2_b + tx * 4 + 1), __ldg(P.fc2_b + tx * 4 + 2), __ldg(P.fc2_b + tx * 4 + 3));
     const long tiles = (total + TB_TOK - 1) / TB_TOK;
     for (long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         const long tok0 = tile * TB_TOK;
@@ -261,18 +265,31 @@ tb_out_kernel(const float* __restrict__ x, const float* __restrict__ o, TbParams
         float x1[8][4];
 #pragma unroll
         for (int t = 0; t < 8; ++t) { x1[t][0] = bp.x; x1[t][1] = bp.y; x1[t][2] = bp.z; x1[t][3] = bp.w; }
-        tile_linear<TB_DIM>(s_a, TB_PITCH, s_wp, TB_DIM, 0, x1);           // ref :65 proj
+        if (mode != 2) {
+            tile_linear<TB_DIM>(s_a, TB_PITCH, s_wp, TB_DIM, 0, x1);       // ref :65 proj
+            if (mode == 1) {                                                // EffAttention.forward ends here
 #pragma unroll
-        for (int t = 0; t < 8; ++t) {                                       // ref :85 x + atten(...)
-            const long tok = tok0 + ty + 8 * t;
-            float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (tok < total) xv = *reinterpret_cast<const float4*>(x + tok * TB_DIM + tx * 4);
-            x1[t][0] += xv.x; x1[t][1] += xv.y; x1[t][2] += xv.z; x1[t][3] += xv.w;
-            *reinterpret_cast<float4*>(s_x1 + (ty + 8 * t) * TB_PITCH + tx * 4) = make_float4(x1[t][0], x1[t][1], x1[t][2], x1[t][3]);
+                for (int t = 0; t < 8; ++t) {
+                    const long tok = tok0 + ty + 8 * t;
+                    if (tok < total) *reinterpret_cast<float4*>(y + tok * TB_DIM + tx * 4) = make_float4(x1[t][0], x1[t][1], x1[t][2], x1[t][3]);
+                }
+                continue;
+            }
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {                                   // ref :85 x + atten(...)
+                const long tok = tok0 + ty + 8 * t;
+                float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (tok < total) xv = *reinterpret_cast<const float4*>(x + tok * TB_DIM + tx * 4);
+                x1[t][0] += xv.x; x1[t][1] += xv.y; x1[t][2] += xv.z; x1[t][3] += xv.w;
+                *reinterpret_cast<float4*>(s_x1 + (ty + 8 * t) * TB_PITCH + tx * 4) = make_float4(x1[t][0], x1[t][1], x1[t][2], x1[t][3]);
+            }
+            __syncthreads();
+            layer_norm_tile(s_x1, s_a, P.ln2_w, P.ln2_b);                   // ref :86 norm2
+            __syncthreads();
+        } else {
+#pragma unroll
+            for (int t = 0; t < 8; ++t) { x1[t][0] = x1[t][1] = x1[t][2] = x1[t][3] = 0.f; }   // no residual in Mlp.forward
         }
-        __syncthreads();
-        layer_norm_tile(s_x1, s_a, P.ln2_w, P.ln2_b);                       // ref :86 norm2
-        __syncthreads();
         {   // fc1 + ReLU (ref :22-23): thread -> token tid/2, hidden units (tid%2)*8 .. +7
             const int tok = threadIdx.x >> 1, h0 = (threadIdx.x & 1) * 8;
             float hacc[8];
@@ -343,14 +360,69 @@ int m2t_transblock_forward(const float* d_x, float* d_y, const float* const* d_p
     const int grid = (int)(tiles < 2L * sms ? tiles : 2L * sms);
     M2T_ENSURE_SMEM(tb_qkv_kernel, TBQ_SMEM);
     M2T_ENSURE_SMEM(tb_out_kernel, TBO_SMEM);
-    tb_qkv_kernel<<<grid, TB_THREADS, TBQ_SMEM, s>>>(d_x, P, qkv, total);
+    tb_qkv_kernel<<<grid, TB_THREADS, TBQ_SMEM, s>>>(d_x, P, qkv, total, 1);
     M2T_LAUNCH_CHECK("tb_qkv_kernel");
     const int n = N / 16, nchunks = (N + n - 1) / n;
     const float scale = 1.0f / sqrtf((float)TB_HD);                      // head_dim ** -0.5 (ref :35)
     tb_attn_kernel<<<dim3((unsigned)(B * nchunks), TB_HEADS), TBA_THREADS, 0, s>>>(qkv, o, N, n, nchunks,
                                                                                  scale * 1.4426950408889634f);
     M2T_LAUNCH_CHECK("tb_attn_kernel");
-    tb_out_kernel<<<grid, TB_THREADS, TBO_SMEM, s>>>(d_x, o, P, d_y, total);
+    tb_out_kernel<<<grid, TB_THREADS, TBO_SMEM, s>>>(d_x, o, P, d_y, total, 0);
+    M2T_LAUNCH_CHECK("tb_out_kernel");
+    return M2T_OK;
+}
+
+// EffAttention.forward alone (ref util/rlutrans.py:47-66): proj(BDAttn(qkv(reduce(x)))).  d_params: reduce.weight,
+// qkv.weight, proj.weight, proj.bias (EffAttention.state_dict() order); same workspace as the whole block.
+int m2t_rlutrans_attention(const float* d_x, float* d_y, const float* const* d_params, int n_params, int B, int N, int dim,
+                           int num_heads, void* d_workspace, void* stream) {
+    if (!d_x || !d_y || !d_params || !d_workspace) { set_error("rlutrans attention: null pointer"); return M2T_E_ARG; }
+    if (n_params != 4) { set_error("rlutrans attention: expected the 4 tensors of EffAttention.state_dict(), got %d", n_params); return M2T_E_ARG; }
+    if (dim != TB_DIM || num_heads != TB_HEADS) { set_error("rlutrans attention: dim %d / num_heads %d: built for 64 / 8", dim, num_heads); return M2T_E_UNSUPPORTED; }
+    if (B < 1 || N < 16) { set_error("rlutrans attention: B %d, N %d (the reference's chunk length N // 16 must be >= 1)", B, N); return M2T_E_ARG; }
+    for (int i = 0; i < 4; ++i)
+        if (!d_params[i]) { set_error("rlutrans attention: parameter %d is null", i); return M2T_E_ARG; }
+    M2T_TRY(check_device());
+    cudaStream_t s = (cudaStream_t)stream;
+    TbParams P{};
+    P.reduce_w = d_params[0]; P.qkv_w = d_params[1]; P.proj_w = d_params[2]; P.proj_b = d_params[3];
+    const long total = (long)B * N;
+    float* qkv = static_cast<float*>(d_workspace);
+    float* o = qkv + total * 3 * TB_DIM;
+    const long tiles = (total + TB_TOK - 1) / TB_TOK;
+    const int sms = device_sm_count();
+    const int grid = (int)(tiles < 2L * sms ? tiles : 2L * sms);
+    M2T_ENSURE_SMEM(tb_qkv_kernel, TBQ_SMEM);
+    M2T_ENSURE_SMEM(tb_out_kernel, TBO_SMEM);
+    tb_qkv_kernel<<<grid, TB_THREADS, TBQ_SMEM, s>>>(d_x, P, qkv, total, 0);
+    M2T_LAUNCH_CHECK("tb_qkv_kernel");
+    const int n = N / 16, nchunks = (N + n - 1) / n;
+    tb_attn_kernel<<<dim3((unsigned)(B * nchunks), TB_HEADS), TBA_THREADS, 0, s>>>(qkv, o, N, n, nchunks,
+                                                                                 (1.0f / sqrtf((float)TB_HD)) * 1.4426950408889634f);
+    M2T_LAUNCH_CHECK("tb_attn_kernel");
+    tb_out_kernel<<<grid, TB_THREADS, TBO_SMEM, s>>>(d_x, o, P, d_y, total, 1);
+    M2T_LAUNCH_CHECK("tb_out_kernel");
+    return M2T_OK;
+}
+
+// Mlp.forward alone (ref util/rlutrans.py:21-27): fc2(ReLU(fc1(x))) on `tokens` rows of 64 channels.
+// d_params: fc1.weight [16][64], fc1.bias, fc2.weight [64][16], fc2.bias (Mlp.state_dict() order).
+int m2t_rlutrans_mlp(const float* d_x, float* d_y, const float* const* d_params, int n_params, long tokens, int dim,
+                     int hidden, void* stream) {
+    if (!d_x || !d_y || !d_params) { set_error("rlutrans mlp: null pointer"); return M2T_E_ARG; }
+    if (n_params != 4) { set_error("rlutrans mlp: expected the 4 tensors of Mlp.state_dict(), got %d", n_params); return M2T_E_ARG; }
+    if (dim != TB_DIM || hidden != TB_HID) { set_error("rlutrans mlp: %d -> %d -> %d: built for 64 -> 16 -> 64", dim, hidden, dim); return M2T_E_UNSUPPORTED; }
+    if (tokens < 1) { set_error("rlutrans mlp: %ld tokens", tokens); return M2T_E_ARG; }
+    for (int i = 0; i < 4; ++i)
+        if (!d_params[i]) { set_error("rlutrans mlp: parameter %d is null", i); return M2T_E_ARG; }
+    M2T_TRY(check_device());
+    TbParams P{};
+    P.fc1_w = d_params[0]; P.fc1_b = d_params[1]; P.fc2_w = d_params[2]; P.fc2_b = d_params[3];
+    const long tiles = (tokens + TB_TOK - 1) / TB_TOK;
+    const int sms = device_sm_count();
+    const int grid = (int)(tiles < 2L * sms ? tiles : 2L * sms);
+    M2T_ENSURE_SMEM(tb_out_kernel, TBO_SMEM);
+    tb_out_kernel<<<grid, TB_THREADS, TBO_SMEM, (cudaStream_t)stream>>>(d_x, d_x, P, d_y, tokens, 2);
     M2T_LAUNCH_CHECK("tb_out_kernel");
     return M2T_OK;
 }

@@ -13,7 +13,7 @@ import torch
 from . import _lib
 from ._lib import M2TError
 
-__all__ = ["images_to_device"]
+__all__ = ["images_to_device", "images_from_device"]
 
 
 @torch.no_grad()
@@ -38,3 +38,21 @@ def images_to_device(images, device="cuda", denom: float = 255.0, non_blocking: 
         _lib.check(lib.m2t_u8hwc_to_f32chw(src.data_ptr(), dst.data_ptr(), b, h, w, c, float(denom),
                                            torch.cuda.current_stream(dev).cuda_stream), "m2t_u8hwc_to_f32chw")
     return dst
+
+
+@torch.no_grad()
+def images_from_device(sr: torch.Tensor, out: torch.Tensor = None, scale: float = 255.0) -> torch.Tensor:
+    """sr: fp32 [B,C,H,W] on a CUDA device, values in [0, 1] -> uint8 [B,H,W,C] on the same device (or into `out`),
+    equal to (sr * scale).round().clamp(0, 255).byte().permute(0, 2, 3, 1): the bytes an image writer would store.
+    Copying THIS to the host moves 3 bytes per pixel instead of 12."""
+    if not sr.is_cuda or sr.dtype != torch.float32 or sr.dim() != 4 or sr.shape[1] not in (1, 3):
+        raise M2TError(f"images_from_device: expected CUDA fp32 [B,C,H,W] with C in (1, 3), got {sr.dtype} {tuple(sr.shape)}")
+    b, c, h, w = sr.shape
+    sr = sr.contiguous()
+    lib = _lib.load()
+    with torch.cuda.device(sr.device):
+        if out is None:
+            out = torch.empty(b, h, w, c, dtype=torch.uint8, device=sr.device)
+        _lib.check(lib.m2t_f32chw_to_u8hwc(sr.data_ptr(), out.data_ptr(), b, h, w, c, float(scale),
+                                           torch.cuda.current_stream(sr.device).cuda_stream), "m2t_f32chw_to_u8hwc")
+    return out

@@ -6,9 +6,10 @@ and default initialisation (nn.Linear / nn.LayerNorm defaults), so a TransBlock 
 between the two unchanged.
 
 `TransBlock.forward` is the engine's fused three-kernel path (include/m2trans_b200.h,
-m2t_transblock_forward): CUDA fp32 in, CUDA fp32 out, no CPU or PyTorch fallback.  Mlp and
-EffAttention are parameter containers: the reference only ever calls them from TransBlock.forward
-(ref :85-86), and their arithmetic lives inside the fused kernels.
+m2t_transblock_forward): CUDA fp32 in, CUDA fp32 out, no CPU or PyTorch fallback.  The reference only
+ever calls Mlp and EffAttention from TransBlock.forward (ref :85-86), where their arithmetic lives inside
+the fused kernels; called on their own they run the same kernels in a standalone mode
+(m2t_rlutrans_mlp / m2t_rlutrans_attention).
 """
 from __future__ import annotations
 
@@ -22,6 +23,23 @@ from ._lib import M2TError
 from ._params import state_tensors
 
 __all__ = ["Mlp", "EffAttention", "TransBlock"]
+
+
+def _check_tokens(x, what, dim):
+    if not isinstance(x, torch.Tensor) or not x.is_cuda:
+        raise M2TError(f"{what}: expected a CUDA tensor; the B200 engine has no CPU path")
+    if x.dtype != torch.float32:
+        raise M2TError(f"{what}: expected float32 (the reference's dtype), got {x.dtype}")
+    if x.dim() < 2 or x.shape[-1] != dim:
+        raise M2TError(f"{what}: expected [..., {dim}], got {tuple(x.shape)}")
+
+
+def _device_params(module, x, what):
+    params = [p.detach() for p in state_tensors(module)]          # also right on DataParallel replicas
+    for p in params:
+        if p.device != x.device or p.dtype != torch.float32:
+            raise M2TError(f"{what}: parameters must be float32 on the input's device")
+    return [p.contiguous() for p in params]
 
 
 class Mlp(nn.Module):
@@ -38,8 +56,21 @@ class Mlp(nn.Module):
         self.fc2 = nn.Linear(hidden_features, out_features)
         self.drop = nn.Dropout(drop)
 
+    @torch.no_grad()
     def forward(self, x):
-        raise M2TError("Mlp.forward: fused into TransBlock.forward on the B200 engine; call the TransBlock")
+        """x [..., 64] fp32 CUDA -> same shape: fc2(ReLU(fc1(x))) (ref :21-27)."""
+        _check_tokens(x, "Mlp.forward", self.fc1.in_features)
+        if (self.fc1.in_features, self.fc1.out_features, self.fc2.out_features) != (64, 16, 64):
+            raise M2TError("Mlp.forward: the engine implements 64 -> 16 -> 64 (the TransBlock defaults, ref :81)")
+        lib = _lib.load()
+        params = _device_params(self, x, "Mlp.forward")
+        with torch.cuda.device(x.device):
+            xc = x.contiguous()
+            y = torch.empty_like(xc)
+            ptrs = (C.c_void_p * 4)(*[p.data_ptr() for p in params])
+            _lib.check(lib.m2t_rlutrans_mlp(xc.data_ptr(), y.data_ptr(), ptrs, 4, xc.numel() // 64, 64, 16,
+                                            torch.cuda.current_stream(x.device).cuda_stream), "m2t_rlutrans_mlp")
+        return y
 
 
 class EffAttention(nn.Module):
@@ -59,8 +90,23 @@ class EffAttention(nn.Module):
         self.proj = nn.Linear(dim, dim)
         self.attn_drop = nn.Dropout(attn_drop)
 
+    @torch.no_grad()
     def forward(self, x):
-        raise M2TError("EffAttention.forward: fused into TransBlock.forward on the B200 engine; call the TransBlock")
+        """x [B, N, 64] fp32 CUDA, N >= 16 -> same shape: proj(chunked attention(qkv(reduce(x)))) (ref :47-66)."""
+        _check_tokens(x, "EffAttention.forward", self.reduce.in_features)
+        if x.dim() != 3 or self.reduce.in_features != 64 or self.num_heads != 8:
+            raise M2TError(f"EffAttention.forward: expected [B, N, 64] with 8 heads, got {tuple(x.shape)}")
+        b, n, _ = x.shape
+        lib = _lib.load()
+        params = _device_params(self, x, "EffAttention.forward")
+        with torch.cuda.device(x.device):
+            xc = x.contiguous()
+            y = torch.empty_like(xc)
+            ws = torch.empty(max(int(lib.m2t_transblock_workspace_bytes(b, n, 64)), 16), dtype=torch.uint8, device=x.device)
+            ptrs = (C.c_void_p * 4)(*[p.data_ptr() for p in params])
+            _lib.check(lib.m2t_rlutrans_attention(xc.data_ptr(), y.data_ptr(), ptrs, 4, b, n, 64, self.num_heads, ws.data_ptr(),
+                                                  torch.cuda.current_stream(x.device).cuda_stream), "m2t_rlutrans_attention")
+        return y
 
 
 class TransBlock(nn.Module):

@@ -38,3 +38,29 @@ def test_metrics_and_loader_argument_errors():
     assert lib.m2t_u8hwc_to_f32chw(None, 1, 1, 4, 4, 3, 255.0, None) == E_ARG
     assert lib.m2t_u8hwc_to_f32chw(1, 1, 1, 4, 4, 2, 255.0, None) == E_ARG and "colors" in _err(lib)
     assert lib.m2t_u8hwc_to_f32chw(1, 1, 1, 4, 4, 3, 0.0, None) == E_ARG
+    assert lib.m2t_f32chw_to_u8hwc(None, 1, 1, 4, 4, 3, 255.0, None) == E_ARG
+    assert lib.m2t_f32chw_to_u8hwc(1, 1, 1, 4, 4, 2, 255.0, None) == E_ARG and "colors" in _err(lib)
+    assert lib.m2t_f32chw_to_u8hwc(1, 1, 0, 4, 4, 3, 255.0, None) == E_ARG
+
+
+def test_attn_z_stage_argument_errors():
+    lib = _lib.load()
+    assert lib.m2t_stage_attn_z(64, None, 1, 1, 1, None, 1, 1, 16, 16, None) == E_ARG
+    assert lib.m2t_stage_attn_z(128, 1, 1, 1, 1, None, 1, 1, 16, 16, None) != 0 and "C=128" in _err(lib)
+    assert lib.m2t_stage_attn_z(64, 1, 1, 1, 1, None, 0, 1, 16, 16, None) == E_ARG and "branch" in _err(lib)
+
+
+def test_bench_arms_print_the_same_config():
+    """The driver compares the `config` of the GPU arm and of `--impl reference`: one function builds both."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(os.path.dirname(os.path.dirname(__file__)), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    for name in ("cfg1", "cfg2", "cfg3", "cfg4", "cfg5"):
+        cfg = bench.workload_config(name)
+        assert list(cfg) == ["workload"] and cfg["workload"].startswith(name + ":")
+    assert bench.WORKLOADS["cfg3"][4] == "strong" and bench.WORKLOADS["cfg4"][:2] == (4, 64) and bench.WORKLOADS["cfg2"][4] == "weak"
+    from m2trans_b200.sharding import shard_range
+    assert [shard_range(32, r, 8) for r in (0, 7)] == [(0, 4), (28, 32)]         # cfg3 at 8 GPUs: 4 frames each
+    assert shard_range(64, 3, 8) == (24, 32) and shard_range(256, 7, 8) == (224, 256)

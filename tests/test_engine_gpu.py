@@ -328,3 +328,45 @@ def test_attn_z_agrees_with_split_kernels(scale, shape):
     print(f"x{scale} {shape}: attn_z vs split max-abs {d:.2e}; vs oracle attn_z {pz:.1f} dB / {az:.2e}, split {ps:.1f} dB / {as_:.2e}")
     assert d <= 1.5e-3
     assert pz >= PSNR_MIN and az <= MAXABS_MAX and ps >= PSNR_MIN and as_ <= MAXABS_MAX
+
+
+def test_cftm_forward_standalone_matches_reference_golden(golden_dir):
+    """`model.body[i](x)` on the reference surface: one CFTM through a one-block engine plan, against the fixture the
+    REAL reference CFTM produced (oracle/make_golden.py unit_cases) and against the block inside a full model."""
+    from m2trans_b200.M2Trans_network import CFTM, M2TError
+    from m2trans_b200.synthetic import synthetic_state_dict
+    u = np.load(os.path.join(golden_dir, "units.npz"))
+    sd = synthetic_state_dict(2, 5, n_blocks=1)
+    blk = CFTM(nf=64, block_size=8, halo_size=1, norm=True)
+    blk.load_state_dict({k[len("body.0."):]: v for k, v in sd.items() if k.startswith("body.0.")}, strict=True)
+    blk = blk.cuda().eval()
+    x = torch.from_numpy(u["cftm_in"]).cuda()
+    y = blk(x).cpu()
+    want = torch.from_numpy(u["cftm_out"])
+    rel = float((y - want).abs().max() / want.std())
+    print(f"CFTM standalone: max err / std = {rel:.2e}")
+    assert tuple(y.shape) == tuple(want.shape) and rel <= 3e-3
+    y2 = blk(torch.cat((x, x.flip(0)), 0))                     # another batch size -> another plan; frames independent
+    assert float((y2[0].cpu() - y[0]).abs().max()) <= 1e-5 * float(want.abs().max())
+    m = _model(2, 5).module                                    # the same block reached through a whole model
+    assert float((m.body[0](x).cpu() - y).abs().max()) == 0.0   # body.0 of the 8-block checkpoint holds the same tensors
+    with pytest.raises(M2TError):
+        blk(torch.rand(1, 64, 40, 32, device="cuda"))          # not a multiple of 32
+
+
+@pytest.mark.parametrize("ch,h,w", [(16, 20, 27), (64, 9, 16), (256, 8, 13)])
+def test_tblock_pads_to_the_block_like_the_reference(ch, h, w):
+    """ref :297-302, :339: sizes that are not multiples of 8 are reflect-padded right / bottom and cropped back."""
+    import torch.nn.functional as F
+    from oracle import m2trans_oracle as O
+    from m2trans_b200.M2Trans_network import TBlock
+    torch.manual_seed(ch + h)
+    blk = TBlock(ch).cuda()
+    x = torch.randn(2, ch, h, w)
+    pr, pb = (8 - w % 8) % 8, (8 - h % 8) % 8
+    want = O.tblock(F.pad(x, (0, pr, 0, pb), mode="reflect"), blk.qkv_conv.weight.detach().cpu(), blk.rel_h.detach().cpu(),
+                    blk.rel_w.detach().cpu())[:, :, :h, :w]
+    got = blk(x.cuda()).cpu()
+    err = float((got - want).abs().max() / want.std())
+    print(f"TBlock C={ch} {h}x{w}: max err / std = {err:.2e}")
+    assert got.shape == x.shape and err <= 2e-2

@@ -169,3 +169,12 @@ def test_parameter_discovery_on_dataparallel_replicas():
     tw = [p for _, p in tb.state_dict(keep_vars=True).items()]
     tr = state_tensors(_fake_replica(tb))
     assert len(tr) == 12 and all(a.data_ptr() == b.data_ptr() for a, b in zip(tr, tw))
+
+
+def test_library_carries_the_hash_of_the_sources_it_was_built_from():
+    """build() rebuilds when the hash compiled into the .so differs from the hash of the tree (not on mtimes), so a
+    stale binary cannot travel with changed sources unnoticed."""
+    from m2trans_b200 import _lib, build
+    tag = build.source_hash()
+    assert len(tag) == 16 and build.built_hash() == tag and not build._stale()
+    assert _lib.load().m2t_version().decode().endswith("m2t-src-hash:" + tag)

@@ -35,6 +35,20 @@ def test_images_to_device_all_byte_values_and_errors():
         images_to_device(np.zeros((4, 4, 3), dtype=np.uint8), device="cpu")
 
 
+@pytest.mark.parametrize("shape", [(1, 3, 64, 64), (2, 3, 37, 51), (2, 1, 33, 40), (1, 3, 512, 512)])
+def test_images_from_device_matches_torch(shape):
+    """fp32 CHW -> uint8 HWC on the device (what writing the SR batch to image files does) equals the torch expression."""
+    from m2trans_b200.loader import images_from_device, images_to_device
+    g = torch.Generator().manual_seed(shape[2])
+    sr = (torch.rand(shape, generator=g) * 1.2 - 0.1).cuda()                       # includes values outside [0, 1]
+    sr[0, 0, 0, :8] = torch.tensor([0.5 / 255, 1.5 / 255, 2.5 / 255, 0.0, 1.0, -3.0, 7.0, 254.5 / 255]).cuda()   # ties, ends
+    want = (sr * 255.0).round().clamp(0, 255).to(torch.uint8).permute(0, 2, 3, 1).contiguous()
+    got = images_from_device(sr)
+    assert got.shape == want.shape and got.dtype == torch.uint8 and torch.equal(got, want)
+    back = images_to_device(got.cpu().numpy())                                      # round trip through the loader kernel
+    assert torch.equal(back, want.permute(0, 3, 1, 2).float() / 255.)
+
+
 def test_eval_loop_uint8_to_metrics_matches_oracle():
     """The reference's test loop (test.py:87-116) end to end on the device: uint8 LR/HR arrays -> loader conversion ->
     model(lr) -> Y-channel PSNR / SSIM, against the CPU oracle of each piece chained the same way."""

@@ -66,3 +66,23 @@ def test_non_contiguous_input_and_errors():
         m(torch.randn(1, 64, 64, device="cuda").half())
     with pytest.raises(M2TError):
         m(torch.randn(1, 64, 32, device="cuda"))
+
+
+@pytest.mark.parametrize("b,n", [(2, 256), (1, 17), (3, 1000)])
+def test_submodules_run_on_their_own(b, n):
+    """Mlp.forward (ref :21-27) and EffAttention.forward (ref :47-66) are public classes of the reference file: called
+    directly they run the block's kernels in a standalone mode and match the oracle's restatement of each."""
+    sd = synthetic_transblock_state_dict(4)
+    m = _block(4)
+    x = synthetic_tokens(b, n, seed=11)
+    ya = m.atten(x.cuda()).cpu()
+    ym = m.mlp(x.cuda()).cpu()
+    ea = float((ya - R.eff_attention(sd, x)).abs().max())
+    em = float((ym - R.mlp(sd, x)).abs().max())
+    print(f"B={b} N={n}: EffAttention max-abs {ea:.2e}, Mlp max-abs {em:.2e}")
+    assert ea <= TOL and em <= TOL
+    assert ym.shape == x.shape and m.mlp(x.cuda().reshape(-1, 64)).shape == (b * n, 64)     # Mlp takes any [..., 64]
+    with pytest.raises(M2TError):
+        m.atten(torch.randn(1, 15, 64, device="cuda"))
+    with pytest.raises(M2TError):
+        m.mlp(torch.randn(4, 32, device="cuda"))
