@@ -46,7 +46,7 @@ def test_images_from_device_matches_torch(shape):
     got = images_from_device(sr)
     assert got.shape == want.shape and got.dtype == torch.uint8 and torch.equal(got, want)
     back = images_to_device(got.cpu().numpy())                                      # round trip through the loader kernel
-    assert torch.equal(back, want.permute(0, 3, 1, 2).float() / 255.)
+    assert torch.equal(back.cpu(), want.permute(0, 3, 1, 2).cpu().float() / 255.)        # the loader's expression, on the CPU
 
 
 def test_eval_loop_uint8_to_metrics_matches_oracle():
