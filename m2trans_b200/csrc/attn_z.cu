@@ -158,8 +158,7 @@ attn_z_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ 
     uint64_t* pzs_ready = bars + 15;         // PZ / sum written to smem
     uint64_t* o_full = bars + 16;
     uint64_t* pair_done = bars + 17;         // O consumed and the tile no longer needed
-    uint64_t* x_full = bars + 18;            // [4] extra MQ slots in the operand region (free from o_full to a_full)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
     float* sinv = reinterpret_cast<float*>(sm + CF::OFF_INV);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -187,7 +186,6 @@ attn_z_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ 
         mbar_init(pzs_ready, CF::NEPI);
         mbar_init(o_full, 1);
         mbar_init(pair_done, CF::NEPI);
-        for (int s = 0; s < 4; ++s) mbar_init(&x_full[s], 1);
         mbar_fence_init();
         tma_prefetch_desc(&mapT);
         tma_prefetch_desc(&mapMQ);
@@ -215,18 +213,10 @@ attn_z_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ 
             __syncwarp();
             ++g;
         };
-        // MQ box i = 0..11 is (K chunk i / 3, 128-row slab i % 3).  Boxes 4..7 of every pair go to four extra slots in
-        // the operand region, which nobody uses between the previous pair's last O MMA and this pair's A conversion:
-        // eight boxes are in flight before the first MMA instead of four (the stream is latency-bound: a slot round
-        // trip is ~2 K cycles against 256 cycles of MMA per box).
+        // MQ box i = 0..11 is (K chunk i / 3, 128-row slab i % 3).  (Four extra slots in the operand region, idle during
+        // phase 1, were tried: eight boxes in flight instead of four did not shorten the phase -- 128 CTAs pulling the same
+        // 278 KB per pair run at the chip's L2 bandwidth, ~32 B/clk per SM -- and were removed again.)
         auto mq_box = [&](int i) { ring_load(&mapMQ, i / 3, (i % 3) * 128); };
-        auto mq_xbox = [&](int i) {
-            if (elect_one_sync()) {
-                mbar_expect_tx(&x_full[i - 4], AZ_SLOT);
-                tma_load_2d(sm + CF::OFF_OPER + (i - 4) * AZ_SLOT, &mapMQ, &x_full[i - 4], (i / 3) * 64, (i % 3) * 128);
-            }
-            __syncwarp();
-        };
         if constexpr (!RING) {
             if (elect_one_sync()) {                      // constants: loaded while the previous kernel drains
                 mbar_expect_tx(w_full, CF::W_BYTES);
@@ -240,11 +230,7 @@ attn_z_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ 
             const AzPair pc = az_pair(p, nwx, per_img);
             // the first four weight boxes do not wait for this pair's MMAs (the ring has four slots), the tile does
             // not wait for the ring: issuing in this order cannot deadlock and lets the weights run ahead
-            if constexpr (RING) {
-                mq_box(0); mq_box(1); mq_box(2); mq_box(3);
-                mbar_wait(o_full, (it & 1) ^ 1);           // the previous pair's O MMAs have read PZ: the operand region is free
-                mq_xbox(4); mq_xbox(5); mq_xbox(6); mq_xbox(7);
-            }
+            if constexpr (RING) { mq_box(0); mq_box(1); mq_box(2); mq_box(3); }
             if (it == 0) pdl_wait();
             mbar_wait(pair_done, (it & 1) ^ 1);
             if (elect_one_sync()) {
@@ -254,7 +240,7 @@ attn_z_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ 
             }
             __syncwarp();
             if constexpr (RING) {
-                for (int i = 8; i < 3 * NBLK; ++i) mq_box(i);
+                for (int i = 4; i < 3 * NBLK; ++i) mq_box(i);
                 for (int i = 0; i < 2 * NBLK; ++i) ring_load(&mapWV, i / 2, (i % 2) * 128);
             }
         }
@@ -273,25 +259,22 @@ attn_z_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ 
             tc_fence_after();
             // phase 1: [QR | A] = Zq . MQ^T
             if constexpr (RING) {
-                for (int i = 0; i < 3 * NBLK; ++i) {
+                for (int i = 0; i < 3 * NBLK; ++i, ++g) {
                     const int kb = i / 3, sl = i % 3;
-                    const bool extra = i >= 4 && i < 8;                  // boxes 4..7 sit in the operand region
                     const uint32_t s = g % CF::NSLOT, ph = (g / CF::NSLOT) & 1;
-                    if (extra) mbar_wait(&x_full[i - 4], it & 1);
-                    else mbar_wait(&r_full[s], ph);
+                    mbar_wait(&r_full[s], ph);
                     tc_fence_after();
                     if (elect_one_sync()) {
                         const uint64_t da0 = umma_desc_at(tmpl_q, base + CF::OFF_TILE + kb * AZ_CHUNK + AZ_QOFF);
-                        const uint64_t db0 = umma_desc_at(tmpl, extra ? base + CF::OFF_OPER + (i - 4) * AZ_SLOT : base + CF::OFF_W + s * AZ_SLOT);
+                        const uint64_t db0 = umma_desc_at(tmpl, base + CF::OFF_W + s * AZ_SLOT);
                         const uint32_t idesc = sl < 2 ? umma_idesc_f16(128, 128) : umma_idesc_f16(128, 32);
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
                             umma_f16_ss(tmem_base + sl * 128, da0 + 2 * k, db0 + 2 * k, idesc, (kb | k) ? 1u : 0u);
-                        if (!extra) umma_commit(&r_empty[s]);
+                        umma_commit(&r_empty[s]);
                         if (i == 3 * NBLK - 1) umma_commit(a_full);
                     }
                     __syncwarp();
-                    if (!extra) ++g;
                 }
             } else {
                 if (elect_one_sync()) {

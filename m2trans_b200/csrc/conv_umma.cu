@@ -29,6 +29,16 @@
 //               the tensor pipe had the room (29 % busy).
 //
 // Warp roles (224 threads): warps 0-3 epilogue, warp 4 TMA loads, warp 5 MMA issuer, warp 6 TMA stores.
+//
+// What bounds it (round 2, clock64 stamps + ncu at cfg2): shared-memory bandwidth.  Per 128-pixel tile the 36 MMAs read
+// 147 KB of A (the halo tile, once per tap and K step) and 74 KB of B, TMA writes 55 KB (Y halo + X tile), the epilogue
+// reads and rewrites the 32 KB X tile, the statistics pass reads it again and the TMA store reads it once more: ~400 KB
+// = 3.2 K cycles at 128 B/clk, against 3.4-3.6 K cycles measured per tile (MMA issue 1.15 K, the MMA warp waits 1.3-2.2 K
+// per tile for a free accumulator).  A second epilogue warpgroup (channels 32..63 of every pixel) was built and
+// measured: the accumulate phase fell from 1.2 K to 0.75 K cycles, the statistics pass rose from 1.4 K to 2.0 K, the tile
+// time and the forward (1.301 vs 1.310 ms) did not move -- not kept.  L2 evict_last hints on the fp32 residual stream
+// (67 MB at cfg2, re-read by branch_prep_all and by the next ff conv) changed nothing either: at cfg2 the kernel runs at
+// 41 % of DRAM bandwidth, at cfg4 (79 % of the copy bandwidth on algorithmic bytes) the stream cannot stay in L2.
 #include "common.cuh"
 #include "tma.cuh"
 #include "umma.cuh"

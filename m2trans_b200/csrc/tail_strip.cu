@@ -44,6 +44,9 @@ static_assert(TS_SMEM <= 232448, "tail_strip exceeds the shared memory of an SM"
 constexpr int TS_E1 = 512, TS_E2 = 128;
 constexpr int TS_THREADS = TS_E1 + TS_E2 + 64;          // + warp 20 TMA, warp 21 MMA
 constexpr uint32_t TS_COL_D = 256;
+#ifndef TS_IDLE_NS
+#define TS_IDLE_NS 200
+#endif
 
 struct TsItem { int bl, x0, ya, nsteps, yhi; };
 
@@ -127,7 +130,7 @@ tail_strip_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
             const TsItem ti = ts_item(item, nstrips, nseg, SH, hn, hout);
             for (int s = 0; s < ti.nsteps; ++s, ++g) {
                 const uint32_t st = g & 1;
-                mbar_wait(&a_empty[st], ((g >> 1) & 1) ^ 1);
+                mbar_wait_idle(&a_empty[st], ((g >> 1) & 1) ^ 1, TS_IDLE_NS);
                 if (elect_one_sync()) {
                     mbar_expect_tx(&a_full[st], TS_ASTAGE);
                     tma_load_4d(sm + TS_OFF_A + st * TS_ASTAGE, &mapA, &a_full[st], 0, ti.x0 - 1, ti.ya + TS_AR * s - 1, ti.bl);
@@ -142,8 +145,8 @@ tail_strip_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         constexpr uint64_t tmpl = umma_smem_desc(0, 16, 1024, UMMA_LAYOUT_SW128);
         auto conv = [&](uint32_t j) {               // conv GEMM of step j: D[j & 1] = U[j & 1] . Wc^T
             const uint32_t buf = j & 1, ph = (j >> 1) & 1;
-            mbar_wait(&u_full[buf], ph);
-            mbar_wait(&d_empty[buf], ph ^ 1);
+            mbar_wait_idle(&u_full[buf], ph, TS_IDLE_NS);
+            mbar_wait_idle(&d_empty[buf], ph ^ 1, TS_IDLE_NS);
             tc_fence_after();
             if (elect_one_sync()) {
                 const uint64_t db0 = umma_desc_at(tmpl, base + TS_OFF_WC);
@@ -165,9 +168,9 @@ tail_strip_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
             const TsItem ti = ts_item(item, nstrips, nseg, SH, hn, hout);
             for (int s = 0; s < ti.nsteps; ++s, ++g) {
                 const uint32_t st = g & 1;
-                mbar_wait(&a_full[st], (g >> 1) & 1);
+                mbar_wait_idle(&a_full[st], (g >> 1) & 1, TS_IDLE_NS);
                 for (int hf = 0; hf < 2; ++hf) {
-                    mbar_wait(&acc_empty[hf], (g & 1) ^ 1);
+                    mbar_wait_idle(&acc_empty[hf], (g & 1) ^ 1, TS_IDLE_NS);
                     tc_fence_after();
                     if (elect_one_sync()) {
                         const uint64_t da0 = umma_desc_at(tmpl, base + TS_OFF_A + st * TS_ASTAGE);
@@ -274,7 +277,7 @@ tail_strip_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
             for (int s = 0; s < ti.nsteps; ++s, ++g) {
                 const uint32_t buf = g & 1;
                 const int R0 = 2 * (ti.ya + TS_AR * s - 1);                    // U row of this step's first row
-                mbar_wait(&d_full[buf], (g >> 1) & 1);
+                mbar_wait_idle(&d_full[buf], (g >> 1) & 1, TS_IDLE_NS);
                 tc_fence_after();
 #pragma unroll 1
                 for (int r2 = 0; r2 < 2; ++r2) {

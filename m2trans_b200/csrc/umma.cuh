@@ -39,23 +39,33 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// try_wait with a suspend-time hint: the hardware parks the warp until the phase completes (or the hint elapses) instead
-// of returning after a short implementation-defined interval.  ncu on tail_strip showed 10-13 % of all issue slots
-// going to the polling loops of the warps that wait most of the time (TMA / MMA / conv-epilogue roles).
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.b32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return ok != 0;
 }
 // Bounded wait: a lost arrival turns into a trap (kernel error) instead of a hung GPU box (~4 s of SM clocks).
+// (try_wait with a suspend-time hint was measured: ptxas turns it into a NANOSLEEP polling loop that executes MORE
+// instructions -- tail_strip 178 M vs 187 M warp instructions with 4.3 M NANOSLEEPs -- and adds wake-up latency to
+// every dependent phase: cfg1, a pure latency chain, went from 0.577 to 0.614 ms.  Not kept.)
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > (8ll << 30)) { asm volatile("trap;"); }
+    }
+}
+// The same for roles that wait most of the time (TMA / MMA issue warps, the conv-epilogue warps of tail_strip): sleep
+// between polls so that the polling loop does not take issue slots from the compute warps of the same sub-partition.
+__device__ __forceinline__ void mbar_wait_idle(uint64_t* bar, uint32_t parity, uint32_t ns) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        asm volatile("nanosleep.u32 %0;" ::"r"(ns));
         if (clock64() - t0 > (8ll << 30)) { asm volatile("trap;"); }
     }
 }
