@@ -262,6 +262,12 @@ int m2t_clip_stage_attention(const void* d_qkv, void* d_out, const float* d_bias
 size_t m2t_metrics_workspace_bytes(int B, int H, int W, int shave);
 int m2t_eval_psnr_ssim(const float* d_sr, const float* d_hr, int B, int colors, int H, int W, int shave,
                        float rgb_range, float* d_out, void* d_workspace, void* stream);
+/* GMSD of the test loop (ref test.py:98-99: piq.gmsd(hr, sr, data_range=1., reduction='none')); piq is third-party and
+ * absent offline, so this follows its published algorithm (csrc/gmsd.cu): d_out[B] fp32, one value per image.  d_x, d_y:
+ * fp32 [B, colors, H, W] device tensors (colors 1 or 3), H, W >= 2. */
+size_t m2t_gmsd_workspace_bytes(int B, int H, int W);
+int m2t_eval_gmsd(const float* d_x, const float* d_y, int B, int colors, int H, int W, float data_range, float* d_out,
+                  void* d_workspace, void* stream);
 
 /* ---- loader conversion (device side) -----------------------------------------
  * Replaces ndarray2tensor(img) / 255. of the benchmark loader (ref datas/benchmark.py:66-69, utils.py:237-240) on the

@@ -86,6 +86,8 @@ SIGNATURES = {
     "m2t_clip_stage_attention": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "m2t_metrics_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "m2t_eval_psnr_ssim": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp]),
+    "m2t_gmsd_workspace_bytes": (_sz, [_i, _i, _i]),
+    "m2t_eval_gmsd": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _vp]),
     "m2t_u8hwc_to_f32chw": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _vp]),
     "m2t_f32chw_to_u8hwc": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _vp]),
     "m2t_probe_umma": (_i, [_vp, _u32, _vp, _u32, _u64, _u64, _u32, _u32, _i, _u32, _i, _vp, _vp]),

@@ -12,7 +12,7 @@ import torch
 from . import _lib
 from ._lib import M2TError
 
-__all__ = ["psnr_ssim", "calc_psnr_ssim"]
+__all__ = ["psnr_ssim", "calc_psnr_ssim", "gmsd"]
 
 
 @torch.no_grad()
@@ -49,3 +49,25 @@ def calc_psnr_ssim(sr, hr, scale, rgb_range=1.0):
     _, batch = psnr_ssim(sr, hr, scale, rgb_range)
     p, s = batch.tolist()
     return p, s
+
+
+@torch.no_grad()
+def gmsd(x: torch.Tensor, y: torch.Tensor, data_range: float = 1.0) -> torch.Tensor:
+    """piq.gmsd(x, y, data_range=data_range, reduction='none') of ref test.py:98-99 on the device: fp32 CUDA [B, C, H, W]
+    (C = 1 or 3) -> fp32 CUDA [B].  piq is absent offline: the kernel follows its published algorithm (parity unpinned)."""
+    for t, n in ((x, "x"), (y, "y")):
+        if not isinstance(t, torch.Tensor) or not t.is_cuda:
+            raise M2TError(f"gmsd: {n} must be a CUDA tensor; the B200 engine has no CPU path")
+        if t.dtype != torch.float32 or t.dim() != 4:
+            raise M2TError(f"gmsd: {n} must be float32 [B,C,H,W], got {t.dtype} {tuple(t.shape)}")
+    if x.shape != y.shape or x.shape[1] not in (1, 3) or x.shape[2] < 2 or x.shape[3] < 2:
+        raise M2TError(f"gmsd: need equal shapes [B, 1|3, H>=2, W>=2], got {tuple(x.shape)} and {tuple(y.shape)}")
+    b, c, h, w = x.shape
+    lib = _lib.load()
+    with torch.cuda.device(x.device):
+        ws = torch.empty(int(lib.m2t_gmsd_workspace_bytes(b, h, w)) + 256, dtype=torch.uint8, device=x.device)
+        out = torch.empty(b, dtype=torch.float32, device=x.device)
+        off = (-ws.data_ptr()) % 256
+        _lib.check(lib.m2t_eval_gmsd(x.contiguous().data_ptr(), y.contiguous().data_ptr(), b, c, h, w, float(data_range), out.data_ptr(),
+                                     ws.data_ptr() + off, torch.cuda.current_stream(x.device).cuda_stream), "m2t_eval_gmsd")
+    return out

@@ -76,3 +76,24 @@ def test_loop_metrics(sr, hr, scale, rgb_range=1.0, colors=3, dtype=torch.float3
     """(psnr, ssim) of one batch as ref test.py:103-116 computes them."""
     s, h = prepare(sr, hr, scale, rgb_range, colors)
     return calc_psnr(s, h), ssim(s, h, dtype=dtype)
+
+
+def gmsd(x, y, data_range=1.0):
+    """piq.gmsd(x, y, data_range, reduction='none') (ref test.py:98-99).  `piq` (pinned nowhere: `pip install piq`, ref
+    README) is absent offline -- PARITY UNPINNED; this restates the published algorithm (Xue et al., IEEE TIP 2014) the way
+    piq implements it: luma of x / data_range, zero pad bottom / right by max(H % 2, W % 2), 2 x 2 average pooling,
+    Prewitt / 3 gradient magnitudes with zero padding, GMS with c = 170 / 255^2, population standard deviation per image."""
+    import torch.nn.functional as F
+
+    def luma(t):
+        t = t.double() / data_range
+        return (0.299 * t[:, 0:1] + 0.587 * t[:, 1:2] + 0.114 * t[:, 2:3]) if t.shape[1] == 3 else t
+    a, b = luma(x), luma(y)
+    p = max(a.shape[2] % 2, a.shape[3] % 2)
+    a, b = (F.avg_pool2d(F.pad(t, (0, p, 0, p)), 2, 2) for t in (a, b))
+    k = torch.tensor([[1.0, 0.0, -1.0]] * 3, dtype=torch.float64) / 3.0
+    kern = torch.stack((k, k.t()))[:, None]
+    ga, gb = (torch.sqrt((F.conv2d(t, kern, padding=1) ** 2).sum(1, keepdim=True) + 1e-12) for t in (a, b))
+    c = 170.0 / 255.0 ** 2
+    gms = (2 * ga * gb + c) / (ga ** 2 + gb ** 2 + c)
+    return gms.flatten(1).std(dim=1, unbiased=False)

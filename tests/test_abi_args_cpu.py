@@ -64,3 +64,11 @@ def test_bench_arms_print_the_same_config():
     from m2trans_b200.sharding import shard_range
     assert [shard_range(32, r, 8) for r in (0, 7)] == [(0, 4), (28, 32)]         # cfg3 at 8 GPUs: 4 frames each
     assert shard_range(64, 3, 8) == (24, 32) and shard_range(256, 7, 8) == (224, 256)
+
+
+def test_gmsd_argument_errors():
+    lib = _lib.load()
+    assert lib.m2t_gmsd_workspace_bytes(1, 1, 64) == 0 and lib.m2t_gmsd_workspace_bytes(2, 37, 50) > 2 * 2 * 19 * 25 * 4
+    assert lib.m2t_eval_gmsd(None, 1, 1, 3, 64, 64, 1.0, 1, 1, None) == E_ARG
+    assert lib.m2t_eval_gmsd(1, 1, 1, 2, 64, 64, 1.0, 1, 1, None) == E_ARG and "colors" in _err(lib)
+    assert lib.m2t_eval_gmsd(1, 1, 1, 3, 64, 64, 0.0, 1, 1, None) == E_ARG

@@ -38,3 +38,19 @@ def test_ssim_known_answers():
     c = M.ssim(x - 4080, y - 4080, dtype=torch.float64)
     assert abs(a - c) < 0.05
     assert M._gauss().sum().item() == pytest.approx(1.0, abs=1e-6)
+
+
+def test_gmsd_oracle_properties():
+    """The GMSD restatement (piq absent: parity unpinned): 0 for identical images, symmetric, grows with distortion, odd
+    sizes padded like piq (both dimensions by max(H % 2, W % 2))."""
+    import torch
+    from oracle import metrics_oracle as MO
+    g = torch.Generator().manual_seed(3)
+    a = torch.rand(2, 3, 37, 50, generator=g)
+    n = torch.randn(a.shape, generator=g)
+    small, big = (a + 0.02 * n).clamp(0, 1), (a + 0.2 * n).clamp(0, 1)
+    assert float(MO.gmsd(a, a).abs().max()) == 0.0
+    assert torch.allclose(MO.gmsd(a, small), MO.gmsd(small, a))
+    assert (MO.gmsd(a, big) > MO.gmsd(a, small)).all() and float(MO.gmsd(a, big).max()) < 0.35
+    gray = a[:, :1]
+    assert MO.gmsd(gray, gray.flip(3)).shape == (2,)

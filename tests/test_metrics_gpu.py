@@ -63,3 +63,18 @@ def test_identical_images_and_errors():
         psnr_ssim(x[:, :, :14, :14].contiguous(), x[:, :, :14, :14].contiguous(), 2)        # 10 x 10 after shaving
     with pytest.raises(M2TError):
         psnr_ssim(x.cpu(), x.cpu(), 2)
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 64, 96), (1, 3, 37, 50), (3, 1, 33, 33), (1, 3, 512, 512)])
+def test_gmsd_matches_oracle(shape):
+    """piq.gmsd of ref test.py:98-99 on the device against the oracle's fp64 restatement of the published algorithm."""
+    from oracle import metrics_oracle as MO
+    from m2trans_b200.metrics import gmsd
+    g = torch.Generator().manual_seed(shape[2] + shape[3])
+    hr = torch.rand(shape, generator=g)
+    sr = (hr + 0.05 * torch.randn(shape, generator=g)).clamp(0, 1)
+    got = gmsd(hr.cuda(), sr.cuda()).cpu().double()
+    want = MO.gmsd(hr, sr)
+    print(f"gmsd {shape}: {got.tolist()} vs {want.tolist()}")
+    assert got.shape == (shape[0],) and float((got - want).abs().max()) <= 2e-5
+    assert float(gmsd(hr.cuda(), hr.cuda()).abs().max()) <= 1e-6          # identical images: GMS == 1 everywhere

@@ -104,21 +104,7 @@ def install_stubs(model_kind, scale):
     piq = types.ModuleType("piq")
 
     def gmsd(x, y, data_range=1.0, reduction="none"):
-        """Gradient Magnitude Similarity Deviation (Xue et al. 2014) as piq states it: luma, 2x average pooling, Prewitt / 3,
-        GMS = (2 g1 g2 + c) / (g1^2 + g2^2 + c) with c = 170 / 255^2, deviation = population std of the GMS map."""
-        import torch.nn.functional as F
-        def luma(t):
-            t = t / data_range
-            return (0.299 * t[:, 0:1] + 0.587 * t[:, 1:2] + 0.114 * t[:, 2:3]) if t.shape[1] == 3 else t
-        a, b = luma(x.float()), luma(y.float())
-        ph, pw = a.shape[2] % 2, a.shape[3] % 2
-        a, b = (F.avg_pool2d(F.pad(t, (0, pw, 0, ph)), 2, 2) for t in (a, b))
-        k = torch.tensor([[1.0, 0.0, -1.0]] * 3).to(a) / 3.0
-        kern = torch.stack((k, k.t()))[:, None]
-        ga, gb = (torch.sqrt((F.conv2d(t, kern, padding=1) ** 2).sum(1, keepdim=True) + 1e-12) for t in (a, b))
-        c = 170.0 / 255.0 ** 2
-        gms = (2 * ga * gb + c) / (ga ** 2 + gb ** 2 + c)
-        return gms.flatten(1).std(dim=1, unbiased=False)
+        return MO.gmsd(x, y, data_range).to(x.dtype)       # the published algorithm, oracle/metrics_oracle.py
     piq.gmsd = gmsd
     piq.fsim = lambda x, y, data_range=1.0, reduction="none": torch.zeros(x.shape[0], device=x.device)   # not restated
     sys.modules["piq"] = piq
