@@ -370,3 +370,19 @@ def test_tblock_pads_to_the_block_like_the_reference(ch, h, w):
     err = float((got - want).abs().max() / want.std())
     print(f"TBlock C={ch} {h}x{w}: max err / std = {err:.2e}")
     assert got.shape == x.shape and err <= 2e-2
+
+
+@pytest.mark.gpu
+def test_released_checkpoints_if_present():
+    """The reference's released model_x{2,3,4}.pt are absent from its checkout.  When a user provides them
+    (checkpoints/ or $M2T_CHECKPOINTS, verified by git blob SHA-1) the default path has to meet the same bar on them."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("released_checkpoint_check", os.path.join(os.path.dirname(__file__), "released_checkpoint_check.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    table = mod.table
+    found, rows = table(sizes=[(48, 56)], kinds=("uniform", "speckle"))
+    if not found:
+        pytest.skip("released checkpoints not present")
+    for scale, h, w, kind, p, e, _ in rows:
+        assert p >= 50.0 and e <= 2e-3, (scale, h, w, kind, p, e)

@@ -178,3 +178,22 @@ def test_library_carries_the_hash_of_the_sources_it_was_built_from():
     tag = build.source_hash()
     assert len(tag) == 16 and build.built_hash() == tag and not build._stale()
     assert _lib.load().m2t_version().decode().endswith("m2t-src-hash:" + tag)
+
+
+def test_released_checkpoint_identification(tmp_path):
+    """git blob SHA-1 (known answers: the empty blob and 'hello\\n'), the container reader and the released-file lookup."""
+    from m2trans_b200 import checkpoints as CK
+    from m2trans_b200.synthetic import save_reference_checkpoint, synthetic_state_dict
+    empty, hello = tmp_path / "empty", tmp_path / "hello"
+    empty.write_bytes(b"")
+    hello.write_bytes(b"hello\n")
+    assert CK.git_blob_sha1(str(empty)) == "e69de29bb2d1d6434b8b29ae775ad8c2e48c5391"
+    assert CK.git_blob_sha1(str(hello)) == "ce013625030ba8dba906f756967f9e9ca394464a"
+    assert sorted(CK.RELEASED_SHA1) == [2, 3, 4] and all(len(v) == 40 for v in CK.RELEASED_SHA1.values())
+    d = tmp_path / "checkpoints"
+    d.mkdir()
+    save_reference_checkpoint(str(d / "model_x2.pt"), 2, 0)          # right name, synthetic content
+    assert CK.identify(str(d / "model_x2.pt")) is None and CK.find_released(str(d)) == {}
+    sd = CK.load_model_state_dict(str(d / "model_x2.pt"))
+    want = synthetic_state_dict(2, 0)
+    assert list(sd) == list(want) and all(torch.equal(sd[k], want[k]) for k in want)
