@@ -32,6 +32,7 @@
 // two CTAs per SM.  TMEM: QR [0,32) | A / PZ / O [32,32+C) | S (C = 64: aliases A, [32,224); C = 256: [288,480)).
 // Warps: 0-3 epilogue / softmax (thread = query row = TMEM lane), 4 TMA, 5 MMA, C = 256 only: 6-9 share the
 // conversions and the final epilogue of the rows of warps 0-3.
+#include <cstdlib>
 #include "common.cuh"
 #include "gelu.cuh"
 #include "tma.cuh"
@@ -96,12 +97,12 @@ struct AzDiv {                                          // division by a runtime
 };
 // pair p -> image b, first row of the upper window (level pixels), first column
 struct AzPair { int b, y, x; };
-__device__ __forceinline__ AzPair az_pair(int p, const AzDiv& nwx, const AzDiv& per_img) {
+__device__ __forceinline__ AzPair az_pair(int p, const AzDiv& nwx, const AzDiv& per_img, int ystep) {
     AzPair c;
     c.b = (int)per_img.div((uint32_t)p);
     const uint32_t r = (uint32_t)p - (uint32_t)c.b * per_img.d;
     const uint32_t py = nwx.div(r);
-    c.y = (int)py * 2 * BLK;
+    c.y = (int)py * ystep;
     c.x = (int)(r - py * nwx.d) * BLK;
     return c;
 }
@@ -138,7 +139,7 @@ __device__ long long g_az_dbg[3 * 64];     // per branch 2..4: CTA 0, epilogue t
 template <int C, bool LO>
 __global__ void __launch_bounds__(AzCfg<C>::THREADS, AzCfg<C>::MIN_CTAS)
 attn_z_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ CUtensorMap mapMQ,
-              const __grid_constant__ CUtensorMap mapWV, int h, int w, int npairs, const AttnFuse fz) {
+              const __grid_constant__ CUtensorMap mapWV, int h, int w, int npairs, int single, const AttnFuse fz) {
     using CF = AzCfg<C>;
     constexpr int NBLK = CF::NBLK;
     constexpr bool RING = CF::RING;
@@ -165,7 +166,9 @@ attn_z_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ 
 #ifdef M2T_TIMING
     if (blockIdx.x == 0 && tid == 0) g_az_dbg[64 * (fz.branch - 1) + 60] = clock64();
 #endif
-    const int nwx_i = w / BLK, nwy = h / BLK, npy = (nwy + 1) / 2;
+    // single != 0 (small inputs, see launch_attn_z): every window is the upper window of its own pair, the lower one is a
+    // phantom like the one below an odd last row -- its rows are computed and dropped
+    const int nwx_i = w / BLK, nwy = h / BLK, npy = single ? nwy : (nwy + 1) / 2, ystep = single ? BLK : 2 * BLK;
     const AzDiv nwx((uint32_t)nwx_i), per_img((uint32_t)(npy * nwx_i));
 
     // zero the 12 padding key rows of every tile chunk (TMA never writes them; the S and PZ MMAs read them)
@@ -227,7 +230,7 @@ attn_z_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ 
         }
         uint32_t it = 0;
         for (int p = blockIdx.x; p < npairs; p += gridDim.x, ++it) {
-            const AzPair pc = az_pair(p, nwx, per_img);
+            const AzPair pc = az_pair(p, nwx, per_img, ystep);
             // the first four weight boxes do not wait for this pair's MMAs (the ring has four slots), the tile does
             // not wait for the ring: issuing in this order cannot deadlock and lets the weights run ahead
             if constexpr (RING) { mq_box(0); mq_box(1); mq_box(2); mq_box(3); }
@@ -473,9 +476,9 @@ attn_z_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ 
             // With the Haar transforms folded into the weights the accumulator row IS IWT^L(attention) in space-to-depth
             // order: column s*16+k belongs to pixel s = dy*2^L + dx of this level pixel's 2^L x 2^L block.
             //   y_k = O' + t_k -> Y[..., 16k..16k+15];   t_{k+1} = n_{k+1}/2 (pre-filled) + y_k/2 -> Tnext in place
-            const AzPair pc = az_pair(p, nwx, per_img);
+            const AzPair pc = az_pair(p, nwx, per_img, ystep);
             const int wy = pc.y + BLK * win;                  // first row of this thread's window
-            const bool valid = wy < h;                        // false for the phantom lower window of an odd last row
+            const bool valid = wy < h && !(single && win);    // false for a phantom lower window (odd last row, single mode)
             constexpr int LV = C == 64 ? 1 : 2;
             constexpr int S = 1 << LV;
             constexpr int SPB = 4;                            // 16-channel sub-pixels per 64-channel block
@@ -646,11 +649,16 @@ int launch_attn_z_c(const __half* T, const __half* MQ, const __half* WV, int B, 
         M2T_TRY(make_tensor_map(&mapWV, WV, 2, 2, dims, str, box, 3));
     }
     const int nwy = h / BLK, nwx = w / BLK;
-    const int npairs = B * ((nwy + 1) / 2) * nwx;
     const int cap = device_sm_count() * CF::MIN_CTAS;
+    // small inputs (every window finds a CTA slot of its own in one wave): one window per CTA.  The chain of a CTA is then one
+    // window's glue long instead of two (the glue is bound by the SM's load/store unit: one 32-byte sector per sub-pixel and
+    // tensor), and twice the SMs work; the weights come from L2 either way.
+    static const bool paired_only = getenv("M2T_AZ_PAIRED") != nullptr;      // measurement aid: always two windows per CTA
+    const int single = !paired_only && B * nwy * nwx <= cap ? 1 : 0;
+    const int npairs = single ? B * nwy * nwx : B * ((nwy + 1) / 2) * nwx;
     const int grid = npairs < cap ? npairs : cap;
     M2T_ENSURE_SMEM((attn_z_kernel<C, LO>), CF::SMEM);
-    M2T_CUDA(launch_pdl(attn_z_kernel<C, LO>, dim3(grid), dim3(CF::THREADS), CF::SMEM, s, mapT, mapMQ, mapWV, h, w, npairs, fz));
+    M2T_CUDA(launch_pdl(attn_z_kernel<C, LO>, dim3(grid), dim3(CF::THREADS), CF::SMEM, s, mapT, mapMQ, mapWV, h, w, npairs, single, fz));
     return M2T_OK;
 }
 
