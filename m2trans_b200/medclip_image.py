@@ -120,6 +120,27 @@ class MedCLIPVisionModelViT(nn.Module):
         sd = dict(self.named_parameters())
         return [sd[name].detach() for name, _ in swin_param_spec()]
 
+    def invalidate(self) -> None:
+        """Forget the packed weights and the captured graphs.  Call after editing parameters through `.data` (such edits keep
+        the tensor's address and version counter, so the (data_ptr, _version) key cannot see them); load_state_dict and
+        .to() / .cuda() call it themselves."""
+        self._packed = None
+        self._packed_key = None
+        self._graphs = {}
+
+    repack = invalidate
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        if hasattr(self, "_graphs"):
+            self.invalidate()
+        return out
+
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        self.invalidate()
+        return out
+
     def _pack(self, device):
         lib = _lib.load()
         params = self._params()
@@ -201,8 +222,14 @@ class MedCLIPVisionModelViT(nn.Module):
                         self.encode_image(sx, stext)                      # warm-up outside the capture
                     torch.cuda.current_stream(dev).wait_stream(side)
                     graph = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(graph):
-                        out = self.encode_image(sx, stext)
+                    try:
+                        # thread_local: CUDA calls of other threads (a DataLoader's pin_memory thread, another model)
+                        # must not invalidate the capture; the region only enqueues kernels on static buffers
+                        with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                            out = self.encode_image(sx, stext)
+                    except RuntimeError:
+                        torch.cuda.synchronize(dev)
+                        return self.encode_image(x, text_features)       # eager (cuda_graph is False here)
                 finally:
                     self.cuda_graph = True
                 entry = (graph, sx, stext, out, packed)

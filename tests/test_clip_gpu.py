@@ -271,3 +271,22 @@ def test_small_batch_graph_replay_equals_eager():
     n = len(tower._graphs)
     tower.encode_image(big)
     assert len(tower._graphs) == n
+
+
+def test_invalidate_after_data_edit():
+    """Edits through `.data` keep a parameter's address and version counter: the packed weights (and the graphs captured
+    over them) stay until `invalidate()`; `.to()` / load_state_dict invalidate on their own."""
+    from m2trans_b200.medclip_image import MedCLIPVisionModelViT, synthetic_state_dict
+    from m2trans_b200.synthetic import synthetic_input
+    tower = MedCLIPVisionModelViT()
+    tower.load_state_dict(synthetic_state_dict(seed=6), strict=False)
+    tower = tower.cuda()
+    x = synthetic_input(1, 224, 224, seed=4).cuda()
+    e0 = tower.encode_image(x)
+    dict(tower.named_parameters())["projection_head.weight"].data.mul_(-1.0)
+    assert torch.equal(tower.encode_image(x), e0)                 # the documented blind spot of the cache key
+    tower.invalidate()
+    e1 = tower.encode_image(x)
+    assert torch.allclose(e1, -e0, atol=1e-6) and tower._packed is not None
+    tower.float()                                                 # any _apply drops the packed blob
+    assert tower._packed is None and tower._graphs == {}
