@@ -25,6 +25,7 @@ VAR_PRECISE_ON, VAR_PRECISE_OFF = 1 << 5, 1 << 6
 VAR_SPLIT_QKV16 = 1 << 7
 VAR_SPLIT_QKV = 1 << 8
 VAR_TILE_TAIL = 1 << 9
+VAR_AZ_PAIRED = 1 << 10
 PHASE_HEAD, PHASE_BODY, PHASE_TAIL, PHASE_ALL = 1, 2, 4, 7
 
 

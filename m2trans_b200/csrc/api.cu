@@ -377,7 +377,8 @@ int m2t_forward_phases(const m2t_plan* plan, const void* d_packed, const float* 
                 if (a > 0 && !(var & (M2T_VAR_SIMT_QKV | M2T_VAR_SPLIT_QKV))) {
                     // branches 2-4: qkv conv inside the attention kernel, q / k / v never formed (attn_z.cu)
                     M2T_TRY(launch_attn_z(C, Tb[a], reinterpret_cast<const __half*>(W + A.mq),
-                                          reinterpret_cast<const __half*>(W + A.wqkv_f) + (size_t)2 * C * C, g.B, h, w, s, fz));
+                                          reinterpret_cast<const __half*>(W + A.wqkv_f) + (size_t)2 * C * C, g.B, h, w, s, fz,
+                                          (var & M2T_VAR_AZ_PAIRED) != 0));
                     continue;
                 }
                 M2T_TRY(run_qkv(var, Tb[a], reinterpret_cast<const __half*>(W + A.wqkv_f), QKV, g.B * h * w, C, s));

@@ -32,7 +32,6 @@
 // two CTAs per SM.  TMEM: QR [0,32) | A / PZ / O [32,32+C) | S (C = 64: aliases A, [32,224); C = 256: [288,480)).
 // Warps: 0-3 epilogue / softmax (thread = query row = TMEM lane), 4 TMA, 5 MMA, C = 256 only: 6-9 share the
 // conversions and the final epilogue of the rows of warps 0-3.
-#include <cstdlib>
 #include "common.cuh"
 #include "gelu.cuh"
 #include "tma.cuh"
@@ -628,7 +627,7 @@ attn_z_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ 
 }
 
 template <int C, bool LO>
-int launch_attn_z_c(const __half* T, const __half* MQ, const __half* WV, int B, int h, int w, cudaStream_t s,
+int launch_attn_z_c(const __half* T, const __half* MQ, const __half* WV, int B, int h, int w, cudaStream_t s, bool paired_only,
                     const AttnFuse& fz) {
     using CF = AzCfg<C>;
     CUtensorMap mapT, mapMQ, mapWV;
@@ -653,7 +652,6 @@ int launch_attn_z_c(const __half* T, const __half* MQ, const __half* WV, int B, 
     // small inputs (every window finds a CTA slot of its own in one wave): one window per CTA.  The chain of a CTA is then one
     // window's glue long instead of two (the glue is bound by the SM's load/store unit: one 32-byte sector per sub-pixel and
     // tensor), and twice the SMs work; the weights come from L2 either way.
-    static const bool paired_only = getenv("M2T_AZ_PAIRED") != nullptr;      // measurement aid: always two windows per CTA
     const int single = !paired_only && B * nwy * nwx <= cap ? 1 : 0;
     const int npairs = single ? B * nwy * nwx : B * ((nwy + 1) / 2) * nwx;
     const int grid = npairs < cap ? npairs : cap;
@@ -674,13 +672,14 @@ int read_az_timing(long long* host64) { memset(host64, 0, sizeof(long long) * 19
 #endif
 
 // T: t_k space-to-depth fp16 [B,h,w,C]; MQ: fp16 [C+32][C] (AttnW::mq); WV: fp16 [C][C] (the v rows of AttnW::wqkv_f)
+// paired_only (M2T_VAR_AZ_PAIRED): two windows per CTA at every size (the results are bit-identical either way)
 int launch_attn_z(int C, const __half* T, const __half* MQ, const __half* WV, int B, int h, int w, cudaStream_t s,
-                  const AttnFuse& fz) {
+                  const AttnFuse& fz, bool paired_only) {
     if (h % BLK || w % BLK) { set_error("attn_z: %dx%d is not a multiple of the 8x8 block", h, w); return M2T_E_ARG; }
     if (fz.Y == nullptr || fz.T != T) { set_error("attn_z: the fused branch glue is not optional"); return M2T_E_ARG; }
     const bool lo = fz.Tlo != nullptr;
-    if (C == 64) return lo ? launch_attn_z_c<64, true>(T, MQ, WV, B, h, w, s, fz) : launch_attn_z_c<64, false>(T, MQ, WV, B, h, w, s, fz);
-    if (C == 256) return lo ? launch_attn_z_c<256, true>(T, MQ, WV, B, h, w, s, fz) : launch_attn_z_c<256, false>(T, MQ, WV, B, h, w, s, fz);
+    if (C == 64) return lo ? launch_attn_z_c<64, true>(T, MQ, WV, B, h, w, s, paired_only, fz) : launch_attn_z_c<64, false>(T, MQ, WV, B, h, w, s, paired_only, fz);
+    if (C == 256) return lo ? launch_attn_z_c<256, true>(T, MQ, WV, B, h, w, s, paired_only, fz) : launch_attn_z_c<256, false>(T, MQ, WV, B, h, w, s, paired_only, fz);
     set_error("attn_z: unsupported channel count %d", C);
     return M2T_E_UNSUPPORTED;
 }

@@ -198,7 +198,7 @@ int launch_attn16_qkv(const __half* T, const __half* Wqkv, const __half* relx, i
 // attn_z.cu : branches 2-4 (C = 64 / 256) with the qkv conv inside the attention kernel, contractions re-associated so
 // that q, k, v never exist (fused glue only).  MQ = AttnW::mq, WV = the v rows of AttnW::wqkv_f.
 int launch_attn_z(int C, const __half* T, const __half* MQ, const __half* WV, int B, int h, int w, cudaStream_t s,
-                  const AttnFuse& fz);
+                  const AttnFuse& fz, bool paired_only = false);
 
 int read_attn_timing(long long* host64);   // development aid, zeros unless built with -DM2T_TIMING (256 values)
 int read_tail_timing(long long* host64);   // the same for the fused tail kernel (64 values)

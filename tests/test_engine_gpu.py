@@ -330,6 +330,20 @@ def test_attn_z_agrees_with_split_kernels(scale, shape):
     assert pz >= PSNR_MIN and az <= MAXABS_MAX and ps >= PSNR_MIN and as_ <= MAXABS_MAX
 
 
+@pytest.mark.parametrize("scale,shape", [(4, (1, 3, 40, 72)), (3, (1, 3, 33, 47)), (2, (1, 3, 96, 72)), (2, (2, 3, 24, 40)), (4, (1, 3, 88, 120))])
+def test_attn_z_single_window_ctas_equal_paired(scale, shape):
+    """Small inputs run one window per CTA in attn_z (the lower window of every pair a phantom); M2T_VAR_AZ_PAIRED keeps
+    vertical window pairs.  The arithmetic of a window does not depend on which half of the accumulator it lives in:
+    bit-identical outputs, in fast and in precise mode, with even and odd window-row counts."""
+    from m2trans_b200 import _lib
+    from m2trans_b200.synthetic import synthetic_input
+    x = synthetic_input(shape[0], shape[2], shape[3], seed=17).cuda()
+    for mode in (_lib.VAR_PRECISE_ON, _lib.VAR_PRECISE_OFF):
+        y1 = _model(scale, 4, variant=mode)(x)
+        y2 = _model(scale, 4, variant=mode | _lib.VAR_AZ_PAIRED)(x)
+        assert torch.equal(y1, y2), (scale, shape, mode, float((y1 - y2).abs().max()))
+
+
 def test_cftm_forward_standalone_matches_reference_golden(golden_dir):
     """`model.body[i](x)` on the reference surface: one CFTM through a one-block engine plan, against the fixture the
     REAL reference CFTM produced (oracle/make_golden.py unit_cases) and against the block inside a full model."""
