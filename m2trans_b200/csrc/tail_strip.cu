@@ -47,6 +47,9 @@ constexpr uint32_t TS_COL_D = 256;
 #ifndef TS_IDLE_NS
 #define TS_IDLE_NS 200
 #endif
+#ifndef TS_MMA_NS
+#define TS_MMA_NS 200                                    // the MMA warp's polls (E1 waits for its GEMM-1 issues)
+#endif
 
 struct TsItem { int bl, x0, ya, nsteps, yhi; };
 
@@ -145,8 +148,8 @@ tail_strip_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         constexpr uint64_t tmpl = umma_smem_desc(0, 16, 1024, UMMA_LAYOUT_SW128);
         auto conv = [&](uint32_t j) {               // conv GEMM of step j: D[j & 1] = U[j & 1] . Wc^T
             const uint32_t buf = j & 1, ph = (j >> 1) & 1;
-            mbar_wait_idle(&u_full[buf], ph, TS_IDLE_NS);
-            mbar_wait_idle(&d_empty[buf], ph ^ 1, TS_IDLE_NS);
+            mbar_wait_idle(&u_full[buf], ph, TS_MMA_NS);
+            mbar_wait_idle(&d_empty[buf], ph ^ 1, TS_MMA_NS);
             tc_fence_after();
             if (elect_one_sync()) {
                 const uint64_t db0 = umma_desc_at(tmpl, base + TS_OFF_WC);
@@ -168,9 +171,9 @@ tail_strip_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
             const TsItem ti = ts_item(item, nstrips, nseg, SH, hn, hout);
             for (int s = 0; s < ti.nsteps; ++s, ++g) {
                 const uint32_t st = g & 1;
-                mbar_wait_idle(&a_full[st], (g >> 1) & 1, TS_IDLE_NS);
+                mbar_wait_idle(&a_full[st], (g >> 1) & 1, TS_MMA_NS);
                 for (int hf = 0; hf < 2; ++hf) {
-                    mbar_wait_idle(&acc_empty[hf], (g & 1) ^ 1, TS_IDLE_NS);
+                    mbar_wait_idle(&acc_empty[hf], (g & 1) ^ 1, TS_MMA_NS);
                     tc_fence_after();
                     if (elect_one_sync()) {
                         const uint64_t da0 = umma_desc_at(tmpl, base + TS_OFF_A + st * TS_ASTAGE);
@@ -193,9 +196,13 @@ tail_strip_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         const int vv = wg >> 1, c0 = (wg & 1) * 32;
         const uint32_t lanef = (uint32_t)(quad * 32) << 16;
         const int H2 = 2 * h, W2 = 2 * w;
-        // U pixel (urow, ucol) of a step -> byte offset in its buffer: M-tile (urow / 4, ucol / 32), row (urow % 4, ucol % 32)
+        // U pixel (urow, ucol) of a step -> byte offset in its buffer: M-tile (urow / 4, ucol / 32), row (urow % 4) * 32 + p(ucol % 32)
+        // with p(u) = u / 2 + 16 (u & 1): even columns first, then the odd ones.  A warp writes the columns 2 lane + vv, i.e.
+        // rows (lane & 15) + 16 vv: eight consecutive lanes have eight different swizzle keys (row & 7) and their 16-byte stores
+        // hit eight different bank groups (with p = identity they shared four: a 2-way conflict on every store, ncu).
         auto uoff = [](int urow, int ucol) -> uint32_t {
-            return (uint32_t)(((urow >> 2) * 2 + (ucol >> 5)) * 16384 + ((urow & 3) * 32 + (ucol & 31)) * 128);
+            const int u = ucol & 31;
+            return (uint32_t)(((urow >> 2) * 2 + (ucol >> 5)) * 16384 + ((urow & 3) * 32 + (u >> 1) + 16 * (u & 1)) * 128);
         };
         uint32_t g = 0;
         for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
@@ -268,6 +275,10 @@ tail_strip_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         float* ring = reinterpret_cast<float*>(sm + TS_OFF_RING);
         auto slot = [](int R) -> int { return (int)((unsigned)(R + 2 * TS_RING) % (unsigned)TS_RING) * (9 * 64); };
         const long plane = (long)hout * wout;
+        // TMEM lane j of an M-tile holds U column u(j) of its 32-column half (see uoff): even columns in lanes 0..15, odd in 16..31
+        const int ucl = lane < 16 ? 2 * lane : 2 * (lane - 16) + 1;
+        const int src_l = lane < 16 ? (lane + 15) : lane - 16;          // lane holding column u - 1 (lane 0: none, patched below)
+        const int src_r = lane < 16 ? lane + 16 : (lane - 15) & 31;     // lane holding column u + 1 (lane 31: none, patched below)
         uint32_t g = 0;
         pdl_wait();
         for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
@@ -297,16 +308,16 @@ tail_strip_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
                             const float r0 = __uint_as_float(dr[(dyi * 3 + 0) * 3 + c]), r1 = __uint_as_float(dr[(dyi * 3 + 1) * 3 + c]);
                             const float r2v = __uint_as_float(dr[(dyi * 3 + 2) * 3 + c]);
                             // out[X] sums D[X-1][tap dx=-1] + D[X][tap dx=0] + D[X+1][tap dx=+1]
-                            const float fl_l = __shfl_up_sync(0xffffffffu, l0, 1);
-                            float fr_l = __shfl_down_sync(0xffffffffu, l2, 1);
-                            const float r2_first = __shfl_sync(0xffffffffu, r2v, 0);
+                            const float fl_l = __shfl_sync(0xffffffffu, l0, src_l);
+                            float fr_l = __shfl_sync(0xffffffffu, l2, src_r);
+                            const float r2_first = __shfl_sync(0xffffffffu, r2v, 0);       // column 32 = column 0 of the right half
                             if (lane == 31) fr_l = r2_first;
-                            float fl_r = __shfl_up_sync(0xffffffffu, r0, 1);
-                            const float l0_last = __shfl_sync(0xffffffffu, l0, 31);
+                            float fl_r = __shfl_sync(0xffffffffu, r0, src_l);
+                            const float l0_last = __shfl_sync(0xffffffffu, l0, 31);        // column 31 of the left half
                             if (lane == 0) fl_r = l0_last;
-                            const float fr_r = __shfl_down_sync(0xffffffffu, r2v, 1);
-                            rw[(dyi * 3 + c) * 64 + lane] = fl_l + l1 + fr_l;
-                            rw[(dyi * 3 + c) * 64 + 32 + lane] = fl_r + r1 + fr_r;
+                            const float fr_r = __shfl_sync(0xffffffffu, r2v, src_r);
+                            rw[(dyi * 3 + c) * 64 + ucl] = fl_l + l1 + fr_l;
+                            rw[(dyi * 3 + c) * 64 + 32 + ucl] = fl_r + r1 + fr_r;
                         }
                     }
                 }
