@@ -216,8 +216,10 @@ attn_z_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ 
             ++g;
         };
         // MQ box i = 0..11 is (K chunk i / 3, 128-row slab i % 3).  (Four extra slots in the operand region, idle during
-        // phase 1, were tried: eight boxes in flight instead of four did not shorten the phase -- 128 CTAs pulling the same
-        // 278 KB per pair run at the chip's L2 bandwidth, ~32 B/clk per SM -- and were removed again.)
+        // phase 1, were tried: eight boxes in flight instead of four did not shorten the phase and were removed again.  The
+        // phase is not bound by the L2 port -- tools/probes/tma_stream_probe.cu: 64 B/clk per SM with >= 2 boxes in flight,
+        // alone or with 148 SMs pulling -- but by shared-memory bandwidth: per 16 KB box TMA writes 16 KB and the four N = 128
+        // MMAs read 16 KB of weights + 16 KB of query rows = 384 cycles at 128 B/clk, which is the ~32 B/clk observed.)
         auto mq_box = [&](int i) { ring_load(&mapMQ, i / 3, (i % 3) * 128); };
         if constexpr (!RING) {
             if (elect_one_sync()) {                      // constants: loaded while the previous kernel drains
