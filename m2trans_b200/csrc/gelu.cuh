@@ -53,9 +53,8 @@ __device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
 }
 __device__ __forceinline__ uint64_t f2_splat(float a) { return f2_pack(a, a); }
 
-// returns half2 bits of (gelu(acc.x + bias.x), gelu(acc.y + bias.y))
-__device__ __forceinline__ uint32_t gelu_pair_h2(uint64_t acc, uint64_t bias) {
-    const uint64_t x = f2_add(acc, bias);
+// (gelu(x.lo), gelu(x.hi)) of a packed pair, fp32 results
+__device__ __forceinline__ uint64_t gelu_pair(uint64_t x) {
     float x0, x1;
     f2_unpack(x, x0, x1);
     const uint64_t a = f2_pack(fabsf(x0), fabsf(x1));
@@ -69,9 +68,13 @@ __device__ __forceinline__ uint32_t gelu_pair_h2(uint64_t acc, uint64_t bias) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(q0));
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(q1));
     const uint64_t na = f2_pack(-fabsf(x0), -fabsf(x1));
-    const uint64_t g = f2_fma(na, f2_pack(e0, e1), f2_pack(fmaxf(x0, 0.f), fmaxf(x1, 0.f)));
+    return f2_fma(na, f2_pack(e0, e1), f2_pack(fmaxf(x0, 0.f), fmaxf(x1, 0.f)));
+}
+
+// returns half2 bits of (gelu(acc.x + bias.x), gelu(acc.y + bias.y))
+__device__ __forceinline__ uint32_t gelu_pair_h2(uint64_t acc, uint64_t bias) {
     float g0, g1;
-    f2_unpack(g, g0, g1);
+    f2_unpack(gelu_pair(f2_add(acc, bias)), g0, g1);
     const __half2 hv = __floats2half2_rn(g0, g1);
     return *reinterpret_cast<const uint32_t*>(&hv);
 }

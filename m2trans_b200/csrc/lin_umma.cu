@@ -37,24 +37,9 @@ __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, const vo
 }
 
 // exact-erf GELU (HF ACT2FN["gelu"]) in the erfc form of gelu.cuh, fp32 results, two elements at a time with the packed
-// fp32x2 instructions (one issue slot per pair for the 11 FMA-pipe operations): the GELU epilogue is issue-bound
+// fp32x2 instructions (one issue slot per pair for the 6 FMA-pipe operations): the GELU epilogue is issue-bound
 // (tools/lin_timing.py: +16 us on a 23 us kernel at N = 384, K = 96 with a scalar form)
-__device__ __forceinline__ void gelu_erfc2(float& x0, float& x1) {
-    const uint64_t a = f2_pack(fabsf(x0), fabsf(x1));
-    uint64_t p = f2_fma(f2_splat(9.250150469597429e-05f), a, f2_splat(-9.215229511028156e-05f));
-    p = f2_fma(p, a, f2_splat(0.00345434108749032f));
-    p = f2_fma(p, a, f2_splat(0.02103373408317566f));
-    p = f2_fma(p, a, f2_splat(0.04988996684551239f));
-    p = f2_fma(p, a, f2_splat(1.f));
-    float p0, p1, r0, r1;
-    f2_unpack(p, p0, p1);
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(p0));
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(p1));
-    uint64_t r = f2_pack(r0, r1);
-    r = f2_mul(r, r); r = f2_mul(r, r); r = f2_mul(r, r); r = f2_mul(r, r);
-    const uint64_t g = f2_fma(f2_mul(a, r), f2_splat(-0.5f), f2_pack(fmaxf(x0, 0.f), fmaxf(x1, 0.f)));
-    f2_unpack(g, x0, x1);
-}
+__device__ __forceinline__ void gelu_erfc2(float& x0, float& x1) { f2_unpack(gelu_pair(f2_pack(x0, x1)), x0, x1); }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
     const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);

@@ -36,22 +36,7 @@ struct MlpCfg {
     static constexpr uint32_t ACC2 = 256;                     // TMEM column of the output accumulator (acc1: 0 and 128)
 };
 
-__device__ __forceinline__ void gelu2(float& x0, float& x1) {  // as lin_umma.cu: exact-erf GELU, erfc form, packed fp32x2
-    const uint64_t a = f2_pack(fabsf(x0), fabsf(x1));
-    uint64_t p = f2_fma(f2_splat(9.250150469597429e-05f), a, f2_splat(-9.215229511028156e-05f));
-    p = f2_fma(p, a, f2_splat(0.00345434108749032f));
-    p = f2_fma(p, a, f2_splat(0.02103373408317566f));
-    p = f2_fma(p, a, f2_splat(0.04988996684551239f));
-    p = f2_fma(p, a, f2_splat(1.f));
-    float p0, p1, r0, r1;
-    f2_unpack(p, p0, p1);
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(p0));
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(p1));
-    uint64_t r = f2_pack(r0, r1);
-    r = f2_mul(r, r); r = f2_mul(r, r); r = f2_mul(r, r); r = f2_mul(r, r);
-    const uint64_t g = f2_fma(f2_mul(a, r), f2_splat(-0.5f), f2_pack(fmaxf(x0, 0.f), fmaxf(x1, 0.f)));
-    f2_unpack(g, x0, x1);
-}
+__device__ __forceinline__ void gelu2(float& x0, float& x1) { f2_unpack(gelu_pair(f2_pack(x0, x1)), x0, x1); }
 
 __device__ __forceinline__ uint32_t bf16x2(float a, float b) {
     const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
