@@ -138,10 +138,18 @@ __device__ long long g_az_dbg[3 * 64];     // per branch 2..4: CTA 0, epilogue t
 template <int C, bool LO>
 __global__ void __launch_bounds__(AzCfg<C>::THREADS, AzCfg<C>::MIN_CTAS)
 attn_z_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ CUtensorMap mapMQ,
-              const __grid_constant__ CUtensorMap mapWV, int h, int w, int npairs, int single, const AttnFuse fz) {
+              const __grid_constant__ CUtensorMap mapWV, const __grid_constant__ CUtensorMap mapTlo,
+              const __grid_constant__ CUtensorMap mapTn, const __grid_constant__ CUtensorMap mapTnlo, int h, int w, int npairs,
+              int single, const AttnFuse fz) {
     using CF = AzCfg<C>;
     constexpr int NBLK = CF::NBLK;
     constexpr bool RING = CF::RING;
+    // Precise mode, C = 256: the glue's 32-byte pieces of Tlo / Tnext / Tnext_lo (one LSU sector per lane and 16-byte pass,
+    // ~2 cycles each: 23 K cycles per pair in branch 3) travel as TMA boxes of whole 512-byte pixel rows instead.  After the
+    // O MMAs the operand region and the weight ring are idle: the t_k residual tile lands in the former, the n_{k+1}/2 tile in
+    // the latter, the epilogue threads update both in place (t_{k+1} and its residual) and one thread stores them.  The weight
+    // ring then cannot run ahead into the next pair (branch 3 only; branch 4 has no next tensor and keeps the ring).
+    constexpr bool STG = LO && RING;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
@@ -159,6 +167,8 @@ attn_z_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ 
     uint64_t* o_full = bars + 16;
     uint64_t* pair_done = bars + 17;         // O consumed and the tile no longer needed
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+    uint64_t* g_full = bars + 20;            // STG: staged tiles landed
+    uint64_t* stage_free = bars + 21;        // STG: the stores have read the ring region
     float* sinv = reinterpret_cast<float*>(sm + CF::OFF_INV);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -188,10 +198,12 @@ attn_z_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ 
         mbar_init(pzs_ready, CF::NEPI);
         mbar_init(o_full, 1);
         mbar_init(pair_done, CF::NEPI);
+        if constexpr (STG) { mbar_init(g_full, 1); mbar_init(stage_free, 1); }
         mbar_fence_init();
         tma_prefetch_desc(&mapT);
         tma_prefetch_desc(&mapMQ);
         tma_prefetch_desc(&mapWV);
+        if constexpr (STG) { tma_prefetch_desc(&mapTlo); tma_prefetch_desc(&mapTn); tma_prefetch_desc(&mapTnlo); }
     }
     tc_fence_before();
     __syncthreads();
@@ -234,6 +246,9 @@ attn_z_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ 
             const AzPair pc = az_pair(p, nwx, per_img, ystep);
             // the first four weight boxes do not wait for this pair's MMAs (the ring has four slots), the tile does
             // not wait for the ring: issuing in this order cannot deadlock and lets the weights run ahead
+            if constexpr (STG) {
+                if (fz.Tnext != nullptr && it > 0) mbar_wait(stage_free, (it - 1) & 1);   // the ring region held the n/2 tile
+            }
             if constexpr (RING) { mq_box(0); mq_box(1); mq_box(2); mq_box(3); }
             if (it == 0) pdl_wait();
             mbar_wait(pair_done, (it & 1) ^ 1);
@@ -513,18 +528,18 @@ attn_z_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ 
                 // this thread will touch back into L2 now (no registers held), block 0 also into registers
                 if (has_next) {
 #pragma unroll
-                    for (int nb = 1; nb < NBLK; ++nb)
+                    for (int nb = STG ? 0 : 1; nb < NBLK; ++nb)
 #pragma unroll
                         for (int j = 0; j < JN; ++j) az_prefetch_l2(fz.Tnext + tnext_off(nb * SPB + j0 + j));
-                    load_h(0, hcur);
+                    if constexpr (!STG) load_h(0, hcur);
                 }
                 if constexpr (LO) {
 #pragma unroll
-                    for (int nb = 1; nb < NBLK; ++nb)
+                    for (int nb = STG ? 0 : 1; nb < NBLK; ++nb)
 #pragma unroll
                         for (int j = 0; j < JN; ++j) az_prefetch_l2(fz.Tlo + trow_off + (nb * SPB + j0 + j) * NB);
                 }
-                load_l(0, lcur);
+                if constexpr (!STG) load_l(0, lcur);
             }
 
             // ---- phase 6: PZ / sum -> fp16 operand tile ---------------------------------------------------------------
@@ -545,6 +560,107 @@ attn_z_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ 
             mbar_wait(tile_full, it & 1);                     // completed long ago: makes the TMA-written t_k rows visible here
             tc_fence_after();
             M2T_ZT(7);
+            if constexpr (STG) {
+                uint8_t* stl = sm + CF::OFF_OPER;                 // t_k residual tile -> t_{k+1} residual in place
+                uint8_t* sth = sm + CF::OFF_W;                    // n_{k+1}/2 tile -> t_{k+1} in place (the weight ring)
+                const int nv = (pc.y + BLK < h && !single) ? 2 : 1;   // real windows of this pair
+                if (tid == 0) {
+                    mbar_expect_tx(g_full, (uint32_t)(nv * NBLK * 8192 * (has_next ? 2 : 1)));
+                    for (int wv = 0; wv < nv; ++wv)
+                        for (int nb = 0; nb < NBLK; ++nb) {
+                            tma_load_4d(stl + nb * AZ_OPCH + wv * 8192, &mapTlo, g_full, nb * 64, pc.x, pc.y + BLK * wv, pc.b);
+                            if (has_next)
+                                tma_load_4d(sth + nb * AZ_SLOT + wv * 8192, &mapTn, g_full, nb * 64, pc.x, pc.y + BLK * wv, pc.b);
+                        }
+                }
+                mbar_wait(g_full, it & 1);
+#pragma unroll 1
+                for (int nb = 0; nb < NBLK; ++nb) {
+                    const uint8_t* tst = sm + CF::OFF_TILE + nb * AZ_CHUNK + trow * 128;
+                    uint8_t* lrow = stl + nb * AZ_OPCH + m * 128;
+                    uint8_t* hrow = sth + nb * AZ_SLOT + m * 128;
+#pragma unroll
+                    for (int jj = 0; jj < JN; ++jj) {
+                        const int j = j0 + jj;
+                        const int s = nb * SPB + j;
+                        uint32_t r[16];
+                        tmem_ld16(tmem_base + lane_sel + CF::TM_A + s * NB, r);
+                        const uint32_t c0o = (uint32_t)(((2 * j) ^ (m & 7)) << 4), c1o = (uint32_t)(((2 * j + 1) ^ (m & 7)) << 4);
+                        uint4 tk[2], tl[2];
+                        tk[0] = *reinterpret_cast<const uint4*>(tst + (((2 * j) ^ (trow & 7)) << 4));
+                        tk[1] = *reinterpret_cast<const uint4*>(tst + (((2 * j + 1) ^ (trow & 7)) << 4));
+                        tl[0] = *reinterpret_cast<const uint4*>(lrow + c0o);
+                        tl[1] = *reinterpret_cast<const uint4*>(lrow + c1o);
+                        tmem_ld_wait();
+                        if (valid) {
+                            const int fy = ly * S + s / S, fx = lx * S + s % S;
+                            const long pix = ((long)pc.b * fz.Hp + fy) * fz.Wp + fx;
+                            float yv[NB];
+                            const __half2* th = reinterpret_cast<const __half2*>(tk);
+                            const __half2* tlh = reinterpret_cast<const __half2*>(tl);
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) {
+                                const float2 tf = __half22float2(th[e]), lf = __half22float2(tlh[e]);
+                                yv[2 * e] = __uint_as_float(r[2 * e]) + (tf.x + lf.x);
+                                yv[2 * e + 1] = __uint_as_float(r[2 * e + 1]) + (tf.y + lf.y);
+                            }
+                            uint4 yo[2], yl[2];
+                            __half2* yh = reinterpret_cast<__half2*>(yo);
+                            __half2* ylh = reinterpret_cast<__half2*>(yl);
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) {
+                                yh[e] = __floats2half2_rn(yv[2 * e], yv[2 * e + 1]);
+                                const float2 yr = __half22float2(yh[e]);
+                                ylh[e] = __floats2half2_rn((yv[2 * e] - yr.x) * 2048.f, (yv[2 * e + 1] - yr.y) * 2048.f);
+                            }
+                            stg256(fz.Y + pix * NF + NB * br, yo[0], yo[1]);
+                            stg256(fz.Ylo + pix * NF + NB * br, yl[0], yl[1]);
+                            if (has_next) {
+                                uint4 hc[2], to[2], tol[2];
+                                hc[0] = *reinterpret_cast<const uint4*>(hrow + c0o);
+                                hc[1] = *reinterpret_cast<const uint4*>(hrow + c1o);
+                                __half2* tnh = reinterpret_cast<__half2*>(to);
+                                __half2* tnl = reinterpret_cast<__half2*>(tol);
+                                const __half2* hh = reinterpret_cast<const __half2*>(hc);
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) {
+                                    const float2 hf = __half22float2(hh[e]);
+                                    const float t0 = fmaf(0.5f, yv[2 * e], hf.x), t1 = fmaf(0.5f, yv[2 * e + 1], hf.y);
+                                    tnh[e] = __floats2half2_rn(t0, t1);
+                                    const float2 tr = __half22float2(tnh[e]);
+                                    tnl[e] = __floats2half2_rn(t0 - tr.x, t1 - tr.y);
+                                }
+                                *reinterpret_cast<uint4*>(hrow + c0o) = to[0];
+                                *reinterpret_cast<uint4*>(hrow + c1o) = to[1];
+                                *reinterpret_cast<uint4*>(lrow + c0o) = tol[0];
+                                *reinterpret_cast<uint4*>(lrow + c1o) = tol[1];
+                            }
+                        }
+                    }
+                }
+                tc_fence_before();
+                if (has_next) {
+                    fence_proxy_async();                          // in-place updates -> the TMA stores below
+                    asm volatile("bar.sync 1, %0;" ::"n"(CF::NEPI * 32) : "memory");
+                    if (tid == 0) {
+                        for (int wv = 0; wv < nv; ++wv)
+                            for (int nb = 0; nb < NBLK; ++nb) {
+                                tma_store_4d(&mapTn, sth + nb * AZ_SLOT + wv * 8192, nb * 64, pc.x, pc.y + BLK * wv, pc.b);
+                                tma_store_4d(&mapTnlo, stl + nb * AZ_OPCH + wv * 8192, nb * 64, pc.x, pc.y + BLK * wv, pc.b);
+                            }
+                        tma_store_commit();
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(pair_done);
+                if (has_next && tid == 0) {                       // after the arrive: the next tile need not wait for this
+                    tma_store_wait_read();
+                    mbar_arrive(stage_free);
+                }
+                __syncwarp();
+                M2T_ZT(8);
+                continue;
+            }
 #pragma unroll 1
             for (int nb = 0; nb < NBLK; ++nb) {
                 if (valid && nb + 1 < NBLK) {
@@ -623,6 +739,7 @@ attn_z_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ 
             M2T_ZT(8);
         }
     }
+    if constexpr (STG) { if (tid == 0) tma_store_wait_all(); }
     tc_fence_before();
     __syncthreads();
     if (warp == 5) tmem_dealloc(tmem_base, CF::TM_COLS);
@@ -657,8 +774,21 @@ int launch_attn_z_c(const __half* T, const __half* MQ, const __half* WV, int B, 
     const int single = !paired_only && B * nwy * nwx <= cap ? 1 : 0;
     const int npairs = single ? B * nwy * nwx : B * ((nwy + 1) / 2) * nwx;
     const int grid = npairs < cap ? npairs : cap;
+    CUtensorMap mapTlo = mapT, mapTn = mapT, mapTnlo = mapT;      // used by the staged glue only (precise mode, C = 256)
+    if (LO && CF::RING) {
+        const uint64_t dims[4] = {(uint64_t)C, (uint64_t)w, (uint64_t)h, (uint64_t)B};
+        const uint64_t str[4] = {2, (uint64_t)C * 2, (uint64_t)w * C * 2, (uint64_t)h * w * C * 2};
+        const uint32_t box[4] = {64, BLK, BLK, 1};
+        M2T_TRY(make_tensor_map(&mapTlo, fz.Tlo, 2, 4, dims, str, box, 3));
+        if (fz.Tnext != nullptr) {
+            if (fz.Tnext_lo == nullptr) { set_error("attn_z: precise mode needs Tnext_lo with Tnext"); return M2T_E_ARG; }
+            M2T_TRY(make_tensor_map(&mapTn, fz.Tnext, 2, 4, dims, str, box, 3));
+            M2T_TRY(make_tensor_map(&mapTnlo, fz.Tnext_lo, 2, 4, dims, str, box, 3));
+        }
+    }
     M2T_ENSURE_SMEM((attn_z_kernel<C, LO>), CF::SMEM);
-    M2T_CUDA(launch_pdl(attn_z_kernel<C, LO>, dim3(grid), dim3(CF::THREADS), CF::SMEM, s, mapT, mapMQ, mapWV, h, w, npairs, single, fz));
+    M2T_CUDA(launch_pdl(attn_z_kernel<C, LO>, dim3(grid), dim3(CF::THREADS), CF::SMEM, s, mapT, mapMQ, mapWV, mapTlo, mapTn, mapTnlo,
+                        h, w, npairs, single, fz));
     return M2T_OK;
 }
 
