@@ -149,7 +149,8 @@ attn_z_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ 
     // O MMAs the operand region and the weight ring are idle: the t_k residual tile lands in the former, the n_{k+1}/2 tile in
     // the latter, the epilogue threads update both in place (t_{k+1} and its residual) and one thread stores them.  The weight
     // ring then cannot run ahead into the next pair (branch 3 only; branch 4 has no next tensor and keeps the ring).
-    constexpr bool STG = LO && RING;
+    // Fast mode, branch 3: the same for the n_4/2 tile alone, staged in the operand region (the ring keeps running ahead).
+    constexpr bool STG = RING;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
@@ -246,7 +247,7 @@ attn_z_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ 
             const AzPair pc = az_pair(p, nwx, per_img, ystep);
             // the first four weight boxes do not wait for this pair's MMAs (the ring has four slots), the tile does
             // not wait for the ring: issuing in this order cannot deadlock and lets the weights run ahead
-            if constexpr (STG) {
+            if constexpr (STG && LO) {
                 if (fz.Tnext != nullptr && it > 0) mbar_wait(stage_free, (it - 1) & 1);   // the ring region held the n/2 tile
             }
             if constexpr (RING) { mq_box(0); mq_box(1); mq_box(2); mq_box(3); }
@@ -386,6 +387,9 @@ attn_z_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ 
             // ---- phase 2: A -> fp16 operand tile ---------------------------------------------------------------------
             M2T_ZT(0);
             mbar_wait(a_full, it & 1);
+            if constexpr (STG && !LO) {      // fast mode: the previous pair's t_{k+1} tile has left the operand region
+                if (fz.Tnext != nullptr && it > 0) mbar_wait(stage_free, (it - 1) & 1);
+            }
             tc_fence_after();
             M2T_ZT(1);
 #pragma unroll 1
@@ -540,6 +544,7 @@ attn_z_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ 
                         for (int j = 0; j < JN; ++j) az_prefetch_l2(fz.Tlo + trow_off + (nb * SPB + j0 + j) * NB);
                 }
                 if constexpr (!STG) load_l(0, lcur);
+                else if (!LO && !has_next) load_l(0, lcur);       // zeros: the unstaged loop below (fast mode, branch 4)
             }
 
             // ---- phase 6: PZ / sum -> fp16 operand tile ---------------------------------------------------------------
@@ -560,15 +565,17 @@ attn_z_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ 
             mbar_wait(tile_full, it & 1);                     // completed long ago: makes the TMA-written t_k rows visible here
             tc_fence_after();
             M2T_ZT(7);
-            if constexpr (STG) {
-                uint8_t* stl = sm + CF::OFF_OPER;                 // t_k residual tile -> t_{k+1} residual in place
-                uint8_t* sth = sm + CF::OFF_W;                    // n_{k+1}/2 tile -> t_{k+1} in place (the weight ring)
+            if (STG && (LO || has_next)) {
+                uint8_t* stl = sm + CF::OFF_OPER;                 // t_k residual tile -> t_{k+1} residual in place (precise mode)
+                // n_{k+1}/2 tile -> t_{k+1} in place: the weight ring in precise mode, the operand region in fast mode
+                uint8_t* sth = sm + (LO ? CF::OFF_W : CF::OFF_OPER);
                 const int nv = (pc.y + BLK < h && !single) ? 2 : 1;   // real windows of this pair
                 if (tid == 0) {
-                    mbar_expect_tx(g_full, (uint32_t)(nv * NBLK * 8192 * (has_next ? 2 : 1)));
+                    mbar_expect_tx(g_full, (uint32_t)(nv * NBLK * 8192 * ((LO ? 1 : 0) + (has_next ? 1 : 0))));
                     for (int wv = 0; wv < nv; ++wv)
                         for (int nb = 0; nb < NBLK; ++nb) {
-                            tma_load_4d(stl + nb * AZ_OPCH + wv * 8192, &mapTlo, g_full, nb * 64, pc.x, pc.y + BLK * wv, pc.b);
+                            if constexpr (LO)
+                                tma_load_4d(stl + nb * AZ_OPCH + wv * 8192, &mapTlo, g_full, nb * 64, pc.x, pc.y + BLK * wv, pc.b);
                             if (has_next)
                                 tma_load_4d(sth + nb * AZ_SLOT + wv * 8192, &mapTn, g_full, nb * 64, pc.x, pc.y + BLK * wv, pc.b);
                         }
@@ -589,8 +596,12 @@ attn_z_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ 
                         uint4 tk[2], tl[2];
                         tk[0] = *reinterpret_cast<const uint4*>(tst + (((2 * j) ^ (trow & 7)) << 4));
                         tk[1] = *reinterpret_cast<const uint4*>(tst + (((2 * j + 1) ^ (trow & 7)) << 4));
-                        tl[0] = *reinterpret_cast<const uint4*>(lrow + c0o);
-                        tl[1] = *reinterpret_cast<const uint4*>(lrow + c1o);
+                        if constexpr (LO) {
+                            tl[0] = *reinterpret_cast<const uint4*>(lrow + c0o);
+                            tl[1] = *reinterpret_cast<const uint4*>(lrow + c1o);
+                        } else {
+                            tl[0] = make_uint4(0u, 0u, 0u, 0u); tl[1] = make_uint4(0u, 0u, 0u, 0u);
+                        }
                         tmem_ld_wait();
                         if (valid) {
                             const int fy = ly * S + s / S, fx = lx * S + s % S;
@@ -600,9 +611,13 @@ attn_z_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ 
                             const __half2* tlh = reinterpret_cast<const __half2*>(tl);
 #pragma unroll
                             for (int e = 0; e < 8; ++e) {
-                                const float2 tf = __half22float2(th[e]), lf = __half22float2(tlh[e]);
-                                yv[2 * e] = __uint_as_float(r[2 * e]) + (tf.x + lf.x);
-                                yv[2 * e + 1] = __uint_as_float(r[2 * e + 1]) + (tf.y + lf.y);
+                                float2 tf = __half22float2(th[e]);
+                                if constexpr (LO) {
+                                    const float2 lf = __half22float2(tlh[e]);
+                                    tf.x += lf.x; tf.y += lf.y;
+                                }
+                                yv[2 * e] = __uint_as_float(r[2 * e]) + tf.x;
+                                yv[2 * e + 1] = __uint_as_float(r[2 * e + 1]) + tf.y;
                             }
                             uint4 yo[2], yl[2];
                             __half2* yh = reinterpret_cast<__half2*>(yo);
@@ -614,7 +629,7 @@ attn_z_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ 
                                 ylh[e] = __floats2half2_rn((yv[2 * e] - yr.x) * 2048.f, (yv[2 * e + 1] - yr.y) * 2048.f);
                             }
                             stg256(fz.Y + pix * NF + NB * br, yo[0], yo[1]);
-                            stg256(fz.Ylo + pix * NF + NB * br, yl[0], yl[1]);
+                            if constexpr (LO) stg256(fz.Ylo + pix * NF + NB * br, yl[0], yl[1]);
                             if (has_next) {
                                 uint4 hc[2], to[2], tol[2];
                                 hc[0] = *reinterpret_cast<const uint4*>(hrow + c0o);
@@ -632,8 +647,10 @@ attn_z_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ 
                                 }
                                 *reinterpret_cast<uint4*>(hrow + c0o) = to[0];
                                 *reinterpret_cast<uint4*>(hrow + c1o) = to[1];
-                                *reinterpret_cast<uint4*>(lrow + c0o) = tol[0];
-                                *reinterpret_cast<uint4*>(lrow + c1o) = tol[1];
+                                if constexpr (LO) {
+                                    *reinterpret_cast<uint4*>(lrow + c0o) = tol[0];
+                                    *reinterpret_cast<uint4*>(lrow + c1o) = tol[1];
+                                }
                             }
                         }
                     }
@@ -646,7 +663,8 @@ attn_z_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ 
                         for (int wv = 0; wv < nv; ++wv)
                             for (int nb = 0; nb < NBLK; ++nb) {
                                 tma_store_4d(&mapTn, sth + nb * AZ_SLOT + wv * 8192, nb * 64, pc.x, pc.y + BLK * wv, pc.b);
-                                tma_store_4d(&mapTnlo, stl + nb * AZ_OPCH + wv * 8192, nb * 64, pc.x, pc.y + BLK * wv, pc.b);
+                                if constexpr (LO)
+                                    tma_store_4d(&mapTnlo, stl + nb * AZ_OPCH + wv * 8192, nb * 64, pc.x, pc.y + BLK * wv, pc.b);
                             }
                         tma_store_commit();
                     }
@@ -775,15 +793,15 @@ int launch_attn_z_c(const __half* T, const __half* MQ, const __half* WV, int B, 
     const int npairs = single ? B * nwy * nwx : B * ((nwy + 1) / 2) * nwx;
     const int grid = npairs < cap ? npairs : cap;
     CUtensorMap mapTlo = mapT, mapTn = mapT, mapTnlo = mapT;      // used by the staged glue only (precise mode, C = 256)
-    if (LO && CF::RING) {
+    if (CF::RING) {
         const uint64_t dims[4] = {(uint64_t)C, (uint64_t)w, (uint64_t)h, (uint64_t)B};
         const uint64_t str[4] = {2, (uint64_t)C * 2, (uint64_t)w * C * 2, (uint64_t)h * w * C * 2};
         const uint32_t box[4] = {64, BLK, BLK, 1};
-        M2T_TRY(make_tensor_map(&mapTlo, fz.Tlo, 2, 4, dims, str, box, 3));
+        if (LO) M2T_TRY(make_tensor_map(&mapTlo, fz.Tlo, 2, 4, dims, str, box, 3));
         if (fz.Tnext != nullptr) {
-            if (fz.Tnext_lo == nullptr) { set_error("attn_z: precise mode needs Tnext_lo with Tnext"); return M2T_E_ARG; }
+            if (LO && fz.Tnext_lo == nullptr) { set_error("attn_z: precise mode needs Tnext_lo with Tnext"); return M2T_E_ARG; }
             M2T_TRY(make_tensor_map(&mapTn, fz.Tnext, 2, 4, dims, str, box, 3));
-            M2T_TRY(make_tensor_map(&mapTnlo, fz.Tnext_lo, 2, 4, dims, str, box, 3));
+            if (LO) M2T_TRY(make_tensor_map(&mapTnlo, fz.Tnext_lo, 2, 4, dims, str, box, 3));
         }
     }
     M2T_ENSURE_SMEM((attn_z_kernel<C, LO>), CF::SMEM);
