@@ -150,7 +150,11 @@ attn_z_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ 
     // the latter, the epilogue threads update both in place (t_{k+1} and its residual) and one thread stores them.  The weight
     // ring then cannot run ahead into the next pair (branch 3 only; branch 4 has no next tensor and keeps the ring).
     // Fast mode, branch 3: the same for the n_4/2 tile alone, staged in the operand region (the ring keeps running ahead).
-    constexpr bool STG = RING;
+    // C = 64 (branch 2): its next tensor lives one level up, a window covers 4 x 4 of its pixels completely: boxes of
+    // {64 ch, 4, 4} per 64-channel chunk, all staged in the operand region (48 KB: n_3/2 -> t_3 | t_2 residual | t_3 residual).
+    // Precise mode only: -13 % for the kernel at cfg3.  In fast mode the C = 64 glue is 2 K cycles of a 12 K-cycle chain and
+    // the exposed TMA round trip plus the extra block barrier cost more than the LSU pieces (169 vs 150 us at cfg2): not used.
+    constexpr bool STG = true;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
@@ -247,7 +251,7 @@ attn_z_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ 
             const AzPair pc = az_pair(p, nwx, per_img, ystep);
             // the first four weight boxes do not wait for this pair's MMAs (the ring has four slots), the tile does
             // not wait for the ring: issuing in this order cannot deadlock and lets the weights run ahead
-            if constexpr (STG && LO) {
+            if constexpr (RING && LO) {
                 if (fz.Tnext != nullptr && it > 0) mbar_wait(stage_free, (it - 1) & 1);   // the ring region held the n/2 tile
             }
             if constexpr (RING) { mq_box(0); mq_box(1); mq_box(2); mq_box(3); }
@@ -387,7 +391,7 @@ attn_z_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ 
             // ---- phase 2: A -> fp16 operand tile ---------------------------------------------------------------------
             M2T_ZT(0);
             mbar_wait(a_full, it & 1);
-            if constexpr (STG && !LO) {      // fast mode: the previous pair's t_{k+1} tile has left the operand region
+            if constexpr (RING != LO) {      // the previous pair's t_{k+1} tile(s) have left the operand region
                 if (fz.Tnext != nullptr && it > 0) mbar_wait(stage_free, (it - 1) & 1);
             }
             tc_fence_after();
@@ -530,21 +534,23 @@ attn_z_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ 
             if (valid) {
                 // Tnext was written by branch_prep_all several kernels ago and has usually left L2: pull every segment
                 // this thread will touch back into L2 now (no registers held), block 0 also into registers
+                const bool staged = RING ? (LO || has_next) : LO;   // this pair's tiles travel by TMA (phase 8)
                 if (has_next) {
 #pragma unroll
-                    for (int nb = STG ? 0 : 1; nb < NBLK; ++nb)
+                    for (int nb = 0; nb < NBLK; ++nb)
 #pragma unroll
-                        for (int j = 0; j < JN; ++j) az_prefetch_l2(fz.Tnext + tnext_off(nb * SPB + j0 + j));
-                    if constexpr (!STG) load_h(0, hcur);
+                        for (int j = 0; j < JN; ++j)
+                            if (staged || nb > 0) az_prefetch_l2(fz.Tnext + tnext_off(nb * SPB + j0 + j));
+                    if (!staged) load_h(0, hcur);
                 }
                 if constexpr (LO) {
 #pragma unroll
-                    for (int nb = STG ? 0 : 1; nb < NBLK; ++nb)
+                    for (int nb = 0; nb < NBLK; ++nb)
 #pragma unroll
                         for (int j = 0; j < JN; ++j) az_prefetch_l2(fz.Tlo + trow_off + (nb * SPB + j0 + j) * NB);
+                } else {
+                    if (!staged) load_l(0, lcur);                 // zeros for the unstaged loop below
                 }
-                if constexpr (!STG) load_l(0, lcur);
-                else if (!LO && !has_next) load_l(0, lcur);       // zeros: the unstaged loop below (fast mode, branch 4)
             }
 
             // ---- phase 6: PZ / sum -> fp16 operand tile ---------------------------------------------------------------
@@ -565,7 +571,123 @@ attn_z_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ 
             mbar_wait(tile_full, it & 1);                     // completed long ago: makes the TMA-written t_k rows visible here
             tc_fence_after();
             M2T_ZT(7);
-            if (STG && (LO || has_next)) {
+            if constexpr (!RING && LO) {
+              {
+                // C = 64: thread = level-1 pixel (win, qi) with its 2 x 2 sub-pixels s = dy * 2 + dx.  In the next tensor the
+                // sub-pixel is piece (fx & 3) of chunk (fy & 3) of level-2 pixel (ly / 2, lx / 2).
+                uint8_t* sth = sm + CF::OFF_OPER;                 // n_3/2 -> t_3 in place: [chunk][window][4 x 4 px][128 B]
+                uint8_t* stl = sm + CF::OFF_OPER + 16384;         // t_2 residual tile: [window * 64 + qi][128 B]
+                uint8_t* stn = sm + CF::OFF_OPER + 32768;         // t_3 residual, layout of sth
+                const int nv = (pc.y + BLK < h && !single) ? 2 : 1;
+                if (tid == 0) {
+                    mbar_expect_tx(g_full, (uint32_t)(nv * 8192 * ((LO ? 1 : 0) + (has_next ? 1 : 0))));
+                    for (int wv = 0; wv < nv; ++wv) {
+                        if constexpr (LO) tma_load_4d(stl + wv * 8192, &mapTlo, g_full, 0, pc.x, pc.y + BLK * wv, pc.b);
+                        if (has_next)
+                            for (int c2 = 0; c2 < 4; ++c2)
+                                tma_load_4d(sth + c2 * 4096 + wv * 2048, &mapTn, g_full, c2 * 64, pc.x >> 1, (pc.y + BLK * wv) >> 1, pc.b);
+                    }
+                }
+                mbar_wait(g_full, it & 1);
+                const int lyl = qi >> 3, lxl = qi & 7;
+                const uint32_t r2 = (uint32_t)((lyl >> 1) * 4 + (lxl >> 1));
+                const uint8_t* tst = sm + CF::OFF_TILE + trow * 128;
+                const uint8_t* lrow = stl + m * 128;
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                    uint32_t r[16];
+                    tmem_ld16(tmem_base + lane_sel + CF::TM_A + s * NB, r);
+                    uint4 tk[2], tl[2];
+                    tk[0] = *reinterpret_cast<const uint4*>(tst + (((2 * s) ^ (trow & 7)) << 4));
+                    tk[1] = *reinterpret_cast<const uint4*>(tst + (((2 * s + 1) ^ (trow & 7)) << 4));
+                    if constexpr (LO) {
+                        tl[0] = *reinterpret_cast<const uint4*>(lrow + (((2 * s) ^ (m & 7)) << 4));
+                        tl[1] = *reinterpret_cast<const uint4*>(lrow + (((2 * s + 1) ^ (m & 7)) << 4));
+                    } else {
+                        tl[0] = make_uint4(0u, 0u, 0u, 0u); tl[1] = make_uint4(0u, 0u, 0u, 0u);
+                    }
+                    tmem_ld_wait();
+                    if (valid) {
+                        const int dy = s >> 1, dx = s & 1;
+                        const int fy = ly * 2 + dy, fx = lx * 2 + dx;
+                        const long pix = ((long)pc.b * fz.Hp + fy) * fz.Wp + fx;
+                        float yv[NB];
+                        const __half2* th = reinterpret_cast<const __half2*>(tk);
+                        const __half2* tlh = reinterpret_cast<const __half2*>(tl);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            float2 tf = __half22float2(th[e]);
+                            if constexpr (LO) {
+                                const float2 lf = __half22float2(tlh[e]);
+                                tf.x += lf.x; tf.y += lf.y;
+                            }
+                            yv[2 * e] = __uint_as_float(r[2 * e]) + tf.x;
+                            yv[2 * e + 1] = __uint_as_float(r[2 * e + 1]) + tf.y;
+                        }
+                        uint4 yo[2], yl[2];
+                        __half2* yh = reinterpret_cast<__half2*>(yo);
+                        __half2* ylh = reinterpret_cast<__half2*>(yl);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            yh[e] = __floats2half2_rn(yv[2 * e], yv[2 * e + 1]);
+                            const float2 yr = __half22float2(yh[e]);
+                            ylh[e] = __floats2half2_rn((yv[2 * e] - yr.x) * 2048.f, (yv[2 * e + 1] - yr.y) * 2048.f);
+                        }
+                        stg256(fz.Y + pix * NF + NB * br, yo[0], yo[1]);
+                        if constexpr (LO) stg256(fz.Ylo + pix * NF + NB * br, yl[0], yl[1]);
+                        if (has_next) {
+                            const uint32_t c2 = (uint32_t)(2 * (lyl & 1) + dy), pc2 = (uint32_t)(2 * (lxl & 1) + dx);
+                            const uint32_t off = c2 * 4096 + (uint32_t)win * 2048 + r2 * 128;
+                            const uint32_t c0o = ((2 * pc2) ^ (r2 & 7)) << 4, c1o = ((2 * pc2 + 1) ^ (r2 & 7)) << 4;
+                            uint4 hc[2], to[2], tol[2];
+                            hc[0] = *reinterpret_cast<const uint4*>(sth + off + c0o);
+                            hc[1] = *reinterpret_cast<const uint4*>(sth + off + c1o);
+                            __half2* tnh = reinterpret_cast<__half2*>(to);
+                            __half2* tnl = reinterpret_cast<__half2*>(tol);
+                            const __half2* hh = reinterpret_cast<const __half2*>(hc);
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) {
+                                const float2 hf = __half22float2(hh[e]);
+                                const float t0 = fmaf(0.5f, yv[2 * e], hf.x), t1 = fmaf(0.5f, yv[2 * e + 1], hf.y);
+                                tnh[e] = __floats2half2_rn(t0, t1);
+                                const float2 tr = __half22float2(tnh[e]);
+                                tnl[e] = __floats2half2_rn(t0 - tr.x, t1 - tr.y);
+                            }
+                            *reinterpret_cast<uint4*>(sth + off + c0o) = to[0];
+                            *reinterpret_cast<uint4*>(sth + off + c1o) = to[1];
+                            if constexpr (LO) {
+                                *reinterpret_cast<uint4*>(stn + off + c0o) = tol[0];
+                                *reinterpret_cast<uint4*>(stn + off + c1o) = tol[1];
+                            }
+                        }
+                    }
+                }
+                tc_fence_before();
+                if (has_next) {
+                    fence_proxy_async();
+                    asm volatile("bar.sync 1, %0;" ::"n"(CF::NEPI * 32) : "memory");
+                    if (tid == 0) {
+                        for (int wv = 0; wv < nv; ++wv)
+                            for (int c2 = 0; c2 < 4; ++c2) {
+                                tma_store_4d(&mapTn, sth + c2 * 4096 + wv * 2048, c2 * 64, pc.x >> 1, (pc.y + BLK * wv) >> 1, pc.b);
+                                if constexpr (LO)
+                                    tma_store_4d(&mapTnlo, stn + c2 * 4096 + wv * 2048, c2 * 64, pc.x >> 1, (pc.y + BLK * wv) >> 1, pc.b);
+                            }
+                        tma_store_commit();
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(pair_done);
+                if (has_next && tid == 0) {
+                    tma_store_wait_read();
+                    mbar_arrive(stage_free);
+                }
+                __syncwarp();
+                M2T_ZT(8);
+                continue;
+              }
+            }
+            if (RING && (LO || has_next)) {
                 uint8_t* stl = sm + CF::OFF_OPER;                 // t_k residual tile -> t_{k+1} residual in place (precise mode)
                 // n_{k+1}/2 tile -> t_{k+1} in place: the weight ring in precise mode, the operand region in fast mode
                 uint8_t* sth = sm + (LO ? CF::OFF_W : CF::OFF_OPER);
@@ -679,6 +801,7 @@ attn_z_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ 
                 M2T_ZT(8);
                 continue;
             }
+            if constexpr (!LO) {      // fast mode without a next tensor (branch 4): nothing to stage, y pieces only
 #pragma unroll 1
             for (int nb = 0; nb < NBLK; ++nb) {
                 if (valid && nb + 1 < NBLK) {
@@ -755,6 +878,7 @@ attn_z_kernel(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ 
             __syncwarp();
             if (lane == 0) mbar_arrive(pair_done);
             M2T_ZT(8);
+            }
         }
     }
     if constexpr (STG) { if (tid == 0) tma_store_wait_all(); }
@@ -793,6 +917,21 @@ int launch_attn_z_c(const __half* T, const __half* MQ, const __half* WV, int B, 
     const int npairs = single ? B * nwy * nwx : B * ((nwy + 1) / 2) * nwx;
     const int grid = npairs < cap ? npairs : cap;
     CUtensorMap mapTlo = mapT, mapTn = mapT, mapTnlo = mapT;      // used by the staged glue only (precise mode, C = 256)
+    if (!CF::RING) {                                              // C = 64: own level for Tlo, one level up for the next tensor
+        const uint64_t dims[4] = {(uint64_t)C, (uint64_t)w, (uint64_t)h, (uint64_t)B};
+        const uint64_t str[4] = {2, (uint64_t)C * 2, (uint64_t)w * C * 2, (uint64_t)h * w * C * 2};
+        const uint32_t box[4] = {64, BLK, BLK, 1};
+        if (LO) M2T_TRY(make_tensor_map(&mapTlo, fz.Tlo, 2, 4, dims, str, box, 3));
+        if (fz.Tnext != nullptr) {
+            if (LO && fz.Tnext_lo == nullptr) { set_error("attn_z: precise mode needs Tnext_lo with Tnext"); return M2T_E_ARG; }
+            const uint64_t h2 = (uint64_t)h / 2, w2 = (uint64_t)w / 2;
+            const uint64_t dims2[4] = {256, w2, h2, (uint64_t)B};
+            const uint64_t str2[4] = {2, 512, w2 * 512, h2 * w2 * 512};
+            const uint32_t box2[4] = {64, BLK / 2, BLK / 2, 1};
+            M2T_TRY(make_tensor_map(&mapTn, fz.Tnext, 2, 4, dims2, str2, box2, 3));
+            if (LO) M2T_TRY(make_tensor_map(&mapTnlo, fz.Tnext_lo, 2, 4, dims2, str2, box2, 3));
+        }
+    }
     if (CF::RING) {
         const uint64_t dims[4] = {(uint64_t)C, (uint64_t)w, (uint64_t)h, (uint64_t)B};
         const uint64_t str[4] = {2, (uint64_t)C * 2, (uint64_t)w * C * 2, (uint64_t)h * w * C * 2};
