@@ -60,6 +60,7 @@ extern "C" {
 #define M2T_VAR_SPLIT_QKV    (1u << 8) /* branches 2-4: separate qkv GEMM + attention kernels (QKV through HBM) instead of attn_z */
 #define M2T_VAR_TILE_TAIL    (1u << 9) /* x2/x4: the tiled fused tail (tail_fused.cu) instead of the strip-marching one (tail_strip.cu) */
 #define M2T_VAR_AZ_PAIRED    (1u << 10) /* attn_z: two windows per CTA even for small inputs (default: one window per CTA when all fit in one wave) */
+#define M2T_VAR_W2_PAIR      (1u << 11) /* precise mode: ff conv as a CTA pair per two tiles (conv_pair.cu, tcgen05 cta_group::2) instead of two 32-channel CTAs per tile; bit-identical, not faster */
 #define M2T_VAR_PRECISE_ON   (1u << 5)
 #define M2T_VAR_PRECISE_OFF  (1u << 6)
 

@@ -26,6 +26,7 @@ VAR_SPLIT_QKV16 = 1 << 7
 VAR_SPLIT_QKV = 1 << 8
 VAR_TILE_TAIL = 1 << 9
 VAR_AZ_PAIRED = 1 << 10
+VAR_W2_PAIR = 1 << 11
 PHASE_HEAD, PHASE_BODY, PHASE_TAIL, PHASE_ALL = 1, 2, 4, 7
 
 

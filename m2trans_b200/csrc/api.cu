@@ -397,7 +397,7 @@ int m2t_forward_phases(const m2t_plan* plan, const void* d_packed, const float* 
         }
         const bool last = i == plan->cfg.n_blocks - 1;      // the last block also emits fp16(res + x) for the tail
         if (precise && !(var & M2T_VAR_SIMT_CONV))
-            M2T_TRY(launch_ffconv_umma_w2(Y, reinterpret_cast<const __half*>(ws + plan->o_ylo),
+            M2T_TRY(((var & M2T_VAR_W2_PAIR) ? launch_ffconv_pair : launch_ffconv_umma_w2)(Y, reinterpret_cast<const __half*>(ws + plan->o_ylo),
                                           reinterpret_cast<const __half*>(W + L.blk[i].ffw2),
                                           reinterpret_cast<const float*>(W + L.blk[i].ffb), Xin, X,
                                           stats + (i + 1) * stat_stride, g, s, last ? res : nullptr, last ? XR : nullptr));

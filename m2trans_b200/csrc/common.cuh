@@ -221,6 +221,10 @@ int launch_ffconv_umma(const __half* Y, const __half* Wp, const float* bias, con
 int launch_ffconv_umma_w2(const __half* Y, const __half* Ylo, const __half* Wp2, const float* bias, const float* Xin,
                           float* Xout, double* stats, const Geom& g, cudaStream_t s, const float* res = nullptr,
                           __half* xr = nullptr);
+// conv_pair.cu: the same contract as a CTA pair per two tiles (tcgen05 cta_group::2, cluster of 2)
+int launch_ffconv_pair(const __half* Y, const __half* Ylo, const __half* Wp2, const float* bias, const float* Xin,
+                          float* Xout, double* stats, const Geom& g, cudaStream_t s, const float* res = nullptr,
+                          __half* xr = nullptr);
 
 // tail_simt.cu
 //   tail_up : A fp16 [B,h,w,64] -> out fp16 [B, r h + 2 pad, r w + 2 pad, 64] (interior only; pad = 0 or 1)

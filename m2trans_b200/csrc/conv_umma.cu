@@ -39,6 +39,10 @@
 // time and the forward (1.301 vs 1.310 ms) did not move -- not kept.  L2 evict_last hints on the fp32 residual stream
 // (67 MB at cfg2, re-read by branch_prep_all and by the next ff conv) changed nothing either: at cfg2 the kernel runs at
 // 41 % of DRAM bandwidth, at cfg4 (79 % of the copy bandwidth on algorithmic bytes) the stream cannot stay in L2.
+// W2 at cfg3 (stamps): the MMA warp never waits and takes 3.5 K cycles per half tile = 48 cycles per MMA = its operand
+// bytes (4 KB of A + 1-2 KB of B) at 128 B/clk.  conv_pair.cu (CTA pair, cta_group::2, each CTA its own tile and half of
+// the weight rows) halves the A reads per tile, gives bit-identical results and is no faster: its M = 256 instructions
+// take about twice as long each.
 #include "common.cuh"
 #include "tma.cuh"
 #include "umma.cuh"

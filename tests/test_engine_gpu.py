@@ -344,6 +344,19 @@ def test_attn_z_single_window_ctas_equal_paired(scale, shape):
         assert torch.equal(y1, y2), (scale, shape, mode, float((y1 - y2).abs().max()))
 
 
+@pytest.mark.parametrize("scale,shape", [(2, (1, 3, 32, 40)), (3, (2, 3, 33, 47)), (4, (2, 3, 64, 64))])
+def test_ffconv_cta_pair_equals_split_ctas(scale, shape):
+    """Precise mode: the ff conv as a CTA pair on two SMs (conv_pair.cu: tcgen05 cta_group::2, M = 256 over two tiles, each
+    CTA serving half of the weight rows) issues the same products in the same order as the default two-CTAs-per-tile kernel:
+    bit-identical outputs, with odd tile counts (a pair's last step has one tile) and several images."""
+    from m2trans_b200 import _lib
+    from m2trans_b200.synthetic import synthetic_input
+    x = synthetic_input(shape[0], shape[2], shape[3], seed=5).cuda()
+    ya = _model(scale, 3, variant=_lib.VAR_PRECISE_ON)(x)
+    yb = _model(scale, 3, variant=_lib.VAR_PRECISE_ON | _lib.VAR_W2_PAIR)(x)
+    assert torch.equal(ya, yb), float((ya - yb).abs().max())
+
+
 def test_cftm_forward_standalone_matches_reference_golden(golden_dir):
     """`model.body[i](x)` on the reference surface: one CFTM through a one-block engine plan, against the fixture the
     REAL reference CFTM produced (oracle/make_golden.py unit_cases) and against the block inside a full model."""

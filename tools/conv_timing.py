@@ -11,11 +11,14 @@ from m2trans_b200.M2Trans_network import M2Trans  # noqa: E402
 from m2trans_b200.synthetic import synthetic_input, synthetic_state_dict  # noqa: E402
 
 lib = _lib.load()
-args = types.SimpleNamespace(scale=4, rgb_range=1.0, colors=3, n_feats=64, n_blocks=2)
+# usage: python tools/conv_timing.py [cfg2|cfg3|cfg4]   (cfg3 = x3: the precise-mode kernel ffconv_umma_kernel<W2>)
+WORK = {"cfg2": (4, 16, 128, 128), "cfg3": (3, 32, 200, 266), "cfg4": (4, 64, 270, 480)}
+scale, B, H, W = WORK[sys.argv[1] if len(sys.argv) > 1 else "cfg2"]
+args = types.SimpleNamespace(scale=scale, rgb_range=1.0, colors=3, n_feats=64, n_blocks=2)
 m = M2Trans(args).cuda()
 m.cuda_graph = False
-m.load_state_dict(synthetic_state_dict(4, 0, n_blocks=2))
-x = synthetic_input(16, 128, 128).cuda()
+m.load_state_dict(synthetic_state_dict(scale, 0, n_blocks=2))
+x = synthetic_input(B, H, W).cuda()
 for _ in range(3):
     m(x)
 torch.cuda.synchronize()
