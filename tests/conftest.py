@@ -17,3 +17,12 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _library_matches_sources():
+    """The engine library is git-ignored and travels with the tree: rebuild it (nvcc cross-compiles without a GPU) when the
+    hash compiled into it differs from the hash of the sources, so that no test ever runs a stale binary."""
+    from m2trans_b200 import build
+    if build._stale():
+        build.build()
