@@ -97,3 +97,95 @@ def gmsd(x, y, data_range=1.0):
     c = 170.0 / 255.0 ** 2
     gms = (2 * ga * gb + c) / (ga ** 2 + gb ** 2 + c)
     return gms.flatten(1).std(dim=1, unbiased=False)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# FSIM (ref test.py:95-96: piq.fsim(hr, sr, data_range=1., reduction='none')).  `piq` is absent offline -- PARITY UNPINNED.
+# Restated from the published algorithm (Zhang, Zhang, Mou, Zhang: "FSIM: a feature similarity index for image quality
+# assessment", IEEE TIP 2011, with Kovesi's phase congruency PC_2 as in the authors' phasecong2) with piq's defaults:
+# 4 scales, 4 orientations, min wavelength 6, mult 2, sigma_f 0.55, delta_theta 1.2, k 2, chromatic (FSIMc) for RGB.
+def _fsim_meshgrid(h, w):
+    def axis(n):
+        if n % 2:
+            return torch.arange(-(n - 1) / 2, n / 2, dtype=torch.float64) / (n - 1)
+        return torch.arange(-n / 2, n / 2, dtype=torch.float64) / n
+    return torch.meshgrid(axis(h), axis(w), indexing="ij")
+
+
+def _fsim_filters(h, w, scales=4, orientations=4, min_length=6, mult=2, sigma_f=0.55, delta_theta=1.2):
+    gx, gy = _fsim_meshgrid(h, w)
+    radius = torch.fft.ifftshift(torch.sqrt(gx ** 2 + gy ** 2))
+    theta = torch.fft.ifftshift(torch.atan2(-gy, gx))
+    lowpass = 1.0 / (1.0 + (radius / 0.45) ** 30)          # Butterworth, cutoff 0.45, order 15 (radius already shifted)
+    radius[0, 0] = 1.0
+    sin_t, cos_t = torch.sin(theta), torch.cos(theta)
+    log_gabor = []
+    for s in range(scales):
+        f0 = 1.0 / (min_length * mult ** s)
+        g = torch.exp(-(torch.log(radius / f0) ** 2) / (2 * math.log(sigma_f) ** 2)) * lowpass
+        g[0, 0] = 0.0
+        log_gabor.append(g)
+    theta_sigma = math.pi / (orientations * delta_theta)
+    spread = []
+    for o in range(orientations):
+        a = o * math.pi / orientations
+        ds = sin_t * math.cos(a) - cos_t * math.sin(a)
+        dc = cos_t * math.cos(a) + sin_t * math.sin(a)
+        spread.append(torch.exp(-(torch.atan2(ds, dc).abs() ** 2) / (2 * theta_sigma ** 2)))
+    # [orientations, scales, h, w]
+    return torch.stack(spread)[:, None] * torch.stack(log_gabor)[None]
+
+
+def _phase_congruency(lum, k=2.0):
+    """lum [N,1,H,W] float64 in [0,255] -> PC_2 map [N,1,H,W]."""
+    n, _, h, w = lum.shape
+    filt = _fsim_filters(h, w)                                         # [O,S,H,W]
+    o_n, s_n = filt.shape[:2]
+    eps = torch.finfo(torch.float64).eps
+    resp = torch.fft.ifft2(torch.fft.fft2(lum)[:, :, None] * filt[None])   # [N,O,S,H,W] complex: even + i odd
+    even, odd = resp.real, resp.imag
+    an = resp.abs()
+    sum_e, sum_o = even.sum(2, keepdim=True), odd.sum(2, keepdim=True)
+    x_energy = torch.sqrt(sum_e ** 2 + sum_o ** 2) + eps
+    mean_e, mean_o = sum_e / x_energy, sum_o / x_energy
+    energy = (even * mean_e + odd * mean_o - (even * mean_o - odd * mean_e).abs()).sum(2, keepdim=True)
+    # noise threshold from the smallest scale (Rayleigh statistics of the filter response to noise)
+    em_n = (filt[:, :1] ** 2).sum((-2, -1), keepdim=True)[None]        # [1,O,1,1,1]
+    median_e2n = (an[:, :, :1] ** 2).flatten(-2).median(dim=-1, keepdim=True).values[..., None]   # lower median, like torch
+    noise_power = (-median_e2n / math.log(0.5)) / em_n
+    f_ifft = torch.fft.ifft2(filt).real * math.sqrt(h * w)             # [O,S,H,W]
+    sum_an2 = (f_ifft ** 2).sum(1, keepdim=True).sum((-2, -1), keepdim=True)[None]
+    sum_aiaj = torch.zeros_like(sum_an2)
+    for s in range(s_n - 1):
+        sum_aiaj = sum_aiaj + (f_ifft[:, s:s + 1] * f_ifft[:, s + 1:]).sum(1, keepdim=True).sum((-2, -1), keepdim=True)[None]
+    noise_energy2 = 2 * noise_power * sum_an2 + 4 * noise_power * sum_aiaj
+    tau = torch.sqrt(noise_energy2 / 2)
+    thr = (tau * math.sqrt(math.pi / 2) + k * torch.sqrt((2 - math.pi / 2) * tau ** 2)) / 1.7
+    energy = torch.clamp(energy - thr, min=0.0)
+    return ((energy.sum((1, 2)) + eps) / (an.sum((1, 2)) + eps))[:, None]
+
+
+def fsim(x, y, data_range=1.0, chromatic=True):
+    """Per-image FSIM (FSIMc for 3-channel inputs) of [N,C,H,W] tensors, float64 arithmetic."""
+    import torch.nn.functional as F
+    x, y = (t.double() / float(data_range) * 255.0 for t in (x, y))
+    ks = max(1, round(min(x.shape[-2:]) / 256))
+    x, y = F.avg_pool2d(x, ks), F.avg_pool2d(y, ks)
+    if x.shape[1] == 3:
+        m = torch.tensor([[0.299, 0.587, 0.114], [0.5959, -0.2746, -0.3213], [0.2115, -0.5227, 0.3112]], dtype=torch.float64)
+        xq, yq = (torch.einsum("kc,nchw->nkhw", m, t) for t in (x, y))
+        xl, yl = xq[:, :1], yq[:, :1]
+    else:
+        xl, yl, chromatic = x, y, False
+    pcx, pcy = _phase_congruency(xl), _phase_congruency(yl)
+    sch = torch.tensor([[-3.0, 0.0, 3.0], [-10.0, 0.0, 10.0], [-3.0, 0.0, 3.0]], dtype=torch.float64) / 16.0
+    kern = torch.stack((sch, sch.t()))[:, None]
+    gx, gy = (torch.sqrt((F.conv2d(t, kern, padding=1) ** 2).sum(1, keepdim=True)) for t in (xl, yl))
+
+    def sim(a, b, c):
+        return (2 * a * b + c) / (a ** 2 + b ** 2 + c)
+    pc_max = torch.maximum(pcx, pcy)
+    score = sim(gx, gy, 160.0) * sim(pcx, pcy, 0.85) * pc_max
+    if chromatic:
+        score = score * (sim(xq[:, 1:2], yq[:, 1:2], 200.0) * sim(xq[:, 2:3], yq[:, 2:3], 200.0)).abs() ** 0.03
+    return score.sum((1, 2, 3)) / pc_max.sum((1, 2, 3))

@@ -54,3 +54,35 @@ def test_gmsd_oracle_properties():
     assert (MO.gmsd(a, big) > MO.gmsd(a, small)).all() and float(MO.gmsd(a, big).max()) < 0.35
     gray = a[:, :1]
     assert MO.gmsd(gray, gray.flip(3)).shape == (2,)
+
+
+def test_fsim_oracle_properties():
+    """FSIM restated from the published algorithm (piq absent: unpinned): 1 for identical images, falls monotonically with
+    noise, handles grayscale (no chromatic term), odd sizes and the average-pooling path of large frames (min side >= 384)."""
+    import torch
+    from oracle import metrics_oracle as MO
+    g = torch.Generator().manual_seed(3)
+    x = torch.nn.functional.avg_pool2d(torch.rand(2, 3, 75, 98, generator=g), 3, 1, 1)
+    assert torch.allclose(MO.fsim(x, x), torch.ones(2, dtype=torch.float64), atol=1e-12)
+    prev = 1.0
+    for sigma in (0.01, 0.03, 0.1, 0.3):
+        v = float(MO.fsim(x, (x + sigma * torch.randn(x.shape, generator=g)).clamp(0, 1)).mean())
+        assert 0.0 < v < prev
+        prev = v
+    gray = x[:, :1]
+    assert torch.allclose(MO.fsim(gray, gray), torch.ones(2, dtype=torch.float64), atol=1e-12)
+    assert float(MO.fsim(gray, gray * 0.8).min()) < 1.0
+    big = torch.rand(1, 3, 400, 390, generator=g)
+    v = MO.fsim(big, (big + 0.05 * torch.randn(big.shape, generator=g)).clamp(0, 1))
+    assert v.shape == (1,) and 0.5 < float(v) < 1.0
+    # data_range only rescales
+    assert torch.allclose(MO.fsim(x * 255.0, (x * 0.9) * 255.0, data_range=255.0), MO.fsim(x, x * 0.9), atol=1e-12)
+
+
+def test_fsim_argument_errors():
+    import pytest
+    import torch
+    from m2trans_b200 import metrics
+    from m2trans_b200._lib import M2TError
+    with pytest.raises(M2TError):
+        metrics.fsim(torch.rand(1, 3, 32, 32), torch.rand(1, 3, 32, 32))          # no CPU path

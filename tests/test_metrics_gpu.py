@@ -78,3 +78,28 @@ def test_gmsd_matches_oracle(shape):
     print(f"gmsd {shape}: {got.tolist()} vs {want.tolist()}")
     assert got.shape == (shape[0],) and float((got - want).abs().max()) <= 2e-5
     assert float(gmsd(hr.cuda(), hr.cuda()).abs().max()) <= 1e-6          # identical images: GMS == 1 everywhere
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 75, 98), (1, 1, 64, 80), (1, 3, 400, 390)])
+def test_fsim_matches_oracle(shape):
+    """Device FSIM (torch.fft on the GPU, filter bank cached) against the oracle's float64 restatement: float64 path to
+    1e-9, float32 path (what piq computes in) to 2e-4; wrong shapes / channel counts are refused."""
+    import torch
+    from m2trans_b200 import metrics
+    from m2trans_b200._lib import M2TError
+    from oracle import metrics_oracle as MO
+    g = torch.Generator().manual_seed(sum(shape))
+    x = torch.nn.functional.avg_pool2d(torch.rand(shape, generator=g), 3, 1, 1)
+    y = (x + 0.04 * torch.randn(shape, generator=g)).clamp(0, 1)
+    want = MO.fsim(x, y)
+    got64 = metrics.fsim(x.cuda(), y.cuda())
+    got32 = metrics.fsim(x.cuda(), y.cuda(), dtype=torch.float32)
+    print(shape, want.tolist(), got64.tolist(), got32.tolist())
+    assert got64.shape == (shape[0],) and got64.dtype == torch.float32
+    assert float((got64.double().cpu() - want).abs().max()) <= 1e-6       # float32 result of a float64 evaluation
+    assert float((got32.double().cpu() - want).abs().max()) <= 2e-4
+    assert torch.allclose(metrics.fsim(x.cuda(), x.cuda()), torch.ones(shape[0], device="cuda"), atol=1e-6)
+    with pytest.raises(M2TError):
+        metrics.fsim(x.cuda(), y.cuda()[:, :, :-1])
+    with pytest.raises(M2TError):
+        metrics.fsim(torch.rand(1, 2, 32, 32, device="cuda"), torch.rand(1, 2, 32, 32, device="cuda"))

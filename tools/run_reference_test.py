@@ -8,7 +8,7 @@ What the script provides around the unmodified reference file:
     (a few small frames each) and US1K/US1K_train_{HR,LR_bicubic/X<s>} (test.py builds the TRAINING set too: 1000 tiny frames);
   * `./checkpoints/model_x<s>.pt` in the reference's container format (synthetic.reference_checkpoint);
   * `sys.modules` stand-ins for the third-party packages that are absent offline: imageio (PIL), skimage.color, pytorch_msssim
-    (the published SSIM algorithm, oracle/metrics_oracle.py), piq (GMSD restated from the published algorithm; FSIM returns 0 --
+    (the published SSIM algorithm, oracle/metrics_oracle.py), piq (GMSD and FSIM restated from the published algorithms:
     both are printed by test.py but are not on the engine's path);
   * `models.M2Trans_network` = m2trans_b200.M2Trans_network (--model engine: needs a B200) or, on a CPU-only box, a module
     with the same surface whose forward is the CPU oracle (--model oracle): that run proves the harness -- dataset tree, stubs,
@@ -106,7 +106,7 @@ def install_stubs(model_kind, scale):
     def gmsd(x, y, data_range=1.0, reduction="none"):
         return MO.gmsd(x, y, data_range).to(x.dtype)       # the published algorithm, oracle/metrics_oracle.py
     piq.gmsd = gmsd
-    piq.fsim = lambda x, y, data_range=1.0, reduction="none": torch.zeros(x.shape[0], device=x.device)   # not restated
+    piq.fsim = lambda x, y, data_range=1.0, reduction="none": MO.fsim(x, y, data_range).to(x.dtype)     # published algorithm
     sys.modules["piq"] = piq
 
     # the drop-in: models/M2Trans_network.py of the reference tree is shadowed by this repo's module
