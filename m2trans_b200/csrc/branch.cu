@@ -196,7 +196,8 @@ branch_post_kernel(int branch, const __half* __restrict__ O, const float* __rest
 // Measured and not kept (round 2): the next chunk's loads issued before the current chunk is converted, coordinates carried
 // along instead of two divisions per chunk, the residual computed only where it is stored, one wave of 4 CTAs per SM:
 // 24.8 vs 26.6 us per launch at cfg2, but 626 vs 599 us at cfg4 and 154 vs 145 us at cfg3, where this kernel already runs
-// at 87 % of the copy bandwidth.
+// at 87 % of the copy bandwidth.  The same kernel with 8 CTAs per SM: 26.7 / 154 / 607 us (no better anywhere); what the
+// one-wave form saves at cfg2 is the per-CTA fp64 finalise of the statistics (half as many CTAs).
 __global__ void __launch_bounds__(256)
 branch_prep_all_kernel(const float* __restrict__ X, const double* __restrict__ stats, __half* __restrict__ T1,
                        __half* __restrict__ T1lo, __half* __restrict__ H2, __half* __restrict__ H3,
