@@ -268,7 +268,14 @@ branch_prep_all_kernel(const float* __restrict__ X, const double* __restrict__ s
 int launch_branch_prep_all(const float* X, const double* stats, __half* T1, __half* T1lo, __half* H2, __half* H3,
                            __half* H4, const Geom& g, cudaStream_t s) {
     const long nchunks = (long)g.B * g.Hp * g.Wp / 64;
-    const long slots = 8L * device_sm_count();          // 256 threads, 32 registers: 8 CTAs per SM
+    // 256 threads x 64 registers: 4 CTAs per SM are resident.  Every CTA finalises the statistics of its image(s) in fp64
+    // (~1.5 K cycles): with few chunks per CTA one wave of CTAs beats two half as long ones (cfg2: 24.4 vs 26.3 us), with many
+    // chunks per CTA the finer split balances better (cfg4: 599 vs 626 us).
+    const long sms = device_sm_count();
+#ifndef PREP_SMALL_MULT
+#define PREP_SMALL_MULT 4
+#endif
+    const long slots = (nchunks < 32L * 4L * sms ? (long)PREP_SMALL_MULT : 8L) * sms;
     const unsigned grid = (unsigned)(nchunks < slots ? nchunks : slots);
     M2T_CUDA(launch_pdl(branch_prep_all_kernel, dim3(grid), dim3(256), 0, s, X, stats, T1, T1lo, H2, H3, H4, g.B, g.Hp, g.Wp));
     return M2T_OK;
