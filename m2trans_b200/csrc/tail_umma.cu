@@ -10,6 +10,9 @@
 // A variant of tail_up that staged the output in shared memory and sent it out with TMA stores (one per 32-pixel segment
 // and output row) was measured SLOWER (cfg2 +20 us, cfg3 +3 %): the per-unit barrier and the wait for the store to read
 // the staging tile cost more than the per-thread 32-byte stores they replaced.
+// Round 2: a per-warp staging tile with only __syncwarp and 16-byte stores that cover four complete 128-byte lines per
+// instruction (instead of 32 lanes x 32 B in 32 lines) was slower as well (51 vs 45 us at cfg2, 844 vs 704 us at cfg3): the
+// epilogue is bound by instruction issue, not by the LSU's sector rate.
 #include "common.cuh"
 #include "gelu.cuh"
 #include "tma.cuh"
