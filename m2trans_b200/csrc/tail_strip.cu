@@ -120,6 +120,7 @@ tail_strip_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_trigger();                              // persistent one-wave grid: whatever follows may be launched now, it cannot take our SMs
 
     if (warp == 20) {
         // ---- TMA producer ---------------------------------------------------------------------------------
@@ -352,7 +353,6 @@ tail_strip_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
             }
         }
     }
-    pdl_trigger();
     tc_fence_before();
     __syncthreads();
     if (warp == 21) tmem_dealloc(tmem_base, 512);
