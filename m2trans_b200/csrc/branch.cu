@@ -201,11 +201,11 @@ branch_post_kernel(int branch, const __half* __restrict__ O, const float* __rest
 __global__ void __launch_bounds__(256)
 branch_prep_all_kernel(const float* __restrict__ X, const double* __restrict__ stats, __half* __restrict__ T1,
                        __half* __restrict__ T1lo, __half* __restrict__ H2, __half* __restrict__ H3,
-                       __half* __restrict__ H4, int B, int Hp, int Wp, int one_wave) {
+                       __half* __restrict__ H4, int B, int Hp, int Wp, int resident) {
     __shared__ float smu[NF], srs[NF];
-    // one wave of CTAs (small inputs): let the next kernel's launch proceed now, so that its CTAs start the moment ours leave
-    // (the register file is full, they cannot take our slots early); a multi-wave grid admits it only as it drains
-    if (one_wave) pdl_trigger();
+    // the CTAs of the last (on small inputs: the only) wave let the next kernel's launch proceed now, so that its CTAs start
+    // the moment ours leave (the register file is full, they cannot take our slots early)
+    pdl_trigger_last_wave(resident);
     pdl_wait();
     const int t = threadIdx.x;
     const int npix = Hp * Wp;
@@ -265,7 +265,6 @@ branch_prep_all_kernel(const float* __restrict__ X, const double* __restrict__ s
         }
         stg256(dst, o[0], o[1]);
     }
-    if (!one_wave) pdl_trigger();
 }
 
 int launch_branch_prep_all(const float* X, const double* stats, __half* T1, __half* T1lo, __half* H2, __half* H3,
@@ -281,7 +280,7 @@ int launch_branch_prep_all(const float* X, const double* stats, __half* T1, __ha
     const long slots = (nchunks < 32L * 4L * sms ? (long)PREP_SMALL_MULT : 8L) * sms;
     const unsigned grid = (unsigned)(nchunks < slots ? nchunks : slots);
     M2T_CUDA(launch_pdl(branch_prep_all_kernel, dim3(grid), dim3(256), 0, s, X, stats, T1, T1lo, H2, H3, H4, g.B, g.Hp, g.Wp,
-                        grid <= 4 * sms ? 1 : 0));
+                        resident_ctas(branch_prep_all_kernel, 256, 0)));
     return M2T_OK;
 }
 

@@ -84,9 +84,31 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     if (prof_active()) prof_mark(s, reinterpret_cast<const void*>(kernel));
     return e;
 }
+// CTAs of `kernel` that are resident on the device at once (occupancy x SMs); cached per kernel
+template <typename K>
+inline int resident_ctas(K kernel, int block, size_t smem) {
+    static int cached = 0;                         // one instance per kernel type and call site pattern (K is the function type)
+    static const void* cached_for = nullptr;
+    const void* key = reinterpret_cast<const void*>(kernel);
+    if (cached_for != key) {
+        int per_sm = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+        cached = per_sm * device_sm_count();
+        cached_for = key;
+    }
+    return cached;
+}
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// Multi-wave grids: the CTAs of the LAST wave let the dependent kernel's launch proceed when they start (all earlier CTAs
+// have left by then, so nothing can take slots this grid still needs); the launch latency of the dependent then overlaps
+// the last wave instead of following it.  `resident` = resident_ctas(kernel, block, smem).
+__device__ __forceinline__ void pdl_trigger_last_wave(int resident) {
+    const long id = (long)blockIdx.x + (long)gridDim.x * ((long)blockIdx.y + (long)gridDim.y * blockIdx.z);
+    const long n = (long)gridDim.x * gridDim.y * gridDim.z;
+    if (n - id <= (long)resident) pdl_trigger();
+}
 
 // 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256).  A thread that owns 32 contiguous, 32-byte-aligned bytes
 // touches its sector once instead of twice: scattered per-pixel epilogues are bound by sector transactions.

@@ -32,7 +32,7 @@ __device__ __forceinline__ uint64_t hd_fma2(uint64_t a, uint64_t b, uint64_t c) 
 
 __global__ void __launch_bounds__(HEAD_THREADS)
 head_conv_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
-                 float* __restrict__ res, double* __restrict__ stats, int B, int H, int W, int Hp, int Wp, int one_wave) {
+                 float* __restrict__ res, double* __restrict__ stats, int B, int H, int W, int Hp, int Wp, int resident) {
     __shared__ float sx[3][HEAD_TH + 2][HEAD_TW + 2];
     __shared__ float red[HEAD_TH][2][NF];
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
@@ -46,7 +46,7 @@ head_conv_kernel(const float* __restrict__ x, const float* __restrict__ w, const
         w23[k] = hd_pack(wv.z, wv.w);
     }
     const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + 4 * cq));
-    if (one_wave) pdl_trigger();     // every CTA is resident: the next kernel's launch may proceed, it finds no free slot before we leave
+    pdl_trigger_last_wave(resident); // the CTAs of the last wave admit the next kernel's launch: it finds no free slot before they leave
     pdl_wait();
 
     const int tiles_x = Wp / HEAD_TW, tiles_y = Hp / HEAD_TH;
@@ -105,15 +105,13 @@ head_conv_kernel(const float* __restrict__ x, const float* __restrict__ w, const
         for (int wv = 0; wv < HEAD_TH; ++wv) tot += (double)red[wv][k][c];
         atomicAdd(&stats[((long)b * NF + c) * 2 + k], tot);
     }
-    if (!one_wave) pdl_trigger();       // multi-wave grid: admit the next kernel only as this one drains
 }
 
 int launch_head(const float* x, const float* w, const float* b, float* res, double* stats, const Geom& g,
                 cudaStream_t s) {
     const int tiles = g.B * (g.Hp / HEAD_TH) * (g.Wp / HEAD_TW);
-    // 128 threads x ~154 registers: three CTAs per SM are resident
     M2T_CUDA(launch_pdl(head_conv_kernel, dim3((unsigned)tiles), dim3(HEAD_THREADS), 0, s, x, w, b, res, stats, g.B, g.H,
-                        g.W, g.Hp, g.Wp, tiles <= 3 * device_sm_count() ? 1 : 0));
+                        g.W, g.Hp, g.Wp, resident_ctas(head_conv_kernel, HEAD_THREADS, 0)));
     return M2T_OK;
 }
 
