@@ -21,4 +21,16 @@ for r in rows[2:]:
     for k in KEYS:
         if k in idx:
             parts.append(f"{k.split('.')[0]}={r[idx[k]]}{units[idx[k]]}")
+    # top stall reasons of the sampled warps (pc sampling, all samples)
+    st = []
+    for h_ in hdr:
+        if h_.startswith("smsp__pcsamp_warps_issue_stalled_") and not h_.endswith("_not_issued"):
+            try:
+                st.append((float(r[idx[h_]].replace(",", "")), h_[len("smsp__pcsamp_warps_issue_stalled_"):]))
+            except ValueError:
+                pass
+    tot = sum(v for v, _ in st)
+    if tot > 0:
+        st.sort(reverse=True)
+        parts.append("stalls: " + ", ".join(f"{n} {100 * v / tot:.0f}%" for v, n in st[:4]))
     print(" | ".join(parts))
